@@ -1,0 +1,276 @@
+#!/usr/bin/env python3
+"""bench.py — AR-CVAE train molecules/s on B200 (BASELINE.json metric), beside the CPU path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload train|sample]
+
+One "step" = one full default-config training step (encoder fwd + BPTT, decoder fwd + bwd, fused loss, two Adam
+updates) on one synthetic SELFIES-shaped batch of B=4096 x T=128 per GPU (BASELINE configs[1]; N>1: data parallel,
+global batch 4096*N, configs[2] at N=8 -> "scaling": "weak").
+  value : molecules/s, inputs already resident in HBM, CUDA events, barrier + synchronize on both sides, max over ranks
+  e2e   : the same step through the public API from pinned HOST buffers: H2D copy of tokens / conditions / eps and a
+          D2H read of the loss inside the timed region
+  roofline : the dominant kernel category, timed with CUDA events on the launch stream in a second, instrumented pass
+  cpu_baseline : the CPU restatement of the reference step (oracle/, torch fp32, all host threads) on a bounded sample
+--impl reference times that CPU restatement alone (MLX is not installable here: "kind": "port").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DIMS = dict(vocab_size=80, embedding_dim=128, hidden_dim=256, latent_dim=128, num_conditions=1, num_layers=2)
+HYPER = dict(beta=0.05, lambda_prop=0.1, lambda_collapse=0.001, free_bits=1.0, lambda_mi=0.01)
+LR = 2e-4
+B_PER_GPU, T = 4096, 128
+CPU_SAMPLE_B = 64
+# algorithmic FLOP of the reference formulation
+FLOP_FWD_PER_MOLECULE = 128 * (1_835_008 + 829_440) + 786_944          # 341,836,288 at T=128
+FLOP_STEP_PER_MOLECULE = 3 * FLOP_FWD_PER_MOLECULE                     # fwd + bwd = 3x
+LOSS_BYTES_PER_MOLECULE = T * 80 * 4 * 2 + T * 4                       # logits read + dlogits write + tokens
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(",") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_step_rate(steps, warmup, B=CPU_SAMPLE_B):
+    """molecules/s of the CPU restatement of the reference step (trainer.py:292-333) on this host's cores."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+    import arcvae_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = O.Config(**DIMS)
+    params = O.init_params(cfg, seed=67, dtype=torch.float32)
+    state = O.adam_init(params)
+    x, cond, eps, tf_mask = O.synthetic_batch(B, T, cfg, seed=67, tf_ratio=0.9)
+    xt, ct, et = torch.as_tensor(x), torch.as_tensor(cond), torch.as_tensor(eps)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        vals, grads, params, state = O.train_step(params, state, xt, ct, cfg.num_layers, et, tf_mask, LR,
+                                                  target_mi=4.85, **HYPER)
+        float(vals["total_loss"])
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(times) / len(times)
+    return B / (ms / 1e3), ms, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = min(args.steps, 8), min(args.warmup, 2)
+    rate, ms, cores = cpu_step_rate(steps, max(1, warmup))
+    sample = f"B={CPU_SAMPLE_B} molecules per step of the B={B_PER_GPU} x T={T} workload (same dims), {steps} timed steps"
+    line = {"impl": "reference", "metric": "AR-CVAE train molecules/s", "value": rate, "unit": "molecules/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": max(1, warmup), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"default AR-CVAE train step, B={B_PER_GPU} x T={T} per GPU (configs[1])",
+                       "cpu_sample": sample},
+            "cpu_baseline": {"value": rate, "unit": "molecules/s", "cores": cores, "kind": "port", "sample": sample,
+                             "note": "MLX is not installable in this image; this is oracle/arcvae_oracle.py, a torch-CPU "
+                                     "fp32 restatement of the reference step"},
+            "e2e": {"value": rate, "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--precision", default=os.environ.get("ARCVAE_PRECISION", "fp32"))
+    ap.add_argument("--batch", type=int, default=B_PER_GPU)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import mlx_vae_b200 as M
+    from mlx_vae_b200.data import synthetic_batch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B = args.batch
+    # every rank gets its own shard of the synthetic global batch; the teacher-forcing coins are global (one per position)
+    x, cond, eps, _ = synthetic_batch(B, T, seed=67 + rank, tf_ratio=0.9)
+    _, _, _, tf_mask = synthetic_batch(8, T, seed=67, tf_ratio=0.9)
+    vae = M.ARCVAE(**DIMS, seed=67, precision=args.precision)
+    trainer = M.ARCVAETrainerWithLoss(vae.encoder, vae.decoder, None, None, learning_rate=LR, batch_size=B,
+                                      lambda_prop=HYPER["lambda_prop"], lambda_collapse=HYPER["lambda_collapse"],
+                                      free_bits=HYPER["free_bits"], lambda_mi=HYPER["lambda_mi"])
+    beta, tf = HYPER["beta"], 0.9
+    dx, dc, de = (torch.as_tensor(a).cuda() for a in (x, cond, eps))
+    hx, hc, he = (torch.as_tensor(a).pin_memory() for a in (x, cond, eps))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        return trainer.train_step(dx, dc, beta, tf, eps=de, tf_mask=tf_mask)
+
+    def step_e2e():
+        gx = hx.cuda(non_blocking=True); gc = hc.cuda(non_blocking=True); ge = he.cuda(non_blocking=True)
+        d = trainer.train_step(gx, gc, beta, tf, eps=ge, tf_mask=tf_mask)
+        return float(d["total_loss"])                                   # D2H read of the step's result
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = M._lib.launch_count()
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) / steps
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), M._lib.launch_count() - l0, out
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms, launches, last = timed(step_resident, args.steps)
+    clocks = sampler.stop() if sampler else None
+    for _ in range(2):
+        step_e2e()
+    ms_e2e, _, loss_val = timed(step_e2e, args.steps)
+
+    # instrumented pass: per-category device time (CUDA events on the launch stream around every launch scope)
+    M._lib.timing_enable(True)
+    M._lib.timing_read()
+    nprof = min(args.steps, 3)
+    for _ in range(nprof):
+        step_resident()
+    cats = M._lib.timing_read()
+    M._lib.timing_enable(False)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    per_step = {k: v[0] / nprof for k, v in cats.items() if v[1] > 0}
+    dom = max(per_step, key=per_step.get) if per_step else None
+    roof = None
+    if dom in ("gemm_f32", "gemm_tc", "recurrence"):
+        # GEMM-shaped work of the step: algorithmic FLOP of the reference formulation over the device
+        # time of every launch of the GEMM-shaped categories
+        t_ms = sum(per_step.get(k, 0.0) for k in ("gemm_f32", "gemm_tc", "recurrence"))
+        flop = FLOP_STEP_PER_MOLECULE * B
+        ach = flop / (t_ms * 1e-3) / 1e12
+        roof = {"kernel": "+".join(k for k in ("gemm_f32", "gemm_tc", "recurrence") if k in per_step),
+                "bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                "frac": ach / pk["bf16_sustained"], "traffic": None, "peak_source": pk["src"] + " (sustained bf16)",
+                "ms_per_step": t_ms, "share_of_step": t_ms / ms,
+                "note": "algorithmic FLOP = 3 x 341,836,288 per molecule (SURVEY 8d); timed in a separate instrumented pass"}
+    elif dom == "loss":
+        t_ms = per_step["loss"]
+        by = LOSS_BYTES_PER_MOLECULE * B
+        ach = by / (t_ms * 1e-3) / 1e9
+        roof = {"kernel": "k_loss_fused", "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
+                "frac": ach / pk["hbm"], "traffic": None, "peak_source": pk["src"]}
+    loss_ms = per_step.get("loss")
+    extra = {"per_category_ms": per_step}
+    if loss_ms:
+        extra["loss_kernel_gbs"] = LOSS_BYTES_PER_MOLECULE * B / (loss_ms * 1e-3) / 1e9
+        extra["loss_kernel_frac_of_hbm_peak"] = extra["loss_kernel_gbs"] / pk["hbm"]
+
+    cpu = None
+    if not args.no_cpu:
+        rate, cms, cores = cpu_step_rate(steps=4, warmup=1)
+        cpu = {"value": rate, "unit": "molecules/s", "cores": cores, "kind": "port",
+               "sample": f"B={CPU_SAMPLE_B} molecules per step of the same workload (T={T}, same dims), 4 timed steps",
+               "ms_per_step": cms,
+               "note": "MLX not installable here; oracle/arcvae_oracle.py torch-CPU fp32 restatement of the reference step"}
+
+    h2d = hx.numel() * 4 + hc.numel() * 4 + he.numel() * 4
+    line = {"metric": "AR-CVAE train molecules/s", "value": B * world / (ms * 1e-3), "unit": "molecules/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"default AR-CVAE (V80 E128 H256 L128 C1 NL2) full train step, B={B} x T={T} per GPU "
+                                   f"(configs[1]); global batch {B * world}",
+                       "parallelism": f"dp{world}", "teacher_forcing": 0.9,
+                       "l2": "no explicit flush: every step streams >6 GB of activations (>> 126 MB L2)"},
+            "e2e": {"value": B * world / (ms_e2e * 1e-3), "unit": "molecules/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
+            "gpu_launches": launches, "gpu_launches_per_step": launches // args.steps, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "final_loss": loss_val, **extra}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,67 @@
+"""complete_vae_loss — drop-in for complete_vae_loss.py of the reference, plus the gradient entry point that
+replaces ``mx.value_and_grad(model_loss_fn, argnums=[0, 1])`` (trainer.py:292)."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+from .losses._fused import fused_loss, make_hyper
+
+
+def _run(encoder, decoder, property_predictor, x, conditions, beta, lambda_prop, lambda_collapse,
+         teacher_forcing_ratio, free_bits, lambda_mi, target_mi, eps, tf_mask, seed, pad_mask, backward, allreduce,
+         return_logits=False, backward_hooks=None):
+    if property_predictor is not None:
+        # the reference would raise TypeError here (complete_vae_loss.py:63-67 vs losses/prop.py:5-11, F10)
+        raise NotImplementedError("property_predictor must be None, as in train.py:186")
+    mu, logvar = encoder(x, conditions)                                                         # :38
+    logits = decoder(None, conditions, target_seq=x, teacher_forcing_ratio=teacher_forcing_ratio,
+                     tf_mask=tf_mask)                                                           # :42
+    hp = make_hyper(beta, lambda_prop, lambda_collapse, free_bits, lambda_mi, target_mi, 4.85, pad_mask)
+    targets = encoder._tokens(x)
+    out = fused_loss(logits, targets, mu, logvar, hp, eps=eps, seed=seed, pad_token=decoder.pad_token,
+                     want_grads=backward, want_z=True, inplace_dlogits=backward and not return_logits,
+                     allreduce=allreduce)                                                       # :39, :45-82
+    d = {k: out.losses[i] for i, k in enumerate(_lib.LOSS_KEYS)}                                # :86-99
+    d.update(mu=mu, logvar=logvar, z=out.z)
+    if return_logits:
+        d["logits"] = logits
+    if backward:
+        decoder.backward(out.dlogits)
+        if backward_hooks is not None:
+            backward_hooks.after_decoder_backward(decoder)
+        encoder.backward(out.dmu, out.dlogvar)
+    return d
+
+
+def complete_vae_loss(encoder, decoder, property_predictor, x: torch.Tensor, conditions: torch.Tensor,
+                      beta: float = 0.4, lambda_prop: float = 0.1, lambda_collapse: float = 0.01,
+                      teacher_forcing_ratio: float = 0.9, free_bits: float = 0.5, lambda_mi: float = 0.0,
+                      target_mi: float = 4.85, *, eps: Optional[torch.Tensor] = None, tf_mask=None, seed: int = 0,
+                      pad_mask: bool = False, return_logits: bool = False) -> dict:
+    """complete_vae_loss.py:7-99.  Returns the reference's 12-key dict; scalars are 0-d CUDA tensors (no host sync).
+
+    Keyword-only extras make the stochastic inputs explicit: ``eps`` (the N(0,1) draw of reparameterize, else
+    Philox(seed) on device), ``tf_mask`` (bool [T], else one ``np.random.rand()`` coin per position like
+    decoder.py:180), ``pad_mask`` (opt-in masked CE; the reference is unmasked)."""
+    return _run(encoder, decoder, property_predictor, x, conditions, beta, lambda_prop, lambda_collapse,
+                teacher_forcing_ratio, free_bits, lambda_mi, target_mi, eps, tf_mask, seed, pad_mask, False, None,
+                return_logits)
+
+
+def loss_and_grad(encoder, decoder, property_predictor, x: torch.Tensor, conditions: torch.Tensor, *,
+                  beta: float = 0.4, lambda_prop: float = 0.1, lambda_collapse: float = 0.01,
+                  teacher_forcing_ratio: float = 0.9, free_bits: float = 0.5, lambda_mi: float = 0.0,
+                  target_mi: float = 4.85, eps: Optional[torch.Tensor] = None, tf_mask=None, seed: int = 0,
+                  pad_mask: bool = False, zero_grad: bool = True, allreduce=None):
+    """``mx.value_and_grad(model_loss_fn, argnums=[0,1])(encoder, decoder, x, conditions)`` (trainer.py:292, :305):
+    returns (loss dict, (enc_grads, dec_grads)) with the gradients as nested dicts keyed like the parameter trees
+    (views of ``encoder.grads`` / ``decoder.grads``; parameters the loss does not reach hold exact zeros)."""
+    if zero_grad:
+        encoder.zero_grad()
+        decoder.zero_grad()
+    d = _run(encoder, decoder, property_predictor, x, conditions, beta, lambda_prop, lambda_collapse,
+             teacher_forcing_ratio, free_bits, lambda_mi, target_mi, eps, tf_mask, seed, pad_mask, True, allreduce)
+    return d, (encoder.gradients(), decoder.gradients())

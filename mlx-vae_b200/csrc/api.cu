@@ -1,0 +1,60 @@
+// api.cu — process-wide plumbing of the C ABI: error string, launch counter, version.
+#include <vector>
+
+#include "common.cuh"
+
+namespace arcvae {
+static thread_local std::string g_error;
+std::atomic<uint64_t> g_launches{0};
+void set_error(const std::string& msg) { g_error = msg; }
+
+// ---- per-category event timing -------------------------------------------------------------------------------
+static bool g_timing = false;
+struct Pair { cudaEvent_t a, b; int cat; };
+static std::vector<Pair> g_pairs;      // recorded
+static std::vector<Pair> g_free;       // recycled
+static int g_open[TIME_NCAT] = {0};
+static Pair g_cur[TIME_NCAT];
+void timing_begin(int cat, cudaStream_t st) {
+  if (!g_timing || g_open[cat]++ > 0) return;
+  Pair p;
+  if (!g_free.empty()) { p = g_free.back(); g_free.pop_back(); }
+  else { cudaEventCreate(&p.a); cudaEventCreate(&p.b); }
+  p.cat = cat;
+  cudaEventRecord(p.a, st);
+  g_cur[cat] = p;
+}
+void timing_end(int cat, cudaStream_t st) {
+  if (!g_timing || --g_open[cat] > 0) return;
+  cudaEventRecord(g_cur[cat].b, st);
+  g_pairs.push_back(g_cur[cat]);
+}
+}  // namespace arcvae
+
+extern "C" int arcvae_timing_enable(int on) {
+  arcvae::g_timing = on != 0;
+  return 0;
+}
+// synchronises the device, returns summed milliseconds and launch-scope count per category, then resets
+extern "C" int arcvae_timing_read(double* ms, int* counts, int ncat) {
+  using namespace arcvae;
+  ARCVAE_CUDA(cudaDeviceSynchronize());
+  for (int i = 0; i < ncat; i++) { ms[i] = 0.0; counts[i] = 0; }
+  for (auto& p : g_pairs) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, p.a, p.b);
+    if (p.cat < ncat) { ms[p.cat] += t; counts[p.cat]++; }
+    g_free.push_back(p);
+  }
+  g_pairs.clear();
+  return 0;
+}
+
+extern "C" const char* arcvae_last_error(void) { return arcvae::g_error.c_str(); }
+extern "C" int arcvae_abi_version(void) { return ARCVAE_ABI_VERSION; }
+extern "C" uint64_t arcvae_launch_count(void) { return arcvae::g_launches.load(); }
+extern "C" int arcvae_zero(void* ptr, size_t bytes, void* stream) {
+  if (bytes == 0) return 0;
+  ARCVAE_CUDA(cudaMemsetAsync(ptr, 0, bytes, (cudaStream_t)stream));
+  return 0;
+}

@@ -1,0 +1,323 @@
+// decoder.cu — MLXAutoregressiveDecoder.__call__ (models/decoder.py:113-190), its reverse pass, and the sampler
+// loop of MLXAutoregressiveDecoderSampling.generate_with_temperature (models/decoder_sampling.py:48-128).
+//
+// Reference semantics that shape the design:
+//   * every position calls the LSTM layers on a length-1 sequence WITHOUT state, so
+//       logits[:,t] = fc_out(cell(cell([Emb[tok_{t-1}] ; cond] Wx0^T + b0) Wx1^T + b1)),  cell(a) = s(a_o)*tanh(s(a_i)*tanh(a_g))
+//     (forget gate, Wh, z, z_to_hidden, condition_to_hidden never reach the output);
+//   * the token fed at position t is x[:,t-1] when the host coin of position t-1 came up "teacher forcing",
+//     else argmax(logits[:,t-1]) — one coin per position for the whole batch.
+// So positions whose input is known are time-parallel.  Positions are grouped in LEVELS (level 0: input known;
+// level k: input is the greedy output of a level k-1 position); each level is one batched pass over the rows of
+// its timesteps (time-major rows r = t*B + b, reached through a RowMap).
+//   layer 0  : gather of table = Emb @ Wx0[:, :E]^T + b0 (rows i,g,o only) + cond (x) Wx0[:, E:]  — no GEMM needed
+//   layer l>0: GEMM [rows,H] x [H,3H] on the compacted (i,g,o) weight rows
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace arcvae {
+
+struct DecPrep {
+  float* Wxc[ARCVAE_MAX_LAYERS];  // [3H, D_l]
+  float* bc[ARCVAE_MAX_LAYERS];   // [3H]
+  float* table;                   // [V,3H]
+  float* wc;                      // [3H,C]
+};
+
+static void dec_prep_layout(const arcvae_dims& d, Arena& a, DecPrep* p) {
+  for (int l = 0; l < d.NL; l++) {
+    int D = (l == 0) ? d.E + d.C : d.H;
+    p->Wxc[l] = a.take<float>((size_t)3 * d.H * D);
+    p->bc[l] = a.take<float>((size_t)3 * d.H);
+  }
+  p->table = a.take<float>((size_t)d.V * 3 * d.H);
+  p->wc = a.take<float>((size_t)3 * d.H * d.C);
+}
+
+static int dec_prepare(const arcvae_dims& d, const arcvae_decoder_params* p, const DecPrep& pr, cudaStream_t st) {
+  RowMap id{nullptr, 1};
+  const int H = d.H, H3 = 3 * d.H;
+  for (int l = 0; l < d.NL; l++) {
+    int D = (l == 0) ? d.E + d.C : H;
+    ARCVAE_TRY(compact_gates(p->Wx[l], H, D, pr.Wxc[l], st));
+    ARCVAE_TRY(compact_gates(p->bias[l], H, 1, pr.bc[l], st));
+  }
+  ARCVAE_TRY(gemm_f32(0, 1, d.V, H3, d.E, p->embedding, d.E, pr.Wxc[0], d.E + d.C, pr.table, H3, pr.bc[0], false, id, 1, st));
+  ARCVAE_CUDA(cudaMemcpy2DAsync(pr.wc, (size_t)d.C * sizeof(float), pr.Wxc[0] + d.E, (size_t)(d.E + d.C) * sizeof(float),
+                                (size_t)d.C * sizeof(float), H3, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+struct DecTape {
+  DecPrep prep;
+  int32_t* in_tok;                   // [T,B]
+  float* hd[ARCVAE_MAX_LAYERS];      // [R,H]
+  float* G[ARCVAE_MAX_LAYERS];       // [R,3H], l >= 1
+  int* tlists;                       // [2T] level lists + feedback lists
+  uint8_t* mask;                     // [T]
+};
+
+static size_t dec_tape_layout(const arcvae_dims& d, int B, int T, void* base, size_t cap, DecTape* t) {
+  Arena a(base, cap);
+  DecTape tt;
+  size_t R = (size_t)T * B;
+  dec_prep_layout(d, a, &tt.prep);
+  tt.in_tok = a.take<int32_t>(R);
+  for (int l = 0; l < d.NL; l++) {
+    tt.hd[l] = a.take<float>(R * d.H);
+    tt.G[l] = (l >= 1) ? a.take<float>(R * 3 * d.H) : nullptr;
+  }
+  tt.tlists = a.take<int>((size_t)2 * T + 2);
+  tt.mask = a.take<uint8_t>((size_t)T + 16);
+  if (t) *t = tt;
+  return align_up(a.off, 256);
+}
+
+struct DecScratch {
+  float* dh[2];                       // [R,H]
+  float* dG0;                         // [R,3H]
+  float* dtable;                      // [V,3H]
+  float* dWxc[ARCVAE_MAX_LAYERS];     // compact weight grads
+  float* dbc[ARCVAE_MAX_LAYERS];
+  float* dwc;                         // [3H,C]
+};
+
+static size_t dec_scratch_layout(const arcvae_dims& d, int B, int T, void* base, size_t cap, DecScratch* s) {
+  Arena a(base, cap);
+  DecScratch ss;
+  size_t R = (size_t)T * B;
+  ss.dh[0] = a.take<float>(R * d.H);
+  ss.dh[1] = a.take<float>(R * d.H);
+  ss.dG0 = a.take<float>(R * 3 * d.H);
+  ss.dtable = a.take<float>((size_t)d.V * 3 * d.H);
+  for (int l = 0; l < d.NL; l++) {
+    int D = (l == 0) ? d.E + d.C : d.H;
+    ss.dWxc[l] = a.take<float>((size_t)3 * d.H * D);
+    ss.dbc[l] = a.take<float>((size_t)3 * d.H);
+  }
+  ss.dwc = a.take<float>((size_t)3 * d.H * d.C);
+  if (s) *s = ss;
+  return align_up(a.off, 256);
+}
+
+// in_tok[t,b] = 0 for t == 0; x[b,t-1] where the coin of t-1 is teacher forcing; 0 placeholder otherwise
+__global__ void k_init_dec_inputs(const int32_t* __restrict__ target, const uint8_t* __restrict__ mask, int B, int T,
+                                  int32_t* __restrict__ in_tok) {
+  long total = (long)T * B;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    int t = (int)(i / B), b = (int)(i - (long)t * B);
+    int v = 0;
+    if (t > 0 && target != nullptr && mask[t - 1]) v = target[(long)b * T + (t - 1)];
+    in_tok[i] = v;
+  }
+}
+
+// one batched pass of the decoder stack over the rows selected by `rm`
+static int dec_stack_forward(const arcvae_dims& d, const arcvae_decoder_params* p, const DecPrep& pr, const float* cond,
+                             const int32_t* in_tok, int B, int nrows, RowMap rm, float* const* hd, float* const* G,
+                             float* logits, cudaStream_t st) {
+  const int H = d.H, H3 = 3 * d.H;
+  ARCVAE_TRY(dec_cell0_fwd(pr.table, pr.wc, in_tok, cond, B, d.C, H, nrows, rm, hd[0], st));
+  for (int l = 1; l < d.NL; l++) {
+    ARCVAE_TRY(gemm_f32(0, 1, nrows, H3, H, hd[l - 1], H, pr.Wxc[l], H, G[l], H3, pr.bc[l], false, rm, 1, st));
+    ARCVAE_TRY(dec_cell_fwd(G[l], hd[l], H, nrows, rm, st));
+  }
+  ARCVAE_TRY(gemm_f32(0, 1, nrows, d.V, H, hd[d.NL - 1], H, p->fc_out_w, H, logits, d.V, p->fc_out_b, false, rm, 1, st));
+  return 0;
+}
+
+static int check_dims_dec(const arcvae_dims* d) {
+  ARCVAE_REQUIRE(d != nullptr, "dims");
+  ARCVAE_REQUIRE(d->V > 0 && d->E > 0 && d->H > 0 && d->C > 0, "positive dims");
+  ARCVAE_REQUIRE(d->NL >= 1 && d->NL <= ARCVAE_MAX_LAYERS, "num_layers in [1, 8]");
+  return 0;
+}
+
+}  // namespace arcvae
+
+using namespace arcvae;
+
+extern "C" size_t arcvae_decoder_tape_bytes(const arcvae_dims* d, int B, int T) {
+  return d ? dec_tape_layout(*d, B, T, nullptr, 0, nullptr) : 0;
+}
+extern "C" size_t arcvae_decoder_scratch_bytes(const arcvae_dims* d, int B, int T) {
+  return d ? dec_scratch_layout(*d, B, T, nullptr, 0, nullptr) : 0;
+}
+
+extern "C" int arcvae_decoder_forward(const arcvae_dims* d, const arcvae_decoder_params* p, const float* cond,
+                                      const int32_t* target, const uint8_t* tf_mask_host, int B, int T,
+                                      float* logits_tm, int32_t* dec_inputs_tm, void* tape, size_t tape_bytes,
+                                      int precision, void* stream) {
+  ARCVAE_TRY(check_dims_dec(d));
+  ARCVAE_REQUIRE(B > 0 && T > 0, "empty batch / sequence");
+  ARCVAE_REQUIRE(precision == ARCVAE_PREC_FP32, "decoder: only ARCVAE_PREC_FP32 is built in this version");
+  ARCVAE_REQUIRE(logits_tm != nullptr, "logits output");
+  cudaStream_t st = (cudaStream_t)stream;
+  DecTape tp;
+  size_t need = dec_tape_layout(*d, B, T, tape, tape_bytes, &tp);
+  ARCVAE_REQUIRE(tape != nullptr && need <= tape_bytes, "decoder tape too small");
+
+  // host-side schedule: coin[t] (decoder.py:180), levels, per-level timestep lists and feedback lists
+  std::vector<uint8_t> coin(T, 0);
+  for (int t = 0; t < T; t++) coin[t] = (target != nullptr && tf_mask_host != nullptr && tf_mask_host[t]) ? 1 : 0;
+  std::vector<int> level(T, 0);
+  int maxlevel = 0;
+  for (int t = 1; t < T; t++) {
+    level[t] = coin[t - 1] ? 0 : level[t - 1] + 1;
+    if (level[t] > maxlevel) maxlevel = level[t];
+  }
+  std::vector<int> lists;            // concatenated: per level [timesteps..., feedback timesteps...]
+  std::vector<int> off_t(maxlevel + 2), n_t(maxlevel + 1), off_f(maxlevel + 1), n_f(maxlevel + 1);
+  lists.reserve(2 * T + 2);
+  for (int lv = 0; lv <= maxlevel; lv++) {
+    off_t[lv] = (int)lists.size();
+    for (int t = 0; t < T; t++)
+      if (level[t] == lv) lists.push_back(t);
+    n_t[lv] = (int)lists.size() - off_t[lv];
+    off_f[lv] = (int)lists.size();
+    for (int t = 0; t < T; t++)
+      if (level[t] == lv && !coin[t] && t + 1 < T) lists.push_back(t);
+    n_f[lv] = (int)lists.size() - off_f[lv];
+  }
+  ARCVAE_REQUIRE((int)lists.size() <= 2 * T + 2, "internal: list overflow");
+  ARCVAE_CUDA(cudaMemcpyAsync(tp.tlists, lists.data(), lists.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  ARCVAE_CUDA(cudaMemcpyAsync(tp.mask, coin.data(), (size_t)T, cudaMemcpyHostToDevice, st));
+  // pageable-source async copies are staged before returning, but be explicit: the vectors die with this frame
+  ARCVAE_CUDA(cudaStreamSynchronize(st));
+
+  ARCVAE_TRY(dec_prepare(*d, p, tp.prep, st));
+  {
+    long total = (long)T * B;
+    int grid = (int)((total + 255) / 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    k_init_dec_inputs<<<grid, 256, 0, st>>>(target, tp.mask, B, T, tp.in_tok);
+    ARCVAE_LAUNCHED();
+  }
+  for (int lv = 0; lv <= maxlevel; lv++) {
+    RowMap rm{tp.tlists + off_t[lv], B};
+    int nrows = n_t[lv] * B;
+    ARCVAE_TRY(dec_stack_forward(*d, p, tp.prep, cond, tp.in_tok, B, nrows, rm, tp.hd, tp.G, logits_tm, st));
+    ARCVAE_TRY(argmax_feedback(logits_tm, tp.tlists + off_f[lv], n_f[lv], B, d->V, tp.in_tok, st));
+  }
+  if (dec_inputs_tm != nullptr)
+    ARCVAE_CUDA(cudaMemcpyAsync(dec_inputs_tm, tp.in_tok, (size_t)T * B * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+extern "C" int arcvae_decoder_backward(const arcvae_dims* d, const arcvae_decoder_params* p, const float* cond, int B,
+                                       int T, float* dlogits_tm, void* tape, size_t tape_bytes,
+                                       const arcvae_decoder_params* g, void* scratch, size_t scratch_bytes,
+                                       int precision, void* stream) {
+  ARCVAE_TRY(check_dims_dec(d));
+  ARCVAE_REQUIRE(precision == ARCVAE_PREC_FP32, "decoder: only ARCVAE_PREC_FP32 is built in this version");
+  ARCVAE_REQUIRE(g != nullptr && dlogits_tm != nullptr, "grad pointers");
+  cudaStream_t st = (cudaStream_t)stream;
+  DecTape tp;
+  size_t need = dec_tape_layout(*d, B, T, tape, tape_bytes, &tp);
+  ARCVAE_REQUIRE(tape != nullptr && need <= tape_bytes, "decoder tape too small");
+  DecScratch sc;
+  size_t need_s = dec_scratch_layout(*d, B, T, scratch, scratch_bytes, &sc);
+  ARCVAE_REQUIRE(scratch != nullptr && need_s <= scratch_bytes, "decoder scratch too small");
+  const int H = d->H, H3 = 3 * d->H, V = d->V, E = d->E, C = d->C;
+  const long R = (long)T * B;
+  RowMap id{nullptr, 1};
+  const int top = d->NL - 1;
+
+  // fc_out: logits = h_top @ Wout^T + b
+  ARCVAE_TRY(gemm_f32(1, 0, V, H, (int)R, dlogits_tm, V, tp.hd[top], H, g->fc_out_w, H, nullptr, true, id, pick_splitk(V, H, (int)R), st));
+  ARCVAE_TRY(colsum(dlogits_tm, R, V, V, g->fc_out_b, st));
+  float* dh = sc.dh[0];
+  float* dh_next = sc.dh[1];
+  ARCVAE_TRY(gemm_f32(0, 0, (int)R, H, V, dlogits_tm, V, p->fc_out_w, H, dh, H, nullptr, false, id, 1, st));
+
+  for (int l = top; l >= 1; l--) {
+    ARCVAE_TRY(dec_cell_bwd(tp.G[l], dh, H, R, st));  // G[l] <- dG
+    ARCVAE_CUDA(cudaMemsetAsync(sc.dWxc[l], 0, (size_t)H3 * H * sizeof(float), st));
+    ARCVAE_CUDA(cudaMemsetAsync(sc.dbc[l], 0, (size_t)H3 * sizeof(float), st));
+    ARCVAE_TRY(gemm_f32(1, 0, H3, H, (int)R, tp.G[l], H3, tp.hd[l - 1], H, sc.dWxc[l], H, nullptr, true, id, pick_splitk(H3, H, (int)R), st));
+    ARCVAE_TRY(colsum(tp.G[l], R, H3, H3, sc.dbc[l], st));
+    ARCVAE_TRY(gemm_f32(0, 0, (int)R, H, H3, tp.G[l], H3, tp.prep.Wxc[l], H, dh_next, H, nullptr, false, id, 1, st));
+    ARCVAE_TRY(expand_gates_add(sc.dWxc[l], H, H, g->Wx[l], st));
+    ARCVAE_TRY(expand_gates_add(sc.dbc[l], H, 1, g->bias[l], st));
+    float* tmp = dh; dh = dh_next; dh_next = tmp;
+  }
+  // layer 0: gates recomputed from the table; a0 = table[tok] + cond @ wc^T
+  ARCVAE_TRY(dec_cell0_bwd(tp.prep.table, tp.prep.wc, tp.in_tok, cond, B, C, H, R, dh, sc.dG0, st));
+  ARCVAE_CUDA(cudaMemsetAsync(sc.dtable, 0, (size_t)V * H3 * sizeof(float), st));
+  ARCVAE_CUDA(cudaMemsetAsync(sc.dwc, 0, (size_t)H3 * C * sizeof(float), st));
+  ARCVAE_CUDA(cudaMemsetAsync(sc.dWxc[0], 0, (size_t)H3 * (E + C) * sizeof(float), st));
+  ARCVAE_CUDA(cudaMemsetAsync(sc.dbc[0], 0, (size_t)H3 * sizeof(float), st));
+  ARCVAE_TRY(scatter_rows_by_token(sc.dG0, tp.in_tok, R, H3, V, sc.dtable, cond, B, C, sc.dwc, st));
+  ARCVAE_TRY(colsum(sc.dtable, V, H3, H3, sc.dbc[0], st));
+  // table = Emb @ Wx0c[:, :E]^T + b0c
+  ARCVAE_TRY(gemm_f32(0, 0, V, E, H3, sc.dtable, H3, tp.prep.Wxc[0], E + C, g->embedding, E, nullptr, true, id, 1, st));
+  ARCVAE_TRY(gemm_f32(1, 0, H3, E, V, sc.dtable, H3, p->embedding, E, sc.dWxc[0], E + C, nullptr, true, id, 1, st));
+  ARCVAE_TRY(add_strided(sc.dwc, C, sc.dWxc[0] + E, E + C, H3, C, st));
+  ARCVAE_TRY(expand_gates_add(sc.dWxc[0], H, E + C, g->Wx[0], st));
+  ARCVAE_TRY(expand_gates_add(sc.dbc[0], H, 1, g->bias[0], st));
+  return 0;
+}
+
+// ---- sampler ---------------------------------------------------------------------------------------
+namespace arcvae {
+struct SamplerWs {
+  DecPrep prep;
+  int32_t* cur;      // [B]
+  int32_t* ended;    // [B]
+  int32_t* ended_count;
+  float* hd[ARCVAE_MAX_LAYERS];  // [B,H]
+  float* G[ARCVAE_MAX_LAYERS];   // [B,3H]
+  float* logits;     // [B,V]
+};
+static size_t sampler_layout(const arcvae_dims& d, int B, void* base, size_t cap, SamplerWs* w) {
+  Arena a(base, cap);
+  SamplerWs ww;
+  dec_prep_layout(d, a, &ww.prep);
+  ww.cur = a.take<int32_t>(B);
+  ww.ended = a.take<int32_t>(B);
+  ww.ended_count = a.take<int32_t>(4);
+  for (int l = 0; l < d.NL; l++) {
+    ww.hd[l] = a.take<float>((size_t)B * d.H);
+    ww.G[l] = (l >= 1) ? a.take<float>((size_t)B * 3 * d.H) : nullptr;
+  }
+  ww.logits = a.take<float>((size_t)B * d.V);
+  if (w) *w = ww;
+  return align_up(a.off, 256);
+}
+}  // namespace arcvae
+
+extern "C" size_t arcvae_sampler_workspace_bytes(const arcvae_dims* d, int B, int max_length) {
+  (void)max_length;
+  return d ? sampler_layout(*d, B, nullptr, 0, nullptr) : 0;
+}
+
+extern "C" int arcvae_sample(const arcvae_dims* d, const arcvae_decoder_params* p, const float* cond, int B,
+                             int max_length, float temperature, int early_stopping, int multinomial, uint64_t seed,
+                             int32_t* tokens, int32_t* t_stop, void* workspace, size_t workspace_bytes, int precision,
+                             void* stream) {
+  ARCVAE_TRY(check_dims_dec(d));
+  ARCVAE_REQUIRE(B > 0 && max_length >= 0, "empty batch");
+  ARCVAE_REQUIRE(temperature > 0.f, "temperature must be > 0");
+  ARCVAE_REQUIRE(precision == ARCVAE_PREC_FP32, "sampler: only ARCVAE_PREC_FP32 is built in this version");
+  ARCVAE_REQUIRE(tokens != nullptr && t_stop != nullptr, "outputs");
+  cudaStream_t st = (cudaStream_t)stream;
+  SamplerWs ws;
+  size_t need = sampler_layout(*d, B, workspace, workspace_bytes, &ws);
+  ARCVAE_REQUIRE(workspace != nullptr && need <= workspace_bytes, "sampler workspace too small");
+  ARCVAE_TRY(dec_prepare(*d, p, ws.prep, st));
+  ARCVAE_CUDA(cudaMemsetAsync(ws.cur, 0, (size_t)B * sizeof(int32_t), st));      // start token 0 (decoder_sampling.py:78)
+  ARCVAE_CUDA(cudaMemsetAsync(ws.ended, 0, (size_t)B * sizeof(int32_t), st));
+  ARCVAE_CUDA(cudaMemsetAsync(ws.ended_count, 0, 4 * sizeof(int32_t), st));
+  ARCVAE_TRY(set_int(t_stop, max_length, st));
+  RowMap id{nullptr, 1};
+  for (int t = 0; t < max_length; t++) {
+    // the reference checks `early_stopping and all(has_ended)` BEFORE each step (:87-88); the device records the first
+    // such step in *t_stop and the host slices; later columns are scratch
+    if (early_stopping && t > 0) ARCVAE_TRY(sampler_check_stop(ws.ended_count, B, t, t_stop, st));
+    ARCVAE_TRY(dec_stack_forward(*d, p, ws.prep, cond, ws.cur, B, B, id, ws.hd, ws.G, ws.logits, st));
+    ARCVAE_TRY(select_token(ws.logits, B, d->V, temperature, multinomial, seed, t, max_length, d->end_token, tokens,
+                            ws.cur, ws.ended, ws.ended_count, st));
+  }
+  return 0;
+}

@@ -1,0 +1,229 @@
+// encoder.cu — MLXEncoder.__call__ (models/encoder.py:76-132) forward and its reverse pass (BPTT).
+//
+// Internal layout is TIME-MAJOR: row r = t*B + b, so the rows of one timestep are contiguous.
+//   layer 0 input projection  = gather of table0 = Emb @ Wx0^T + b0  ([V,4H]; V=80 rows make the product a table)
+//   layer l>0 input projection = H_{l-1} @ Wx_l^T + b_l               (time-parallel GEMM over all T*B rows)
+//   recurrence                 = per step: gates_t += h_{t-1} @ Wh^T, LSTM cell (MLX nn.LSTM semantics: zero initial
+//                                state, gate order i,f,g,o, c_0 = i*g)
+//   head                       = [h_T ; Linear(cond)] -> fc_mu / fc_logvar(_hidden) -> tanh bounds
+// precision == ARCVAE_PREC_FP32 runs every contraction as fp32 FFMA tiles (gemm_f32.cu).
+#include "kernels.cuh"
+
+namespace arcvae {
+
+struct EncTape {
+  int32_t* xT;       // [T,B]
+  float* table0;     // [V,4H]
+  float* gates[ARCVAE_MAX_LAYERS];  // [T*B,4H]  activated gates after forward, dA after backward
+  float* c[ARCVAE_MAX_LAYERS];      // [T*B,H]
+  float* h[ARCVAE_MAX_LAYERS];      // [T*B,H]
+  float* u;          // [B,2H]
+  float* lvh;        // [B,2H]  tanh(fc_logvar_hidden(u))
+  float* mu_raw;     // [B,L]
+  float* lv_raw;     // [B,L]
+  float* mu;         // [B,L]
+  float* logvar;     // [B,L]
+};
+
+static size_t enc_tape_layout(const arcvae_dims& d, int B, int T, void* base, size_t cap, EncTape* t) {
+  Arena a(base, cap);
+  size_t R = (size_t)T * B;
+  EncTape tt;
+  tt.xT = a.take<int32_t>(R);
+  tt.table0 = a.take<float>((size_t)d.V * 4 * d.H);
+  for (int l = 0; l < d.NL; l++) {
+    tt.gates[l] = a.take<float>(R * 4 * d.H);
+    tt.c[l] = a.take<float>(R * d.H);
+    tt.h[l] = a.take<float>(R * d.H);
+  }
+  tt.u = a.take<float>((size_t)B * 2 * d.H);
+  tt.lvh = a.take<float>((size_t)B * 2 * d.H);
+  tt.mu_raw = a.take<float>((size_t)B * d.L);
+  tt.lv_raw = a.take<float>((size_t)B * d.L);
+  tt.mu = a.take<float>((size_t)B * d.L);
+  tt.logvar = a.take<float>((size_t)B * d.L);
+  if (t) *t = tt;
+  return align_up(a.off, 256);
+}
+
+struct EncScratch {
+  float* dmu_raw;   // [B,L]
+  float* dlv_raw;   // [B,L]
+  float* dlvh;      // [B,2H]
+  float* du;        // [B,2H]
+  float* dX;        // [T*B,H]  gradient w.r.t. a layer's input sequence (from the layer above)
+  float* dh_rec[2]; // [B,H]
+  float* dc;        // [B,H]
+  float* dtable0;   // [V,4H]
+};
+
+static size_t enc_scratch_layout(const arcvae_dims& d, int B, int T, void* base, size_t cap, EncScratch* s) {
+  Arena a(base, cap);
+  EncScratch ss;
+  ss.dmu_raw = a.take<float>((size_t)B * d.L);
+  ss.dlv_raw = a.take<float>((size_t)B * d.L);
+  ss.dlvh = a.take<float>((size_t)B * 2 * d.H);
+  ss.du = a.take<float>((size_t)B * 2 * d.H);
+  ss.dX = a.take<float>(d.NL > 1 ? (size_t)T * B * d.H : 1);
+  ss.dh_rec[0] = a.take<float>((size_t)B * d.H);
+  ss.dh_rec[1] = a.take<float>((size_t)B * d.H);
+  ss.dc = a.take<float>((size_t)B * d.H);
+  ss.dtable0 = a.take<float>((size_t)d.V * 4 * d.H);
+  if (s) *s = ss;
+  return align_up(a.off, 256);
+}
+
+static int check_dims(const arcvae_dims* d) {
+  ARCVAE_REQUIRE(d != nullptr, "dims");
+  ARCVAE_REQUIRE(d->V > 0 && d->E > 0 && d->H > 0 && d->L > 0 && d->C > 0, "positive dims");
+  ARCVAE_REQUIRE(d->NL >= 1 && d->NL <= ARCVAE_MAX_LAYERS, "num_layers in [1, 8]");
+  return 0;
+}
+
+}  // namespace arcvae
+
+using namespace arcvae;
+
+extern "C" size_t arcvae_encoder_tape_bytes(const arcvae_dims* d, int B, int T) {
+  if (!d) return 0;
+  return enc_tape_layout(*d, B, T, nullptr, 0, nullptr);
+}
+extern "C" size_t arcvae_encoder_scratch_bytes(const arcvae_dims* d, int B, int T) {
+  if (!d) return 0;
+  return enc_scratch_layout(*d, B, T, nullptr, 0, nullptr);
+}
+
+extern "C" int arcvae_encoder_forward(const arcvae_dims* d, const arcvae_encoder_params* p, const int32_t* x,
+                                      const float* cond, int B, int T, float* mu, float* logvar, void* tape,
+                                      size_t tape_bytes, int precision, void* stream) {
+  ARCVAE_TRY(check_dims(d));
+  ARCVAE_REQUIRE(B > 0 && T > 0, "empty batch / sequence");
+  ARCVAE_REQUIRE(precision == ARCVAE_PREC_FP32, "encoder: only ARCVAE_PREC_FP32 is built in this version");
+  cudaStream_t st = (cudaStream_t)stream;
+  EncTape tp;
+  size_t need = enc_tape_layout(*d, B, T, tape, tape_bytes, &tp);
+  ARCVAE_REQUIRE(tape != nullptr && need <= tape_bytes, "encoder tape too small");
+  const int H = d->H, G4 = 4 * d->H;
+  const long R = (long)T * B;
+  RowMap id{nullptr, 1};
+
+  ARCVAE_TRY(transpose_tokens(x, B, T, tp.xT, st));
+  // table0[v,:] = Emb[v,:] @ Wx0^T + b0   (encoder.py:93 gather + nn.LSTM's addmm folded: rows are tokens)
+  ARCVAE_TRY(gemm_f32(0, 1, d->V, G4, d->E, p->embedding, d->E, p->Wx[0], d->E, tp.table0, G4, p->bias[0], false, id, 1, st));
+  for (int l = 0; l < d->NL; l++) {
+    if (l == 0) {
+      ARCVAE_TRY(gather_rows(tp.table0, tp.xT, (int)R, G4, tp.gates[0], st));
+    } else {
+      ARCVAE_TRY(gemm_f32(0, 1, (int)R, G4, H, tp.h[l - 1], H, p->Wx[l], H, tp.gates[l], G4, p->bias[l], false, id, 1, st));
+    }
+    for (int t = 0; t < T; t++) {
+      float* g_t = tp.gates[l] + (long)t * B * G4;
+      float* c_t = tp.c[l] + (long)t * B * H;
+      float* h_t = tp.h[l] + (long)t * B * H;
+      if (t > 0) {
+        // gates_t += h_{t-1} @ Wh^T   (nn.LSTM: `ifgo = ifgo + hidden @ Wh.T` once hidden is not None)
+        ARCVAE_TRY(gemm_f32(0, 1, B, G4, H, h_t - (long)B * H, H, p->Wh[l], H, g_t, G4, nullptr, true, id, 1, st));
+      }
+      ARCVAE_TRY(lstm_cell_fwd(g_t, t > 0 ? c_t - (long)B * H : nullptr, c_t, h_t, B, H, st));
+    }
+  }
+  // head (encoder.py:106-130)
+  const float* h_last = tp.h[d->NL - 1] + (long)(T - 1) * B * H;
+  ARCVAE_TRY(head_build_u(h_last, cond, p->condition_fc_w, p->condition_fc_b, B, H, d->C, tp.u, st));
+  ARCVAE_TRY(gemm_f32(0, 1, B, d->L, 2 * H, tp.u, 2 * H, p->fc_mu_w, 2 * H, tp.mu_raw, d->L, p->fc_mu_b, false, id, 1, st));
+  ARCVAE_TRY(gemm_f32(0, 1, B, 2 * H, 2 * H, tp.u, 2 * H, p->fc_logvar_hidden_w, 2 * H, tp.lvh, 2 * H, p->fc_logvar_hidden_b, false, id, 1, st));
+  ARCVAE_TRY(tanh_inplace(tp.lvh, (long)B * 2 * H, st));
+  ARCVAE_TRY(gemm_f32(0, 1, B, d->L, 2 * H, tp.lvh, 2 * H, p->fc_logvar_w, 2 * H, tp.lv_raw, d->L, p->fc_logvar_b, false, id, 1, st));
+  ARCVAE_TRY(head_bound(tp.mu_raw, tp.lv_raw, (long)B * d->L, tp.mu, tp.logvar, st));
+  if (mu) ARCVAE_CUDA(cudaMemcpyAsync(mu, tp.mu, (size_t)B * d->L * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (logvar) ARCVAE_CUDA(cudaMemcpyAsync(logvar, tp.logvar, (size_t)B * d->L * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+extern "C" int arcvae_encoder_backward(const arcvae_dims* d, const arcvae_encoder_params* p, const float* cond, int B,
+                                       int T, const float* dmu, const float* dlogvar, void* tape, size_t tape_bytes,
+                                       const arcvae_encoder_params* g, void* scratch, size_t scratch_bytes,
+                                       int precision, void* stream) {
+  ARCVAE_TRY(check_dims(d));
+  ARCVAE_REQUIRE(precision == ARCVAE_PREC_FP32, "encoder: only ARCVAE_PREC_FP32 is built in this version");
+  ARCVAE_REQUIRE(g != nullptr && dmu != nullptr && dlogvar != nullptr, "grad pointers");
+  cudaStream_t st = (cudaStream_t)stream;
+  EncTape tp;
+  size_t need = enc_tape_layout(*d, B, T, tape, tape_bytes, &tp);
+  ARCVAE_REQUIRE(tape != nullptr && need <= tape_bytes, "encoder tape too small");
+  EncScratch sc;
+  size_t need_s = enc_scratch_layout(*d, B, T, scratch, scratch_bytes, &sc);
+  ARCVAE_REQUIRE(scratch != nullptr && need_s <= scratch_bytes, "encoder scratch too small");
+  const int H = d->H, G4 = 4 * d->H, L = d->L, H2 = 2 * d->H;
+  const long R = (long)T * B;
+  RowMap id{nullptr, 1};
+
+  // ---- head backward
+  ARCVAE_TRY(head_bound_bwd(tp.mu, tp.logvar, dmu, dlogvar, (long)B * L, sc.dmu_raw, sc.dlv_raw, st));
+  // fc_logvar: lv_raw = lvh @ Wlv^T + b
+  ARCVAE_TRY(gemm_f32(1, 0, L, H2, B, sc.dlv_raw, L, tp.lvh, H2, g->fc_logvar_w, H2, nullptr, true, id, pick_splitk(L, H2, B), st));
+  ARCVAE_TRY(colsum(sc.dlv_raw, B, L, L, g->fc_logvar_b, st));
+  ARCVAE_TRY(gemm_f32(0, 0, B, H2, L, sc.dlv_raw, L, p->fc_logvar_w, H2, sc.dlvh, H2, nullptr, false, id, 1, st));
+  ARCVAE_TRY(tanh_bwd_inplace(sc.dlvh, tp.lvh, (long)B * H2, st));
+  // fc_logvar_hidden: pre = u @ Wlh^T + b
+  ARCVAE_TRY(gemm_f32(1, 0, H2, H2, B, sc.dlvh, H2, tp.u, H2, g->fc_logvar_hidden_w, H2, nullptr, true, id, pick_splitk(H2, H2, B), st));
+  ARCVAE_TRY(colsum(sc.dlvh, B, H2, H2, g->fc_logvar_hidden_b, st));
+  ARCVAE_TRY(gemm_f32(0, 0, B, H2, H2, sc.dlvh, H2, p->fc_logvar_hidden_w, H2, sc.du, H2, nullptr, false, id, 1, st));
+  // fc_mu
+  ARCVAE_TRY(gemm_f32(1, 0, L, H2, B, sc.dmu_raw, L, tp.u, H2, g->fc_mu_w, H2, nullptr, true, id, pick_splitk(L, H2, B), st));
+  ARCVAE_TRY(colsum(sc.dmu_raw, B, L, L, g->fc_mu_b, st));
+  ARCVAE_TRY(gemm_f32(0, 0, B, H2, L, sc.dmu_raw, L, p->fc_mu_w, H2, sc.du, H2, nullptr, true, id, 1, st));
+  // condition_fc: cproj = cond @ Wc^T + bc ; d cproj = du[:, H:2H]
+  ARCVAE_TRY(gemm_f32(1, 0, H, d->C, B, sc.du + H, H2, cond, d->C, g->condition_fc_w, d->C, nullptr, true, id, pick_splitk(H, d->C, B), st));
+  ARCVAE_TRY(colsum(sc.du + H, B, H, H2, g->condition_fc_b, st));
+
+  // ---- BPTT, top layer first
+  for (int l = d->NL - 1; l >= 0; l--) {
+    ARCVAE_CUDA(cudaMemsetAsync(sc.dc, 0, (size_t)B * H * sizeof(float), st));
+    const bool top = (l == d->NL - 1);
+    for (int t = T - 1; t >= 0; t--) {
+      float* g_t = tp.gates[l] + (long)t * B * G4;
+      const float* c_t = tp.c[l] + (long)t * B * H;
+      const float* dh_ext;
+      float* dh_ext_tmp = nullptr;
+      if (top) {
+        dh_ext = nullptr;  // only t = T-1 receives d h_T = du[:, 0:H] (strided), handled below
+        if (t == T - 1) {
+          // copy du[:, 0:H] into a dense [B,H] buffer (dh_rec[1] is free at the first step)
+          dh_ext_tmp = sc.dh_rec[1];
+          ARCVAE_CUDA(cudaMemcpy2DAsync(dh_ext_tmp, (size_t)H * sizeof(float), sc.du, (size_t)H2 * sizeof(float),
+                                        (size_t)H * sizeof(float), B, cudaMemcpyDeviceToDevice, st));
+          dh_ext = dh_ext_tmp;
+        }
+      } else {
+        dh_ext = sc.dX + (long)t * B * H;
+      }
+      const float* dh_rec = (t == T - 1) ? nullptr : sc.dh_rec[0];
+      ARCVAE_TRY(lstm_cell_bwd(g_t, c_t, t > 0 ? c_t - (long)B * H : nullptr, dh_ext, dh_rec, sc.dc, B, H, st));
+      if (t > 0) {
+        // d h_{t-1} (recurrent part) = dA_t @ Wh
+        ARCVAE_TRY(gemm_f32(0, 0, B, H, G4, g_t, G4, p->Wh[l], H, sc.dh_rec[0], H, nullptr, false, id, 1, st));
+      }
+    }
+    float* dA = tp.gates[l];
+    // dWh += dA[1:]^T @ h[:-1]
+    if (T > 1) {
+      long K = (long)(T - 1) * B;
+      ARCVAE_TRY(gemm_f32(1, 0, G4, H, (int)K, dA + (long)B * G4, G4, tp.h[l], H, g->Wh[l], H, nullptr, true, id, pick_splitk(G4, H, (int)K), st));
+    }
+    if (l > 0) {
+      ARCVAE_TRY(colsum(dA, R, G4, G4, g->bias[l], st));
+      // dWx += dA^T @ h_{l-1} ; dX = dA @ Wx
+      ARCVAE_TRY(gemm_f32(1, 0, G4, H, (int)R, dA, G4, tp.h[l - 1], H, g->Wx[l], H, nullptr, true, id, pick_splitk(G4, H, (int)R), st));
+      ARCVAE_TRY(gemm_f32(0, 0, (int)R, H, G4, dA, G4, p->Wx[l], H, sc.dX, H, nullptr, false, id, 1, st));
+    } else {
+      // layer 0: P0 = table0[x]  ->  dtable0 = onehot(x)^T @ dA ; table0 = Emb @ Wx0^T + b0
+      ARCVAE_CUDA(cudaMemsetAsync(sc.dtable0, 0, (size_t)d->V * G4 * sizeof(float), st));
+      ARCVAE_TRY(scatter_rows_by_token(dA, tp.xT, R, G4, d->V, sc.dtable0, nullptr, B, d->C, nullptr, st));
+      ARCVAE_TRY(colsum(sc.dtable0, d->V, G4, G4, g->bias[0], st));
+      ARCVAE_TRY(gemm_f32(0, 0, d->V, d->E, G4, sc.dtable0, G4, p->Wx[0], d->E, g->embedding, d->E, nullptr, true, id, 1, st));
+      ARCVAE_TRY(gemm_f32(1, 0, G4, d->E, d->V, sc.dtable0, G4, p->embedding, d->E, g->Wx[0], d->E, nullptr, true, id, 1, st));
+    }
+  }
+  return 0;
+}

@@ -1,0 +1,84 @@
+// kernels.cuh — internal launch wrappers (pointwise.cu, loss.cu, adam.cu) used by the orchestration in
+// encoder.cu / decoder.cu / sampler.cu.  All of them enqueue on `st` and return 0 / error code.
+#pragma once
+#include "common.cuh"
+
+namespace arcvae {
+
+// x[B,T] -> xT[T,B]
+int transpose_tokens(const int32_t* x, int B, int T, int32_t* xT, cudaStream_t st);
+// out[r,0:N] = table[tok[r],0:N] for r < R
+int gather_rows(const float* table, const int32_t* tok, int R, int N, float* out, cudaStream_t st);
+
+// LSTM cell, forward, in place: gates [Bn,4H] holds pre-activations (i,f,g,o) and receives the activated gates
+// (sigmoid(i), sigmoid(f), tanh(g), sigmoid(o)); c = f*c_prev + i*g (c_prev == nullptr: c = i*g); h = o*tanh(c)
+int lstm_cell_fwd(float* gates, const float* c_prev, float* c, float* h, int Bn, int H, cudaStream_t st);
+// reverse of one step: gates (activated, in) -> dA (pre-activation grads, out, in place).
+// dh = dh_ext + dh_rec (either may be null); dc (in/out, [Bn,H]) carries dL/dc_t in and dL/dc_{t-1} out.
+int lstm_cell_bwd(float* gates, const float* c, const float* c_prev, const float* dh_ext, const float* dh_rec,
+                  float* dc, int Bn, int H, cudaStream_t st);
+
+// decoder cells (zero state: c = i*g, h = o*tanh(c); forget gate unused) on COMPACT gate layout [.., 3H] = (i,g,o)
+// layer 0: a = table[tok[r]] + cond[r % B] @ wc^T   (table [V,3H], wc [3H,C]); rows r = rm(i), i < R
+int dec_cell0_fwd(const float* table, const float* wc, const int32_t* tok, const float* cond, int B, int C, int H,
+                  int R, RowMap rm, float* h, cudaStream_t st);
+// layers >= 1: G [.,3H] pre-activation -> activated in place; h out
+int dec_cell_fwd(float* G, float* h, int H, int R, RowMap rm, cudaStream_t st);
+// backward: G activated (in) -> dG (out, in place) given dh [.,H]
+int dec_cell_bwd(float* G, const float* dh, int H, long R, cudaStream_t st);
+// layer 0 backward with recompute of the gates from the table: dG0 [R,3H] out
+int dec_cell0_bwd(const float* table, const float* wc, const int32_t* tok, const float* cond, int B, int C, int H,
+                  long R, const float* dh, float* dG, cudaStream_t st);
+
+// head: u[b,0:H] = h_last[b,:]; u[b,H:2H] = cond[b,:] @ Wc^T + bc
+int head_build_u(const float* h_last, const float* cond, const float* Wc, const float* bc, int B, int H, int C,
+                 float* u, cudaStream_t st);
+int tanh_inplace(float* x, long n, cudaStream_t st);
+// d <- d * (1 - y*y)
+int tanh_bwd_inplace(float* d, const float* y, long n, cudaStream_t st);
+// mu = 2*tanh(mu_raw/2); logvar = tanh(lv_raw/2) - 1   (encoder.py:126,:130)
+int head_bound(const float* mu_raw, const float* lv_raw, long n, float* mu, float* logvar, cudaStream_t st);
+// dmu_raw = dmu*(1-(mu/2)^2); dlv_raw = dlogvar*0.5*(1-(logvar+1)^2)
+int head_bound_bwd(const float* mu, const float* logvar, const float* dmu, const float* dlogvar, long n,
+                   float* dmu_raw, float* dlv_raw, cudaStream_t st);
+
+// out[n] += sum_r X[r*ldx + n]
+int colsum(const float* X, long R, int N, int ldx, float* out, cudaStream_t st);
+// dtable[tok[r], n] += X[r,n];  optional: dwc[n*C + c] += X[r,n] * cond[(r % B)*C + c]
+int scatter_rows_by_token(const float* X, const int32_t* tok, long R, int N, int V, float* dtable, const float* cond,
+                          int B, int C, float* dwc, cudaStream_t st);
+// copy rows [0,H) U [2H,4H) of a [4H,D] matrix (or [4H] vector, D=1) to a compact [3H,D]; and the adjoint (+=)
+int compact_gates(const float* full, int H, int D, float* compact, cudaStream_t st);
+int expand_gates_add(const float* compact, int H, int D, float* full, cudaStream_t st);
+// strided add: dst[r*ldd + c] += src[r*lds + c], r<R, c<Cn
+int add_strided(const float* src, int lds, float* dst, int ldd, int R, int Cn, cudaStream_t st);
+
+// greedy feedback (decoder.py:185): tok_next[t+1 rows] = argmax(logits[t rows]) for t in tlist (device list, n entries),
+// lowest index wins ties.  logits time-major [T,B,V]; tok time-major [T,B]
+int argmax_feedback(const float* logits, const int* tlist, int ntl, int B, int V, int32_t* tok, cudaStream_t st);
+
+// sampler token selection for one step (decoder_sampling.py:110-123)
+int select_token(const float* logits, int B, int V, float temperature, int multinomial, uint64_t seed, int step,
+                 int max_length, int end_token, int32_t* tokens_out, int32_t* cur, int32_t* ended, int32_t* ended_count,
+                 cudaStream_t st);
+int sampler_check_stop(const int32_t* ended_count, int B, int step, int32_t* t_stop, cudaStream_t st);
+int set_int(int32_t* p, int32_t v, cudaStream_t st);
+
+// Philox4x32-10: 4 x uint32 for (seed, counter = (offset + idx))
+__device__ __forceinline__ void philox4x32(uint64_t seed, uint64_t ctr_lo, uint64_t ctr_hi, uint32_t out[4]) {
+  uint32_t c0 = (uint32_t)ctr_lo, c1 = (uint32_t)(ctr_lo >> 32), c2 = (uint32_t)ctr_hi, c3 = (uint32_t)(ctr_hi >> 32);
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// uniform in (0,1]: (x + 1) * 2^-32 computed in fp32 after dropping to 24 bits -> never 0
+__device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 1.0f) * (1.0f / 16777216.0f); }
+
+}  // namespace arcvae

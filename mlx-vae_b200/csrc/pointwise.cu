@@ -1,0 +1,538 @@
+// pointwise.cu — element-wise / gather / scatter / reduction kernels of the AR-CVAE step.
+// All are HBM-bound: coalesced along the hidden/gate axis, grid-stride loops sized to the 148 SMs.
+#include "kernels.cuh"
+
+namespace arcvae {
+
+static inline int grid_for(long n, int block, int per_sm = 8) {
+  long g = (n + block - 1) / block;
+  long cap = 148L * per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void k_transpose_tokens(const int32_t* __restrict__ x, int B, int T, int32_t* __restrict__ xT) {
+  __shared__ int32_t tile[32][33];
+  int b0 = blockIdx.x * 32, t0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int b = b0 + i, t = t0 + threadIdx.x;
+    if (b < B && t < T) tile[i][threadIdx.x] = x[(long)b * T + t];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int t = t0 + i, b = b0 + threadIdx.x;
+    if (b < B && t < T) xT[(long)t * B + b] = tile[threadIdx.x][i];
+  }
+}
+int transpose_tokens(const int32_t* x, int B, int T, int32_t* xT, cudaStream_t st) {
+  dim3 grid(cdiv(B, 32), cdiv(T, 32)), block(32, 8);
+  k_transpose_tokens<<<grid, block, 0, st>>>(x, B, T, xT);
+  ARCVAE_LAUNCHED();
+  return 0;
+}
+
+__global__ void k_gather_rows(const float* __restrict__ table, const int32_t* __restrict__ tok, int R, int N,
+                              float* __restrict__ out) {
+  long total = (long)R * N;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long r = i / N;
+    int n = (int)(i - r * N);
+    out[i] = table[(long)tok[r] * N + n];
+  }
+}
+int gather_rows(const float* table, const int32_t* tok, int R, int N, float* out, cudaStream_t st) {
+  k_gather_rows<<<grid_for((long)R * N, 256, 16), 256, 0, st>>>(table, tok, R, N, out);
+  ARCVAE_LAUNCHED();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void k_lstm_cell_fwd(float* __restrict__ gates, const float* __restrict__ c_prev, float* __restrict__ c,
+                                float* __restrict__ h, int Bn, int H) {
+  long total = (long)Bn * H;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    long b = idx / H;
+    int j = (int)(idx - b * H);
+    float* g = gates + b * 4L * H;
+    float i_ = sigmoidf_(g[j]);
+    float f_ = sigmoidf_(g[H + j]);
+    float g_ = tanhf_(g[2 * H + j]);
+    float o_ = sigmoidf_(g[3 * H + j]);
+    float cn = i_ * g_;
+    if (c_prev != nullptr) cn = fmaf(f_, c_prev[idx], cn);
+    g[j] = i_; g[H + j] = f_; g[2 * H + j] = g_; g[3 * H + j] = o_;
+    c[idx] = cn;
+    h[idx] = o_ * tanhf_(cn);
+  }
+}
+int lstm_cell_fwd(float* gates, const float* c_prev, float* c, float* h, int Bn, int H, cudaStream_t st) {
+  k_lstm_cell_fwd<<<grid_for((long)Bn * H, 256), 256, 0, st>>>(gates, c_prev, c, h, Bn, H);
+  ARCVAE_LAUNCHED();
+  return 0;
+}
+
+__global__ void k_lstm_cell_bwd(float* __restrict__ gates, const float* __restrict__ c, const float* __restrict__ c_prev,
+                                const float* __restrict__ dh_ext, const float* __restrict__ dh_rec,
+                                float* __restrict__ dc, int Bn, int H) {
+  long total = (long)Bn * H;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    long b = idx / H;
+    int j = (int)(idx - b * H);
+    float* g = gates + b * 4L * H;
+    float i_ = g[j], f_ = g[H + j], g_ = g[2 * H + j], o_ = g[3 * H + j];
+    float dh = 0.f;
+    if (dh_ext != nullptr) dh += dh_ext[idx];
+    if (dh_rec != nullptr) dh += dh_rec[idx];
+    float tc = tanhf_(c[idx]);
+    float dct = dc[idx] + dh * o_ * (1.f - tc * tc);
+    float cp = (c_prev != nullptr) ? c_prev[idx] : 0.f;
+    float d_o = dh * tc;
+    float d_i = dct * g_;
+    float d_g = dct * i_;
+    float d_f = dct * cp;
+    g[j] = d_i * i_ * (1.f - i_);
+    g[H + j] = d_f * f_ * (1.f - f_);
+    g[2 * H + j] = d_g * (1.f - g_ * g_);
+    g[3 * H + j] = d_o * o_ * (1.f - o_);
+    dc[idx] = dct * f_;
+  }
+}
+int lstm_cell_bwd(float* gates, const float* c, const float* c_prev, const float* dh_ext, const float* dh_rec,
+                  float* dc, int Bn, int H, cudaStream_t st) {
+  k_lstm_cell_bwd<<<grid_for((long)Bn * H, 256), 256, 0, st>>>(gates, c, c_prev, dh_ext, dh_rec, dc, Bn, H);
+  ARCVAE_LAUNCHED();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// decoder cells (compact gates i,g,o)
+__device__ __forceinline__ void dec0_preact(const float* __restrict__ table, const float* __restrict__ wc,
+                                            const float* __restrict__ cond_row, int tokv, int C, int H, int j,
+                                            float& ai, float& ag, float& ao) {
+  const float* trow = table + (long)tokv * 3 * H;
+  ai = trow[j]; ag = trow[H + j]; ao = trow[2 * H + j];
+  for (int c = 0; c < C; c++) {
+    float cv = cond_row[c];
+    ai = fmaf(cv, wc[(long)j * C + c], ai);
+    ag = fmaf(cv, wc[(long)(H + j) * C + c], ag);
+    ao = fmaf(cv, wc[(long)(2 * H + j) * C + c], ao);
+  }
+}
+
+__global__ void k_dec_cell0_fwd(const float* __restrict__ table, const float* __restrict__ wc,
+                                const int32_t* __restrict__ tok, const float* __restrict__ cond, int B, int C, int H,
+                                int R, RowMap rm, float* __restrict__ h) {
+  long total = (long)R * H;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    int i = (int)(idx / H);
+    int j = (int)(idx - (long)i * H);
+    long r = rm(i);
+    int b = (int)(r % B);
+    float ai, ag, ao;
+    dec0_preact(table, wc, cond + (long)b * C, tok[r], C, H, j, ai, ag, ao);
+    float cc = sigmoidf_(ai) * tanhf_(ag);
+    h[r * H + j] = sigmoidf_(ao) * tanhf_(cc);
+  }
+}
+int dec_cell0_fwd(const float* table, const float* wc, const int32_t* tok, const float* cond, int B, int C, int H,
+                  int R, RowMap rm, float* h, cudaStream_t st) {
+  if (R <= 0) return 0;
+  k_dec_cell0_fwd<<<grid_for((long)R * H, 256), 256, 0, st>>>(table, wc, tok, cond, B, C, H, R, rm, h);
+  ARCVAE_LAUNCHED();
+  return 0;
+}
+
+__global__ void k_dec_cell_fwd(float* __restrict__ G, float* __restrict__ h, int H, int R, RowMap rm) {
+  long total = (long)R * H;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    int i = (int)(idx / H);
+    int j = (int)(idx - (long)i * H);
+    long r = rm(i);
+    float* g = G + r * 3L * H;
+    float i_ = sigmoidf_(g[j]), g_ = tanhf_(g[H + j]), o_ = sigmoidf_(g[2 * H + j]);
+    g[j] = i_; g[H + j] = g_; g[2 * H + j] = o_;
+    h[r * H + j] = o_ * tanhf_(i_ * g_);
+  }
+}
+int dec_cell_fwd(float* G, float* h, int H, int R, RowMap rm, cudaStream_t st) {
+  if (R <= 0) return 0;
+  k_dec_cell_fwd<<<grid_for((long)R * H, 256), 256, 0, st>>>(G, h, H, R, rm);
+  ARCVAE_LAUNCHED();
+  return 0;
+}
+
+__device__ __forceinline__ void dec_cell_grads(float i_, float g_, float o_, float dh, float& dai, float& dag,
+                                               float& dao) {
+  float cc = i_ * g_;
+  float tc = tanhf_(cc);
+  float dcc = dh * o_ * (1.f - tc * tc);
+  dao = dh * tc * o_ * (1.f - o_);
+  dai = dcc * g_ * i_ * (1.f - i_);
+  dag = dcc * i_ * (1.f - g_ * g_);
+}
+
+__global__ void k_dec_cell_bwd(float* __restrict__ G, const float* __restrict__ dh, int H, long R) {
+  long total = R * H;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    long r = idx / H;
+    int j = (int)(idx - r * H);
+    float* g = G + r * 3L * H;
+    float dai, dag, dao;
+    dec_cell_grads(g[j], g[H + j], g[2 * H + j], dh[idx], dai, dag, dao);
+    g[j] = dai; g[H + j] = dag; g[2 * H + j] = dao;
+  }
+}
+int dec_cell_bwd(float* G, const float* dh, int H, long R, cudaStream_t st) {
+  k_dec_cell_bwd<<<grid_for(R * H, 256), 256, 0, st>>>(G, dh, H, R);
+  ARCVAE_LAUNCHED();
+  return 0;
+}
+
+__global__ void k_dec_cell0_bwd(const float* __restrict__ table, const float* __restrict__ wc,
+                                const int32_t* __restrict__ tok, const float* __restrict__ cond, int B, int C, int H,
+                                long R, const float* __restrict__ dh, float* __restrict__ dG) {
+  long total = R * H;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    long r = idx / H;
+    int j = (int)(idx - r * H);
+    int b = (int)(r % B);
+    float ai, ag, ao;
+    dec0_preact(table, wc, cond + (long)b * C, tok[r], C, H, j, ai, ag, ao);
+    float dai, dag, dao;
+    dec_cell_grads(sigmoidf_(ai), tanhf_(ag), sigmoidf_(ao), dh[idx], dai, dag, dao);
+    float* g = dG + r * 3L * H;
+    g[j] = dai; g[H + j] = dag; g[2 * H + j] = dao;
+  }
+}
+int dec_cell0_bwd(const float* table, const float* wc, const int32_t* tok, const float* cond, int B, int C, int H,
+                  long R, const float* dh, float* dG, cudaStream_t st) {
+  k_dec_cell0_bwd<<<grid_for(R * H, 256), 256, 0, st>>>(table, wc, tok, cond, B, C, H, R, dh, dG);
+  ARCVAE_LAUNCHED();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void k_head_build_u(const float* __restrict__ h_last, const float* __restrict__ cond,
+                               const float* __restrict__ Wc, const float* __restrict__ bc, int B, int H, int C,
+                               float* __restrict__ u) {
+  long total = (long)B * 2 * H;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    long b = idx / (2 * H);
+    int j = (int)(idx - b * 2 * H);
+    float v;
+    if (j < H) {
+      v = h_last[b * H + j];
+    } else {
+      int jj = j - H;
+      v = bc[jj];
+      for (int c = 0; c < C; c++) v = fmaf(cond[b * C + c], Wc[(long)jj * C + c], v);
+    }
+    u[idx] = v;
+  }
+}
+int head_build_u(const float* h_last, const float* cond, const float* Wc, const float* bc, int B, int H, int C,
+                 float* u, cudaStream_t st) {
+  k_head_build_u<<<grid_for((long)B * 2 * H, 256), 256, 0, st>>>(h_last, cond, Wc, bc, B, H, C, u);
+  ARCVAE_LAUNCHED();
+  return 0;
+}
+
+__global__ void k_tanh_inplace(float* x, long n) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    x[i] = tanhf_(x[i]);
+}
+int tanh_inplace(float* x, long n, cudaStream_t st) {
+  k_tanh_inplace<<<grid_for(n, 256), 256, 0, st>>>(x, n);
+  ARCVAE_LAUNCHED();
+  return 0;
+}
+__global__ void k_tanh_bwd_inplace(float* d, const float* __restrict__ y, long n) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    float yy = y[i];
+    d[i] = d[i] * (1.f - yy * yy);
+  }
+}
+int tanh_bwd_inplace(float* d, const float* y, long n, cudaStream_t st) {
+  k_tanh_bwd_inplace<<<grid_for(n, 256), 256, 0, st>>>(d, y, n);
+  ARCVAE_LAUNCHED();
+  return 0;
+}
+
+__global__ void k_head_bound(const float* __restrict__ mu_raw, const float* __restrict__ lv_raw, long n,
+                             float* __restrict__ mu, float* __restrict__ logvar) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    mu[i] = tanhf_(mu_raw[i] * 0.5f) * 2.0f;
+    logvar[i] = tanhf_(lv_raw[i] * 0.5f) - 1.0f;
+  }
+}
+int head_bound(const float* mu_raw, const float* lv_raw, long n, float* mu, float* logvar, cudaStream_t st) {
+  k_head_bound<<<grid_for(n, 256), 256, 0, st>>>(mu_raw, lv_raw, n, mu, logvar);
+  ARCVAE_LAUNCHED();
+  return 0;
+}
+__global__ void k_head_bound_bwd(const float* __restrict__ mu, const float* __restrict__ logvar,
+                                 const float* __restrict__ dmu, const float* __restrict__ dlogvar, long n,
+                                 float* __restrict__ dmu_raw, float* __restrict__ dlv_raw) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    float tm = mu[i] * 0.5f;          // tanh(mu_raw/2)
+    float tl = logvar[i] + 1.0f;      // tanh(lv_raw/2)
+    dmu_raw[i] = dmu[i] * (1.f - tm * tm);            // d/dx 2*tanh(x/2) = 1 - tanh^2
+    dlv_raw[i] = dlogvar[i] * 0.5f * (1.f - tl * tl);  // d/dx tanh(x/2) = (1 - tanh^2)/2
+  }
+}
+int head_bound_bwd(const float* mu, const float* logvar, const float* dmu, const float* dlogvar, long n,
+                   float* dmu_raw, float* dlv_raw, cudaStream_t st) {
+  k_head_bound_bwd<<<grid_for(n, 256), 256, 0, st>>>(mu, logvar, dmu, dlogvar, n, dmu_raw, dlv_raw);
+  ARCVAE_LAUNCHED();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// column sums: block = 32 x 8 (32 columns, 8 row lanes), rows strided over grid.y
+__global__ void k_colsum(const float* __restrict__ X, long R, int N, int ldx, float* __restrict__ out,
+                         long rows_per_block) {
+  __shared__ float red[8][33];
+  int n = blockIdx.x * 32 + threadIdx.x;
+  long r0 = blockIdx.y * rows_per_block;
+  long r1 = r0 + rows_per_block;
+  if (r1 > R) r1 = R;
+  float acc = 0.f;
+  if (n < N)
+    for (long r = r0 + threadIdx.y; r < r1; r += 8) acc += X[r * ldx + n];
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && n < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += red[i][threadIdx.x];
+    atomicAdd(out + n, s);
+  }
+}
+int colsum(const float* X, long R, int N, int ldx, float* out, cudaStream_t st) {
+  if (R <= 0 || N <= 0) return 0;
+  int gx = cdiv(N, 32);
+  long want = (148L * 8 + gx - 1) / gx;
+  long rpb = (R + want - 1) / want;
+  if (rpb < 64) rpb = 64;
+  int gy = cdiv(R, rpb);
+  k_colsum<<<dim3(gx, gy), dim3(32, 8), 0, st>>>(X, R, N, ldx, out, rpb);
+  ARCVAE_LAUNCHED();
+  return 0;
+}
+
+// scatter rows by token with an smem accumulator: block = 128 threads (one per column of a 128-wide slab),
+// each block walks `rows_per_block` rows; thread j owns column j so the smem adds are conflict-free and
+// un-contended.  V*128 floats of smem (V=80: 40 KB).
+__global__ void k_scatter_rows_by_token(const float* __restrict__ X, const int32_t* __restrict__ tok, long R, int N,
+                                        int V, float* __restrict__ dtable, const float* __restrict__ cond, int B, int C,
+                                        float* __restrict__ dwc, long rows_per_block) {
+  extern __shared__ float acc[];  // [V][128]
+  int j = threadIdx.x;
+  int n = blockIdx.x * 128 + j;
+  for (int v = 0; v < V; v++) acc[v * 128 + j] = 0.f;
+  long r0 = blockIdx.y * rows_per_block;
+  long r1 = r0 + rows_per_block;
+  if (r1 > R) r1 = R;
+  float wacc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (n < N) {
+    for (long r = r0; r < r1; r++) {
+      float x = X[r * N + n];
+      acc[tok[r] * 128 + j] += x;
+      if (dwc != nullptr) {
+        const float* cr = cond + (r % B) * C;
+        for (int c = 0; c < C && c < 4; c++) wacc[c] = fmaf(x, cr[c], wacc[c]);
+      }
+    }
+    for (int v = 0; v < V; v++) {
+      float s = acc[v * 128 + j];
+      if (s != 0.f) atomicAdd(dtable + (long)v * N + n, s);
+    }
+    if (dwc != nullptr)
+      for (int c = 0; c < C && c < 4; c++) atomicAdd(dwc + (long)n * C + c, wacc[c]);
+  }
+}
+int scatter_rows_by_token(const float* X, const int32_t* tok, long R, int N, int V, float* dtable, const float* cond,
+                          int B, int C, float* dwc, cudaStream_t st) {
+  if (R <= 0) return 0;
+  ARCVAE_REQUIRE(dwc == nullptr || C <= 4, "num_conditions > 4 not supported by the fused cond-weight reduction");
+  size_t smem = (size_t)V * 128 * sizeof(float);
+  ARCVAE_REQUIRE(smem <= 200 * 1024, "vocab too large for the smem scatter accumulator");
+  static bool attr_set = false;
+  if (!attr_set) {
+    ARCVAE_CUDA(cudaFuncSetAttribute(k_scatter_rows_by_token, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  int gx = cdiv(N, 128);
+  long want = (148L * 4 + gx - 1) / gx;
+  long rpb = (R + want - 1) / want;
+  if (rpb < 256) rpb = 256;
+  int gy = cdiv(R, rpb);
+  k_scatter_rows_by_token<<<dim3(gx, gy), 128, smem, st>>>(X, tok, R, N, V, dtable, cond, B, C, dwc, rpb);
+  ARCVAE_LAUNCHED();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void k_compact_gates(const float* __restrict__ full, int H, int D, float* __restrict__ compact) {
+  long total = 3L * H * D;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long row = i / D;
+    int c = (int)(i - row * D);
+    long src = row < H ? row : row + H;  // i rows [0,H) ; g,o rows [2H,4H)
+    compact[i] = full[src * D + c];
+  }
+}
+int compact_gates(const float* full, int H, int D, float* compact, cudaStream_t st) {
+  k_compact_gates<<<grid_for(3L * H * D, 256), 256, 0, st>>>(full, H, D, compact);
+  ARCVAE_LAUNCHED();
+  return 0;
+}
+__global__ void k_expand_gates_add(const float* __restrict__ compact, int H, int D, float* __restrict__ full) {
+  long total = 3L * H * D;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long row = i / D;
+    int c = (int)(i - row * D);
+    long dst = row < H ? row : row + H;
+    full[dst * D + c] += compact[i];
+  }
+}
+int expand_gates_add(const float* compact, int H, int D, float* full, cudaStream_t st) {
+  k_expand_gates_add<<<grid_for(3L * H * D, 256), 256, 0, st>>>(compact, H, D, full);
+  ARCVAE_LAUNCHED();
+  return 0;
+}
+__global__ void k_add_strided(const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd, int R, int Cn) {
+  long total = (long)R * Cn;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long r = i / Cn;
+    int c = (int)(i - r * Cn);
+    dst[r * ldd + c] += src[r * lds + c];
+  }
+}
+int add_strided(const float* src, int lds, float* dst, int ldd, int R, int Cn, cudaStream_t st) {
+  if (R <= 0 || Cn <= 0) return 0;
+  k_add_strided<<<grid_for((long)R * Cn, 256), 256, 0, st>>>(src, lds, dst, ldd, R, Cn);
+  ARCVAE_LAUNCHED();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one warp per row: argmax with lowest-index tie break (mx.argmax)
+__device__ __forceinline__ void warp_argmax(float& v, int& i) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    int oi = __shfl_xor_sync(0xffffffffu, i, o);
+    if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+  }
+}
+
+__global__ void k_argmax_feedback(const float* __restrict__ logits, const int* __restrict__ tlist, int ntl, int B,
+                                  int V, int32_t* __restrict__ tok) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  int nwarps = (gridDim.x * blockDim.x) >> 5;
+  long total = (long)ntl * B;
+  for (long w = warp; w < total; w += nwarps) {
+    int q = (int)(w / B);
+    int b = (int)(w - (long)q * B);
+    int t = tlist[q];
+    const float* row = logits + ((long)t * B + b) * V;
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int v = lane; v < V; v += 32) {
+      float x = row[v];
+      if (x > bv) { bv = x; bi = v; }   // strictly greater keeps the lowest index within a lane
+    }
+    warp_argmax(bv, bi);
+    if (lane == 0) tok[(long)(t + 1) * B + b] = bi;
+  }
+}
+int argmax_feedback(const float* logits, const int* tlist, int ntl, int B, int V, int32_t* tok, cudaStream_t st) {
+  if (ntl <= 0) return 0;
+  long total = (long)ntl * B;
+  k_argmax_feedback<<<grid_for(total * 32, 256), 256, 0, st>>>(logits, tlist, ntl, B, V, tok);
+  ARCVAE_LAUNCHED();
+  return 0;
+}
+
+// sampler selection: one warp per row.  multinomial: inverse-CDF over softmax(logits/T) with one Philox uniform.
+__global__ void k_select_token(const float* __restrict__ logits, int B, int V, float temperature, int multinomial,
+                               uint64_t seed, int step, int max_length, int end_token, int32_t* __restrict__ tokens_out,
+                               int32_t* __restrict__ cur, int32_t* __restrict__ ended,
+                               int32_t* __restrict__ ended_count) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int b = warp; b < B; b += nwarps) {
+    const float* row = logits + (long)b * V;
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int v = lane; v < V; v += 32) {
+      float x = row[v] / temperature;
+      if (x > bv) { bv = x; bi = v; }
+    }
+    warp_argmax(bv, bi);
+    int choice = bi;
+    if (multinomial) {
+      float s = 0.f;
+      for (int v = lane; v < V; v += 32) s += expf(row[v] / temperature - bv);
+      s = warp_sum(s);
+      uint32_t r4[4];
+      philox4x32(seed, (uint64_t)b, (uint64_t)step, r4);
+      float target = u01(r4[0]) * s;
+      // sequential inverse CDF in index order, 32 entries at a time
+      float run = 0.f;
+      choice = -1;
+      for (int v0 = 0; v0 < V && choice < 0; v0 += 32) {
+        int v = v0 + lane;
+        float p = (v < V) ? expf(row[v] / temperature - bv) : 0.f;
+        float incl = p;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          float y = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += y;
+        }
+        unsigned hit = __ballot_sync(0xffffffffu, (v < V) && (run + incl >= target));
+        if (hit) choice = v0 + (__ffs(hit) - 1);
+        run += __shfl_sync(0xffffffffu, incl, 31);
+      }
+      if (choice < 0) choice = bi;  // rounding left the target just above the total mass
+    }
+    if (lane == 0) {
+      tokens_out[(long)b * max_length + step] = choice;
+      cur[b] = choice;
+      if (choice == end_token && !ended[b]) {
+        ended[b] = 1;
+        atomicAdd(ended_count, 1);
+      }
+    }
+  }
+}
+int select_token(const float* logits, int B, int V, float temperature, int multinomial, uint64_t seed, int step,
+                 int max_length, int end_token, int32_t* tokens_out, int32_t* cur, int32_t* ended, int32_t* ended_count,
+                 cudaStream_t st) {
+  k_select_token<<<grid_for((long)B * 32, 256), 256, 0, st>>>(logits, B, V, temperature, multinomial, seed, step,
+                                                              max_length, end_token, tokens_out, cur, ended,
+                                                              ended_count);
+  ARCVAE_LAUNCHED();
+  return 0;
+}
+
+__global__ void k_sampler_check_stop(const int32_t* ended_count, int B, int step, int32_t* t_stop) {
+  if (*ended_count >= B && *t_stop > step) *t_stop = step;
+}
+int sampler_check_stop(const int32_t* ended_count, int B, int step, int32_t* t_stop, cudaStream_t st) {
+  k_sampler_check_stop<<<1, 1, 0, st>>>(ended_count, B, step, t_stop);
+  ARCVAE_LAUNCHED();
+  return 0;
+}
+
+__global__ void k_set_int(int32_t* p, int32_t v) { *p = v; }
+int set_int(int32_t* p, int32_t v, cudaStream_t st) {
+  k_set_int<<<1, 1, 0, st>>>(p, v);
+  ARCVAE_LAUNCHED();
+  return 0;
+}
+
+}  // namespace arcvae

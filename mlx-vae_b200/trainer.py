@@ -1,0 +1,121 @@
+"""ARCVAETrainerWithLoss — the STEP of trainer.py of the reference (trainer.py:267-333, :489-522) plus the two
+schedules; epoch bookkeeping, plotting and checkpoint I/O of the reference are host glue and out of scope."""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from .complete_vae_loss import _run
+from .parallel import GradSync
+
+
+class _Adam:
+    """mlx.optimizers.Adam as configured at trainer.py:75-76: betas (0.9, 0.999), eps 1e-8, NO bias correction.
+    State lives in two flat buffers shaped like the module's flat parameter buffer."""
+
+    def __init__(self, module, learning_rate: float):
+        self.module = module
+        self.learning_rate = float(learning_rate)
+        self.m = torch.zeros_like(module.params.flat)
+        self.v = torch.zeros_like(module.params.flat)
+
+    def update(self, grad_scale: float = 1.0):
+        p, g = self.module.params.flat, self.module.grads.flat
+        _lib.check(_lib.load().arcvae_adam_step(p.data_ptr(), g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                                                p.numel(), self.learning_rate, 0.9, 0.999, 1e-8, float(grad_scale),
+                                                _lib.stream_ptr()))
+
+    @property
+    def state(self):
+        return {"m": self.m, "v": self.v}
+
+
+class ARCVAETrainerWithLoss:
+    """Constructor signature of trainer.py:20-37.  ``train_step`` is the body of the batch loop (trainer.py:303-333)."""
+
+    def __init__(self, encoder, decoder, property_predictor, dataset, learning_rate: float = 1e-4,
+                 batch_size: int = 32, beta_start: float = 0.0, beta_end: float = 0.4, beta_warmup_epochs: int = 100,
+                 lambda_prop: float = 0.1, lambda_collapse: float = 0.01, free_bits: float = 0.5,
+                 lambda_mi: float = 0.01, grad_clip: float = 1.0, checkpoint_dir: str = "./checkpoints", *,
+                 clip_mode: str = "reference_noop", pad_mask: bool = False, process_group=None):
+        if clip_mode not in ("reference_noop", "global_norm"):
+            raise ValueError("clip_mode must be 'reference_noop' or 'global_norm'")
+        self.encoder, self.decoder, self.property_predictor, self.dataset = encoder, decoder, property_predictor, dataset
+        self.batch_size, self.grad_clip = batch_size, grad_clip
+        self.lambda_prop, self.lambda_collapse = lambda_prop, lambda_collapse
+        self.free_bits, self.lambda_mi = free_bits, lambda_mi
+        self.beta_start, self.beta_end, self.beta_warmup_epochs = beta_start, beta_end, beta_warmup_epochs
+        self.learning_rate = learning_rate
+        self.encoder_optimizer = _Adam(encoder, learning_rate)   # two optimizers, as trainer.py:75-76
+        self.decoder_optimizer = _Adam(decoder, learning_rate)
+        self.clip_mode, self.pad_mask = clip_mode, pad_mask
+        self.sync = GradSync(process_group)
+        self.step_count = 0
+
+    # ---- schedules (trainer.py:102-114) -----------------------------------------------------------------
+    def compute_beta(self, epoch: int) -> float:
+        if epoch < self.beta_warmup_epochs:
+            return float(self.beta_start + (self.beta_end - self.beta_start) * (epoch / self.beta_warmup_epochs))
+        return float(self.beta_end)
+
+    def compute_teacher_forcing_ratio(self, epoch: int, total_epochs: int) -> float:
+        return float(max(0.5, 0.9 - 0.4 * (epoch / total_epochs)))
+
+    # ---- one optimizer step (trainer.py:305-333) ----------------------------------------------------------
+    def train_step(self, molecules: torch.Tensor, conditions: torch.Tensor, beta: float, teacher_forcing_ratio: float,
+                   *, eps: Optional[torch.Tensor] = None, tf_mask=None, seed: Optional[int] = None) -> Dict[str, torch.Tensor]:
+        """value_and_grad -> clip -> two Adam updates.  Returns the loss dict (0-d CUDA tensors; nothing is synced).
+
+        Clipping: the reference's ``_clip_gradients`` sums only arrays at the top level of each gradient dict, every
+        leaf is one level down, so the norm is 0 and nothing is ever scaled (trainer.py:502-514).
+        ``clip_mode='reference_noop'`` reproduces that; ``'global_norm'`` is a real global-norm clip (one host sync).
+        Under data parallelism `molecules` is this rank's shard; losses and gradients are those of the GLOBAL batch."""
+        enc, dec, sync = self.encoder, self.decoder, self.sync
+        enc.zero_grad()
+        dec.zero_grad()
+        if seed is None:
+            seed = self.step_count
+        dp = sync.enabled
+        # forward + loss + decoder reverse pass; under DP the decoder gradients start their all-reduce while the
+        # encoder BPTT is still being computed
+        hooks = _DPHooks(sync) if dp else None
+        d = _run(enc, dec, self.property_predictor, molecules, conditions, beta, self.lambda_prop, self.lambda_collapse,
+                 teacher_forcing_ratio, self.free_bits, self.lambda_mi, 4.85, eps, tf_mask, seed, self.pad_mask, True,
+                 sync.allreduce_stats if dp else None, backward_hooks=hooks)
+        if dp:
+            sync.allreduce_async(enc.grads.flat)
+            sync.wait()
+        scale = 1.0
+        if self.clip_mode == "global_norm" and self.grad_clip > 0:
+            acc = torch.zeros(1, dtype=torch.float64, device=enc.device)
+            lib = _lib.load()
+            for m in (enc, dec):
+                _lib.check(lib.arcvae_sumsq(m.grads.flat.data_ptr(), m.grads.flat.numel(), acc.data_ptr(), _lib.stream_ptr()))
+            norm = float(acc.sqrt().item())
+            if norm > self.grad_clip:
+                scale = self.grad_clip / (norm + 1e-8)
+        self.encoder_optimizer.update(scale)     # trainer.py:320
+        self.decoder_optimizer.update(scale)     # trainer.py:324
+        self.step_count += 1
+        return d
+
+    def _train_epoch_batches(self, beta: float, teacher_forcing_ratio: float) -> Dict[str, float]:
+        """trainer.py:242-416 without the tqdm / logging side paths: iterate ``dataset.to_batches`` and step."""
+        total, n = 0.0, 0
+        for molecules, conditions in self.dataset.to_batches(self.batch_size, shuffle=True):
+            d = self.train_step(molecules, conditions, beta, teacher_forcing_ratio)
+            total += float(d["total_loss"])
+            n += 1
+        return {"loss": total / max(1, n)}
+
+
+class _DPHooks:
+    """Called by the step between the decoder and encoder reverse passes."""
+
+    def __init__(self, sync: GradSync):
+        self.sync = sync
+
+    def after_decoder_backward(self, decoder):
+        self.sync.allreduce_async(decoder.grads.flat)
