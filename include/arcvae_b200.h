@@ -169,6 +169,11 @@ int arcvae_sumsq(const float* g, size_t n, double* out, void* stream);
 int arcvae_gemm_f32(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                     float* C, int ldc, const float* bias, int accumulate, void* stream);
 
+/* bf16 tensor-core GEMM (tcgen05 + TMA) exposed for tests: A, B point to bf16 data.
+ * a_mn=0: A[m*lda+k], 1: A[k*lda+m]; b_mn=0: B[n*ldb+k], 1: B[k*ldb+n]; C fp32 and/or Cb bf16 outputs. */
+int arcvae_gemm_bf16(int a_mn, int b_mn, int M, int N, int K, const void* A, int lda, const void* B, int ldb, float* C,
+                     int ldc, void* Cb, int ldcb, const float* bias, int accumulate, int splitk, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,417 @@
+// gemm_tc.cu — bf16 tensor-core GEMM for the time-parallel contractions of the AR-CVAE step:
+//   D[M,N] (+)= A[M,K] * B[K,N] (+ bias), bf16 operands, fp32 accumulation in TMEM, fp32 and/or bf16 output.
+//
+// sm_100a structure (one CTA per SM, persistent over output tiles, 192 threads):
+//   warp 0      TMA producer   cp.async.bulk.tensor (SWIZZLE_128B) into a multi-stage smem ring, mbarrier complete_tx
+//   warp 1      MMA issuer     one elected thread issues tcgen05.mma (M=128, N=BN<=256, K=16 per instruction),
+//                              tcgen05.commit releases smem stages / publishes the accumulator
+//   warps 2..5  epilogue       tcgen05.ld (32x32b) of the accumulator quarter they own, bias / accumulate / split-K atomics
+// Two accumulators (2 x BN TMEM columns) let the epilogue of tile i overlap the MMAs of tile i+1.
+//
+// Operand layouts (both served by TMA, no transposes in HBM):
+//   K-major   A[m*lda + k], B[n*ldb + k]   forward projections, input gradients against pre-transposed weights
+//   MN-major  A[k*lda + m], B[k*ldb + n]   weight gradients dW = dA^T @ H with K = B*T (split-K + fp32 atomics)
+#include <mutex>
+
+#include "kernels.cuh"
+#include "tc_common.cuh"
+
+namespace arcvae {
+
+using bf16 = __nv_bfloat16;
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;
+constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_THREADS = 192;
+
+struct TcParams {
+  int M, N, K;
+  int BN;            // N tile (multiple of 16, <= 256)
+  int stages;
+  int a_mn, b_mn;    // operand major-ness
+  int mt, nt, splitk, kb_per;
+  float* C; int ldc;
+  bf16* Cb; int ldcb;
+  const float* bias;
+  int accumulate;
+  RowMap rm;
+};
+
+struct __align__(8) TcShared {
+  uint64_t full[TC_MAX_STAGES];
+  uint64_t empty[TC_MAX_STAGES];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-B alignment for SWIZZLE_128B tiles
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t a_bytes = TC_BM * TC_BK * 2;              // 16 KB
+  const uint32_t b_bytes = (uint32_t)p.BN * TC_BK * 2;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  TcShared* sh = reinterpret_cast<TcShared*>(smem + (size_t)p.stages * stage_bytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.mt * p.nt * p.splitk;
+  const int kblocks = (p.K + TC_BK - 1) / TC_BK;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < 2u * (uint32_t)p.BN) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmA);
+    tc::prefetch_tmap(&tmB);
+    for (int s = 0; s < p.stages; s++) {
+      tc::mbar_init(&sh->full[s], 1);
+      tc::mbar_init(&sh->empty[s], 1);
+    }
+    for (int a = 0; a < 2; a++) {
+      tc::mbar_init(&sh->tmem_full[a], 1);
+      tc::mbar_init(&sh->tmem_empty[a], 4);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(&sh->tmem_base, tmem_cols);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = sh->tmem_base;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mi = tile % p.mt;
+        const int ni = (tile / p.mt) % p.nt;
+        const int ks = tile / (p.mt * p.nt);
+        const int m0 = mi * TC_BM, n0 = ni * p.BN;
+        const int gm0 = (int)p.rm(m0);
+        const int kb0 = ks * p.kb_per;
+        const int kb1 = min(kblocks, kb0 + p.kb_per);
+        for (int kb = kb0; kb < kb1; kb++) {
+          tc::mbar_wait(&sh->empty[stage], phase ^ 1);
+          uint8_t* sa = smem + (size_t)stage * stage_bytes;
+          uint8_t* sb = sa + a_bytes;
+          tc::mbar_expect_tx(&sh->full[stage], stage_bytes);
+          const int k0 = kb * TC_BK;
+          if (!p.a_mn) {
+            tc::tma_load_2d(sa, &tmA, &sh->full[stage], k0, gm0);                       // box {64 k, 128 rows}
+          } else {
+            tc::tma_load_2d(sa, &tmA, &sh->full[stage], m0, k0);                        // box {64 m, 64 k} x 2
+            tc::tma_load_2d(sa + 8192, &tmA, &sh->full[stage], m0 + 64, k0);
+          }
+          if (!p.b_mn) {
+            tc::tma_load_2d(sb, &tmB, &sh->full[stage], k0, n0);                        // box {64 k, BN rows}
+          } else {
+            for (int j = 0; j < p.BN / 64; j++)
+              tc::tma_load_2d(sb + j * 8192, &tmB, &sh->full[stage], n0 + j * 64, k0);  // box {64 n, 64 k}
+          }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    const uint32_t idesc = tc::make_idesc_bf16(TC_BM, p.BN, p.a_mn != 0, p.b_mn != 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+      const int ks = tile / (p.mt * p.nt);
+      const int kb0 = ks * p.kb_per;
+      const int kb1 = min(kblocks, kb0 + p.kb_per);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      if (lane == 0) tc::mbar_wait(&sh->tmem_empty[acc], acc_phase ^ 1);
+      __syncwarp();
+      tc::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+      for (int kb = kb0; kb < kb1; kb++) {
+        if (lane == 0) tc::mbar_wait(&sh->full[stage], phase);
+        __syncwarp();
+        tc::tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = tc::smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t sb = sa + a_bytes;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; k++) {
+            const uint64_t da = p.a_mn ? tc::make_smem_desc(sa + k * 2048, 8192, 1024)
+                                       : tc::make_smem_desc(sa + k * 32, 16, 1024);
+            const uint64_t db = p.b_mn ? tc::make_smem_desc(sb + k * 2048, 8192, 1024)
+                                       : tc::make_smem_desc(sb + k * 32, 16, 1024);
+            tc::mma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          tc::mma_commit(&sh->empty[stage]);                  // smem stage free once these MMAs have read it
+          if (kb == kb1 - 1) tc::mma_commit(&sh->tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================================================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1)
+    const int q = warp & 3;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+      const int mi = tile % p.mt;
+      const int ni = (tile / p.mt) % p.nt;
+      const int m0 = mi * TC_BM, n0 = ni * p.BN;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      tc::mbar_wait(&sh->tmem_full[acc], acc_phase);
+      tc::tc_fence_after();
+      const int row_local = m0 + q * 32 + lane;
+      const bool row_ok = row_local < p.M;
+      const long grow = row_ok ? p.rm(row_local) : 0;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
+      const bool atomic = p.splitk > 1;
+      const bool add_bias = p.bias != nullptr && (tile / (p.mt * p.nt)) == 0;
+      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        uint32_t r[16];
+        tc::tmem_ld16(taddr + c0, r);
+        tc::tmem_ld_wait();
+        if (row_ok) {
+          const int nbase = n0 + c0;
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; j++) {
+            v[j] = __uint_as_float(r[j]);
+            if (add_bias && nbase + j < p.N) v[j] += p.bias[nbase + j];
+          }
+          if (p.C != nullptr) {
+            float* dst = p.C + grow * p.ldc + nbase;
+            if (atomic) {
+#pragma unroll
+              for (int j = 0; j < 16; j++)
+                if (nbase + j < p.N) atomicAdd(dst + j, v[j]);
+            } else if (nbase + 16 <= p.N && ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                if (p.accumulate) {
+                  float4 old = *reinterpret_cast<float4*>(dst + j);
+                  o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                }
+                *reinterpret_cast<float4*>(dst + j) = o;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; j++)
+                if (nbase + j < p.N) dst[j] = p.accumulate ? dst[j] + v[j] : v[j];
+            }
+          }
+          if (p.Cb != nullptr) {
+            bf16* dstb = p.Cb + grow * p.ldcb + nbase;
+            if (nbase + 16 <= p.N && ((p.ldcb & 7) == 0) && ((reinterpret_cast<uintptr_t>(dstb) & 15) == 0)) {
+              uint32_t pk[8];
+#pragma unroll
+              for (int j = 0; j < 8; j++) {
+                __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                pk[j] = *reinterpret_cast<uint32_t*>(&t);
+              }
+              *reinterpret_cast<uint4*>(dstb) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              *reinterpret_cast<uint4*>(dstb + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; j++)
+                if (nbase + j < p.N) dstb[j] = __float2bfloat16(v[j]);
+            }
+          }
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&sh->tmem_empty[acc]);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+
+static int get_encode() {
+  static std::once_flag once;
+  static int rc = 0;
+  std::call_once(once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+      set_error("cuTensorMapEncodeTiled is not available from the driver");
+      rc = 3;
+    } else {
+      g_encode = (PFN_encodeTiled)fn;
+    }
+  });
+  return rc;
+}
+
+// row-major bf16 matrix [rows, cols] with pitch ld (elements); box {box_cols (inner), box_rows}
+static int make_tmap(CUtensorMap* m, const bf16* ptr, long rows, long cols, long ld, int box_cols, int box_rows) {
+  ARCVAE_TRY(get_encode());
+  ARCVAE_REQUIRE((ld % 8) == 0 && ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0),
+                 "TMA operands need 16-byte aligned base and pitch (ld multiple of 8 bf16)");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(bf16)};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    return 3;
+  }
+  return 0;
+}
+
+static int pick_bn(int N) {
+  if (N >= 256) return 256;
+  return ((N + 15) / 16) * 16;
+}
+
+int gemm_tc(const TcGemm& g, cudaStream_t st) {
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0) return 0;
+  ARCVAE_REQUIRE(g.C != nullptr || g.Cb != nullptr, "gemm_tc needs an output");
+  ARCVAE_REQUIRE(!(g.a_mn && g.rm.tlist != nullptr), "row map needs a K-major A");
+  ARCVAE_REQUIRE(g.rm.tlist == nullptr || (g.rm.Bt % TC_BM) == 0, "row-mapped tiles must not straddle timesteps");
+  TcParams p;
+  p.M = g.M; p.N = g.N; p.K = g.K;
+  p.BN = pick_bn(g.N);
+  if (g.b_mn) {
+    ARCVAE_REQUIRE(g.N % 64 == 0 || g.N < 64, "MN-major B needs N multiple of 64");
+    p.BN = g.N >= 256 ? 256 : ((g.N + 63) / 64) * 64;
+  }
+  p.a_mn = g.a_mn ? 1 : 0; p.b_mn = g.b_mn ? 1 : 0;
+  p.mt = cdiv(g.M, TC_BM); p.nt = cdiv(g.N, p.BN);
+  const int kblocks = cdiv(g.K, TC_BK);
+  int splitk = g.splitk < 1 ? 1 : g.splitk;
+  if (splitk > kblocks) splitk = kblocks;
+  p.kb_per = cdiv(kblocks, splitk);
+  p.splitk = cdiv(kblocks, p.kb_per);
+  ARCVAE_REQUIRE(p.splitk == 1 || (g.accumulate && g.C != nullptr && g.Cb == nullptr),
+                 "split-K accumulates with fp32 atomics into C");
+  p.C = g.C; p.ldc = g.ldc; p.Cb = g.Cb; p.ldcb = g.ldcb; p.bias = g.bias; p.accumulate = g.accumulate ? 1 : 0;
+  p.rm = g.rm;
+  const size_t stage_bytes = (size_t)TC_BM * TC_BK * 2 + (size_t)p.BN * TC_BK * 2;
+  int stages = (int)((200 * 1024) / stage_bytes);
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  if (stages > p.kb_per + 1 && p.kb_per + 1 >= 2) stages = p.kb_per + 1 > 2 ? p.kb_per + 1 : 2;
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + sizeof(TcShared) + 1024;
+
+  CUtensorMap tmA, tmB;
+  if (!g.a_mn) {
+    // rows of A may be reached through the row map -> describe the whole allocation the map can touch
+    long rows = g.rm.tlist ? g.a_rows_total : g.M;
+    ARCVAE_TRY(make_tmap(&tmA, g.A, rows, g.K, g.lda, TC_BK, TC_BM));
+  } else {
+    ARCVAE_TRY(make_tmap(&tmA, g.A, g.K, g.M, g.lda, 64, TC_BK));
+  }
+  if (!g.b_mn) ARCVAE_TRY(make_tmap(&tmB, g.B, g.N, g.K, g.ldb, TC_BK, p.BN));
+  else ARCVAE_TRY(make_tmap(&tmB, g.B, g.K, g.N, g.ldb, 64, TC_BK));
+
+  static int num_sms = 0;
+  static bool attr = false;
+  if (!attr) {
+    int dev = 0;
+    ARCVAE_CUDA(cudaGetDevice(&dev));
+    ARCVAE_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    ARCVAE_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  ARCVAE_REQUIRE(smem <= 227 * 1024, "gemm_tc shared memory budget");
+  const int total = p.mt * p.nt * p.splitk;
+  const int grid = total < num_sms ? total : num_sms;
+  TimeScope ts(TIME_GEMM_TC, st);
+  gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, p);
+  ARCVAE_LAUNCHED();
+  return 0;
+}
+
+// split-K factor for weight-gradient shapes: enough (tile, split) work items for ~2 per SM
+int pick_splitk_tc(int M, int N, int K) {
+  long tiles = (long)cdiv(M, TC_BM) * cdiv(N, pick_bn(N));
+  long kblocks = cdiv(K, TC_BK);
+  if (tiles >= 148 || kblocks < 16) return 1;
+  long want = (2 * 148 + tiles - 1) / tiles;
+  long maxs = kblocks / 8;
+  if (maxs < 1) maxs = 1;
+  return (int)(want < maxs ? want : maxs);
+}
+
+// ---- fp32 -> bf16 conversion (vectorised, HBM-bound) ------------------------------------------------------------
+__global__ void k_f32_to_bf16(const float* __restrict__ src, bf16* __restrict__ dst, long n) {
+  long n4 = n >> 2;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<const float4*>(src)[i];
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 o = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+    reinterpret_cast<uint2*>(dst)[i] = o;
+  }
+  for (long i = (n4 << 2) + blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    dst[i] = __float2bfloat16(src[i]);
+}
+int f32_to_bf16(const float* src, bf16* dst, long n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  long g = (n / 4 + 255) / 256 + 1;
+  if (g > 148 * 8) g = 148 * 8;
+  TimeScope ts(TIME_POINTWISE, st);
+  k_f32_to_bf16<<<(int)g, 256, 0, st>>>(src, dst, n);
+  ARCVAE_LAUNCHED();
+  return 0;
+}
+// dst[c*R + r] = bf16(src[r*C + c])   (weights only: small)
+__global__ void k_transpose_to_bf16(const float* __restrict__ src, int R, int C, bf16* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int r = r0 + i, c = c0 + threadIdx.x;
+    if (r < R && c < C) tile[i][threadIdx.x] = src[(long)r * C + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < C) dst[(long)c * R + r] = __float2bfloat16(tile[threadIdx.x][i]);
+  }
+}
+int transpose_to_bf16(const float* src, int R, int C, bf16* dst, cudaStream_t st) {
+  k_transpose_to_bf16<<<dim3(cdiv(C, 32), cdiv(R, 32)), dim3(32, 8), 0, st>>>(src, R, C, dst);
+  ARCVAE_LAUNCHED();
+  return 0;
+}
+
+}  // namespace arcvae
+
+// test entry: D = op(A) op(B) with bf16 operands (device pointers to bf16 data)
+extern "C" int arcvae_gemm_bf16(int a_mn, int b_mn, int M, int N, int K, const void* A, int lda, const void* B, int ldb,
+                                float* C, int ldc, void* Cb, int ldcb, const float* bias, int accumulate, int splitk,
+                                void* stream) {
+  using namespace arcvae;
+  TcGemm g;
+  g.M = M; g.N = N; g.K = K;
+  g.A = (const bf16*)A; g.lda = lda; g.a_mn = a_mn != 0;
+  g.B = (const bf16*)B; g.ldb = ldb; g.b_mn = b_mn != 0;
+  g.C = C; g.ldc = ldc; g.Cb = (bf16*)Cb; g.ldcb = ldcb; g.bias = bias; g.accumulate = accumulate != 0;
+  g.splitk = splitk;
+  g.rm = RowMap{nullptr, 1};
+  g.a_rows_total = M;
+  return gemm_tc(g, (cudaStream_t)stream);
+}

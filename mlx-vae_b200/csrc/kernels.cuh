@@ -1,6 +1,8 @@
 // kernels.cuh — internal launch wrappers (pointwise.cu, loss.cu, adam.cu) used by the orchestration in
 // encoder.cu / decoder.cu / sampler.cu.  All of them enqueue on `st` and return 0 / error code.
 #pragma once
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace arcvae {
@@ -63,6 +65,24 @@ int select_token(const float* logits, int B, int V, float temperature, int multi
                  cudaStream_t st);
 int sampler_check_stop(const int32_t* ended_count, int B, int step, int32_t* t_stop, cudaStream_t st);
 int set_int(int32_t* p, int32_t v, cudaStream_t st);
+
+// ---- bf16 tensor-core GEMM (gemm_tc.cu): D[M,N] (+)= A*B (+bias); fp32 accumulate --------------------------------
+struct TcGemm {
+  int M, N, K;
+  const __nv_bfloat16* A; int lda; bool a_mn;   // a_mn=false: A[m*lda + k] (K-major); true: A[k*lda + m] (MN-major)
+  const __nv_bfloat16* B; int ldb; bool b_mn;   // b_mn=false: B[n*ldb + k] (K-major); true: B[k*ldb + n] (MN-major)
+  float* C; int ldc;                            // fp32 output (nullable)
+  __nv_bfloat16* Cb; int ldcb;                  // bf16 output (nullable)
+  const float* bias;                            // [N] or null
+  bool accumulate;                              // C += ...   (mandatory with splitk > 1: fp32 atomics)
+  int splitk;
+  RowMap rm;                                    // rows of A (K-major) and C; rm.Bt must be a multiple of 128
+  long a_rows_total;                            // rows of the allocation behind A when rm is used
+};
+int gemm_tc(const TcGemm& g, cudaStream_t st);
+int pick_splitk_tc(int M, int N, int K);
+int f32_to_bf16(const float* src, __nv_bfloat16* dst, long n, cudaStream_t st);
+int transpose_to_bf16(const float* src, int R, int C, __nv_bfloat16* dst, cudaStream_t st);   // dst[c*R+r] = src[r*C+c]
 
 // Philox4x32-10: 4 x uint32 for (seed, counter = (offset + idx))
 __device__ __forceinline__ void philox4x32(uint64_t seed, uint64_t ctr_lo, uint64_t ctr_hi, uint32_t out[4]) {
