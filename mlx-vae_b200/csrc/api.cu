@@ -16,7 +16,9 @@ static std::vector<Pair> g_free;       // recycled
 static int g_open[TIME_NCAT] = {0};
 static Pair g_cur[TIME_NCAT];
 void timing_begin(int cat, cudaStream_t st) {
-  if (!g_timing || g_open[cat]++ > 0) return;
+  if (!g_timing) return;
+  if (cat != TIME_RECURRENCE && g_open[TIME_RECURRENCE] > 0) return;   // attributed to the enclosing recurrence scope
+  if (g_open[cat]++ > 0) return;
   Pair p;
   if (!g_free.empty()) { p = g_free.back(); g_free.pop_back(); }
   else { cudaEventCreate(&p.a); cudaEventCreate(&p.b); }
@@ -25,7 +27,9 @@ void timing_begin(int cat, cudaStream_t st) {
   g_cur[cat] = p;
 }
 void timing_end(int cat, cudaStream_t st) {
-  if (!g_timing || --g_open[cat] > 0) return;
+  if (!g_timing) return;
+  if (cat != TIME_RECURRENCE && g_open[TIME_RECURRENCE] > 0) return;
+  if (--g_open[cat] > 0) return;
   cudaEventRecord(g_cur[cat].b, st);
   g_pairs.push_back(g_cur[cat]);
 }

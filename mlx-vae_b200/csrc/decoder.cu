@@ -23,9 +23,14 @@ struct DecPrep {
   float* bc[ARCVAE_MAX_LAYERS];   // [3H]
   float* table;                   // [V,3H]
   float* wc;                      // [3H,C]
+  __nv_bfloat16* Wxcb[ARCVAE_MAX_LAYERS];  // bf16 [3H,H], l >= 1
+  __nv_bfloat16* Woutb;                    // bf16 [V,H]
 };
 
 static void dec_prep_layout(const arcvae_dims& d, Arena& a, DecPrep* p) {
+  for (int l = 0; l < ARCVAE_MAX_LAYERS; l++) p->Wxcb[l] = nullptr;
+  for (int l = 1; l < d.NL; l++) p->Wxcb[l] = a.take<__nv_bfloat16>((size_t)3 * d.H * d.H);
+  p->Woutb = a.take<__nv_bfloat16>((size_t)d.V * d.H);
   for (int l = 0; l < d.NL; l++) {
     int D = (l == 0) ? d.E + d.C : d.H;
     p->Wxc[l] = a.take<float>((size_t)3 * d.H * D);
@@ -35,7 +40,8 @@ static void dec_prep_layout(const arcvae_dims& d, Arena& a, DecPrep* p) {
   p->wc = a.take<float>((size_t)3 * d.H * d.C);
 }
 
-static int dec_prepare(const arcvae_dims& d, const arcvae_decoder_params* p, const DecPrep& pr, cudaStream_t st) {
+static int dec_prepare(const arcvae_dims& d, const arcvae_decoder_params* p, const DecPrep& pr, int precision,
+                       cudaStream_t st) {
   RowMap id{nullptr, 1};
   const int H = d.H, H3 = 3 * d.H;
   for (int l = 0; l < d.NL; l++) {
@@ -46,6 +52,10 @@ static int dec_prepare(const arcvae_dims& d, const arcvae_decoder_params* p, con
   ARCVAE_TRY(gemm_f32(0, 1, d.V, H3, d.E, p->embedding, d.E, pr.Wxc[0], d.E + d.C, pr.table, H3, pr.bc[0], false, id, 1, st));
   ARCVAE_CUDA(cudaMemcpy2DAsync(pr.wc, (size_t)d.C * sizeof(float), pr.Wxc[0] + d.E, (size_t)(d.E + d.C) * sizeof(float),
                                 (size_t)d.C * sizeof(float), H3, cudaMemcpyDeviceToDevice, st));
+  if (precision == ARCVAE_PREC_BF16) {
+    for (int l = 1; l < d.NL; l++) ARCVAE_TRY(f32_to_bf16(pr.Wxc[l], pr.Wxcb[l], (long)H3 * H, st));
+    ARCVAE_TRY(f32_to_bf16(p->fc_out_w, pr.Woutb, (long)d.V * H, st));
+  }
   return 0;
 }
 
@@ -56,6 +66,7 @@ struct DecTape {
   float* G[ARCVAE_MAX_LAYERS];       // [R,3H], l >= 1
   int* tlists;                       // [2T] level lists + feedback lists
   uint8_t* mask;                     // [T]
+  __nv_bfloat16* hdb[ARCVAE_MAX_LAYERS];   // bf16 [R,H] copies (tensor-core operands)
 };
 
 static size_t dec_tape_layout(const arcvae_dims& d, int B, int T, void* base, size_t cap, DecTape* t) {
@@ -70,6 +81,7 @@ static size_t dec_tape_layout(const arcvae_dims& d, int B, int T, void* base, si
   }
   tt.tlists = a.take<int>((size_t)2 * T + 2);
   tt.mask = a.take<uint8_t>((size_t)T + 16);
+  for (int l = 0; l < d.NL; l++) tt.hdb[l] = a.take<__nv_bfloat16>(R * d.H);
   if (t) *t = tt;
   return align_up(a.off, 256);
 }
@@ -81,6 +93,8 @@ struct DecScratch {
   float* dWxc[ARCVAE_MAX_LAYERS];     // compact weight grads
   float* dbc[ARCVAE_MAX_LAYERS];
   float* dwc;                         // [3H,C]
+  __nv_bfloat16* dlb;                 // bf16 [R,V] copy of dlogits
+  __nv_bfloat16* dGb;                 // bf16 [R,3H] copy of the pre-activation gradients
 };
 
 static size_t dec_scratch_layout(const arcvae_dims& d, int B, int T, void* base, size_t cap, DecScratch* s) {
@@ -97,6 +111,8 @@ static size_t dec_scratch_layout(const arcvae_dims& d, int B, int T, void* base,
     ss.dbc[l] = a.take<float>((size_t)3 * d.H);
   }
   ss.dwc = a.take<float>((size_t)3 * d.H * d.C);
+  ss.dlb = a.take<__nv_bfloat16>(R * d.V);
+  ss.dGb = a.take<__nv_bfloat16>(R * 3 * d.H);
   if (s) *s = ss;
   return align_up(a.off, 256);
 }
@@ -115,15 +131,18 @@ __global__ void k_init_dec_inputs(const int32_t* __restrict__ target, const uint
 
 // one batched pass of the decoder stack over the rows selected by `rm`
 static int dec_stack_forward(const arcvae_dims& d, const arcvae_decoder_params* p, const DecPrep& pr, const float* cond,
-                             const int32_t* in_tok, int B, int nrows, RowMap rm, float* const* hd, float* const* G,
-                             float* logits, cudaStream_t st) {
+                             const int32_t* in_tok, int B, int nrows, RowMap rm, long rows_total, float* const* hd,
+                             __nv_bfloat16* const* hdb, float* const* G, float* logits, int precision, cudaStream_t st) {
   const int H = d.H, H3 = 3 * d.H;
-  ARCVAE_TRY(dec_cell0_fwd(pr.table, pr.wc, in_tok, cond, B, d.C, H, nrows, rm, hd[0], st));
+  const bool bf = precision == ARCVAE_PREC_BF16;
+  ARCVAE_TRY(dec_cell0_fwd(pr.table, pr.wc, in_tok, cond, B, d.C, H, nrows, rm, hd[0], bf ? hdb[0] : nullptr, st));
   for (int l = 1; l < d.NL; l++) {
-    ARCVAE_TRY(gemm_f32(0, 1, nrows, H3, H, hd[l - 1], H, pr.Wxc[l], H, G[l], H3, pr.bc[l], false, rm, 1, st));
-    ARCVAE_TRY(dec_cell_fwd(G[l], hd[l], H, nrows, rm, st));
+    ARCVAE_TRY(gemm_any(precision, 0, 1, nrows, H3, H, Mat{hd[l - 1], bf ? hdb[l - 1] : nullptr, H},
+                        Mat{pr.Wxc[l], pr.Wxcb[l], H}, G[l], H3, pr.bc[l], false, rm, rows_total, st));
+    ARCVAE_TRY(dec_cell_fwd(G[l], hd[l], bf ? hdb[l] : nullptr, H, nrows, rm, st));
   }
-  ARCVAE_TRY(gemm_f32(0, 1, nrows, d.V, H, hd[d.NL - 1], H, p->fc_out_w, H, logits, d.V, p->fc_out_b, false, rm, 1, st));
+  ARCVAE_TRY(gemm_any(precision, 0, 1, nrows, d.V, H, Mat{hd[d.NL - 1], bf ? hdb[d.NL - 1] : nullptr, H},
+                      Mat{p->fc_out_w, pr.Woutb, H}, logits, d.V, p->fc_out_b, false, rm, rows_total, st));
   return 0;
 }
 
@@ -151,7 +170,7 @@ extern "C" int arcvae_decoder_forward(const arcvae_dims* d, const arcvae_decoder
                                       int precision, void* stream) {
   ARCVAE_TRY(check_dims_dec(d));
   ARCVAE_REQUIRE(B > 0 && T > 0, "empty batch / sequence");
-  ARCVAE_REQUIRE(precision == ARCVAE_PREC_FP32, "decoder: only ARCVAE_PREC_FP32 is built in this version");
+  ARCVAE_REQUIRE(precision == ARCVAE_PREC_FP32 || precision == ARCVAE_PREC_BF16, "precision");
   ARCVAE_REQUIRE(logits_tm != nullptr, "logits output");
   cudaStream_t st = (cudaStream_t)stream;
   DecTape tp;
@@ -186,7 +205,7 @@ extern "C" int arcvae_decoder_forward(const arcvae_dims* d, const arcvae_decoder
   // pageable-source async copies are staged before returning, but be explicit: the vectors die with this frame
   ARCVAE_CUDA(cudaStreamSynchronize(st));
 
-  ARCVAE_TRY(dec_prepare(*d, p, tp.prep, st));
+  ARCVAE_TRY(dec_prepare(*d, p, tp.prep, precision, st));
   {
     long total = (long)T * B;
     int grid = (int)((total + 255) / 256);
@@ -197,7 +216,8 @@ extern "C" int arcvae_decoder_forward(const arcvae_dims* d, const arcvae_decoder
   for (int lv = 0; lv <= maxlevel; lv++) {
     RowMap rm{tp.tlists + off_t[lv], B};
     int nrows = n_t[lv] * B;
-    ARCVAE_TRY(dec_stack_forward(*d, p, tp.prep, cond, tp.in_tok, B, nrows, rm, tp.hd, tp.G, logits_tm, st));
+    ARCVAE_TRY(dec_stack_forward(*d, p, tp.prep, cond, tp.in_tok, B, nrows, rm, (long)T * B, tp.hd, tp.hdb, tp.G,
+                                 logits_tm, precision, st));
     ARCVAE_TRY(argmax_feedback(logits_tm, tp.tlists + off_f[lv], n_f[lv], B, d->V, tp.in_tok, st));
   }
   if (dec_inputs_tm != nullptr)
@@ -210,7 +230,7 @@ extern "C" int arcvae_decoder_backward(const arcvae_dims* d, const arcvae_decode
                                        const arcvae_decoder_params* g, void* scratch, size_t scratch_bytes,
                                        int precision, void* stream) {
   ARCVAE_TRY(check_dims_dec(d));
-  ARCVAE_REQUIRE(precision == ARCVAE_PREC_FP32, "decoder: only ARCVAE_PREC_FP32 is built in this version");
+  ARCVAE_REQUIRE(precision == ARCVAE_PREC_FP32 || precision == ARCVAE_PREC_BF16, "precision");
   ARCVAE_REQUIRE(g != nullptr && dlogits_tm != nullptr, "grad pointers");
   cudaStream_t st = (cudaStream_t)stream;
   DecTape tp;
@@ -224,20 +244,26 @@ extern "C" int arcvae_decoder_backward(const arcvae_dims* d, const arcvae_decode
   RowMap id{nullptr, 1};
   const int top = d->NL - 1;
 
+  const bool bf = precision == ARCVAE_PREC_BF16;
+  if (bf) ARCVAE_TRY(f32_to_bf16(dlogits_tm, sc.dlb, R * V, st));
   // fc_out: logits = h_top @ Wout^T + b
-  ARCVAE_TRY(gemm_f32(1, 0, V, H, (int)R, dlogits_tm, V, tp.hd[top], H, g->fc_out_w, H, nullptr, true, id, pick_splitk(V, H, (int)R), st));
+  ARCVAE_TRY(gemm_any(precision, 1, 0, V, H, (int)R, Mat{dlogits_tm, bf ? sc.dlb : nullptr, V},
+                      Mat{tp.hd[top], bf ? tp.hdb[top] : nullptr, H}, g->fc_out_w, H, nullptr, true, id, R, st));
   ARCVAE_TRY(colsum(dlogits_tm, R, V, V, g->fc_out_b, st));
   float* dh = sc.dh[0];
   float* dh_next = sc.dh[1];
-  ARCVAE_TRY(gemm_f32(0, 0, (int)R, H, V, dlogits_tm, V, p->fc_out_w, H, dh, H, nullptr, false, id, 1, st));
+  ARCVAE_TRY(gemm_any(precision, 0, 0, (int)R, H, V, Mat{dlogits_tm, bf ? sc.dlb : nullptr, V},
+                      Mat{p->fc_out_w, tp.prep.Woutb, H}, dh, H, nullptr, false, id, R, st));
 
   for (int l = top; l >= 1; l--) {
-    ARCVAE_TRY(dec_cell_bwd(tp.G[l], dh, H, R, st));  // G[l] <- dG
+    ARCVAE_TRY(dec_cell_bwd(tp.G[l], dh, bf ? sc.dGb : nullptr, H, R, st));  // G[l] <- dG
     ARCVAE_CUDA(cudaMemsetAsync(sc.dWxc[l], 0, (size_t)H3 * H * sizeof(float), st));
     ARCVAE_CUDA(cudaMemsetAsync(sc.dbc[l], 0, (size_t)H3 * sizeof(float), st));
-    ARCVAE_TRY(gemm_f32(1, 0, H3, H, (int)R, tp.G[l], H3, tp.hd[l - 1], H, sc.dWxc[l], H, nullptr, true, id, pick_splitk(H3, H, (int)R), st));
+    ARCVAE_TRY(gemm_any(precision, 1, 0, H3, H, (int)R, Mat{tp.G[l], bf ? sc.dGb : nullptr, H3},
+                        Mat{tp.hd[l - 1], bf ? tp.hdb[l - 1] : nullptr, H}, sc.dWxc[l], H, nullptr, true, id, R, st));
     ARCVAE_TRY(colsum(tp.G[l], R, H3, H3, sc.dbc[l], st));
-    ARCVAE_TRY(gemm_f32(0, 0, (int)R, H, H3, tp.G[l], H3, tp.prep.Wxc[l], H, dh_next, H, nullptr, false, id, 1, st));
+    ARCVAE_TRY(gemm_any(precision, 0, 0, (int)R, H, H3, Mat{tp.G[l], bf ? sc.dGb : nullptr, H3},
+                        Mat{tp.prep.Wxc[l], tp.prep.Wxcb[l], H}, dh_next, H, nullptr, false, id, R, st));
     ARCVAE_TRY(expand_gates_add(sc.dWxc[l], H, H, g->Wx[l], st));
     ARCVAE_TRY(expand_gates_add(sc.dbc[l], H, 1, g->bias[l], st));
     float* tmp = dh; dh = dh_next; dh_next = tmp;
@@ -269,6 +295,7 @@ struct SamplerWs {
   float* hd[ARCVAE_MAX_LAYERS];  // [B,H]
   float* G[ARCVAE_MAX_LAYERS];   // [B,3H]
   float* logits;     // [B,V]
+  __nv_bfloat16* hdb[ARCVAE_MAX_LAYERS];  // bf16 [B,H]
 };
 static size_t sampler_layout(const arcvae_dims& d, int B, void* base, size_t cap, SamplerWs* w) {
   Arena a(base, cap);
@@ -282,6 +309,7 @@ static size_t sampler_layout(const arcvae_dims& d, int B, void* base, size_t cap
     ww.G[l] = (l >= 1) ? a.take<float>((size_t)B * 3 * d.H) : nullptr;
   }
   ww.logits = a.take<float>((size_t)B * d.V);
+  for (int l = 0; l < d.NL; l++) ww.hdb[l] = a.take<__nv_bfloat16>((size_t)B * d.H);
   if (w) *w = ww;
   return align_up(a.off, 256);
 }
@@ -299,13 +327,13 @@ extern "C" int arcvae_sample(const arcvae_dims* d, const arcvae_decoder_params* 
   ARCVAE_TRY(check_dims_dec(d));
   ARCVAE_REQUIRE(B > 0 && max_length >= 0, "empty batch");
   ARCVAE_REQUIRE(temperature > 0.f, "temperature must be > 0");
-  ARCVAE_REQUIRE(precision == ARCVAE_PREC_FP32, "sampler: only ARCVAE_PREC_FP32 is built in this version");
+  ARCVAE_REQUIRE(precision == ARCVAE_PREC_FP32 || precision == ARCVAE_PREC_BF16, "precision");
   ARCVAE_REQUIRE(tokens != nullptr && t_stop != nullptr, "outputs");
   cudaStream_t st = (cudaStream_t)stream;
   SamplerWs ws;
   size_t need = sampler_layout(*d, B, workspace, workspace_bytes, &ws);
   ARCVAE_REQUIRE(workspace != nullptr && need <= workspace_bytes, "sampler workspace too small");
-  ARCVAE_TRY(dec_prepare(*d, p, ws.prep, st));
+  ARCVAE_TRY(dec_prepare(*d, p, ws.prep, precision, st));
   ARCVAE_CUDA(cudaMemsetAsync(ws.cur, 0, (size_t)B * sizeof(int32_t), st));      // start token 0 (decoder_sampling.py:78)
   ARCVAE_CUDA(cudaMemsetAsync(ws.ended, 0, (size_t)B * sizeof(int32_t), st));
   ARCVAE_CUDA(cudaMemsetAsync(ws.ended_count, 0, 4 * sizeof(int32_t), st));
@@ -315,7 +343,7 @@ extern "C" int arcvae_sample(const arcvae_dims* d, const arcvae_decoder_params* 
     // the reference checks `early_stopping and all(has_ended)` BEFORE each step (:87-88); the device records the first
     // such step in *t_stop and the host slices; later columns are scratch
     if (early_stopping && t > 0) ARCVAE_TRY(sampler_check_stop(ws.ended_count, B, t, t_stop, st));
-    ARCVAE_TRY(dec_stack_forward(*d, p, ws.prep, cond, ws.cur, B, B, id, ws.hd, ws.G, ws.logits, st));
+    ARCVAE_TRY(dec_stack_forward(*d, p, ws.prep, cond, ws.cur, B, B, id, B, ws.hd, ws.hdb, ws.G, ws.logits, precision, st));
     ARCVAE_TRY(select_token(ws.logits, B, d->V, temperature, multinomial, seed, t, max_length, d->end_token, tokens,
                             ws.cur, ws.ended, ws.ended_count, st));
   }

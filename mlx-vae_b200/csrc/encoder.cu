@@ -23,9 +23,13 @@ struct EncTape {
   float* lv_raw;     // [B,L]
   float* mu;         // [B,L]
   float* logvar;     // [B,L]
+  // bf16 copies for the tensor-core path (precision == ARCVAE_PREC_BF16)
+  __nv_bfloat16* hb[ARCVAE_MAX_LAYERS];    // [T*B,H]
+  __nv_bfloat16* Whb[ARCVAE_MAX_LAYERS];   // [4H,H]
+  __nv_bfloat16* Wxb[ARCVAE_MAX_LAYERS];   // [4H,H], l >= 1
 };
 
-static size_t enc_tape_layout(const arcvae_dims& d, int B, int T, void* base, size_t cap, EncTape* t) {
+static size_t enc_tape_layout(const arcvae_dims& d, int B, int T, int prec, void* base, size_t cap, EncTape* t) {
   Arena a(base, cap);
   size_t R = (size_t)T * B;
   EncTape tt;
@@ -42,6 +46,12 @@ static size_t enc_tape_layout(const arcvae_dims& d, int B, int T, void* base, si
   tt.lv_raw = a.take<float>((size_t)B * d.L);
   tt.mu = a.take<float>((size_t)B * d.L);
   tt.logvar = a.take<float>((size_t)B * d.L);
+  for (int l = 0; l < d.NL; l++) {
+    const bool bf = prec == ARCVAE_PREC_BF16;
+    tt.hb[l] = bf ? a.take<__nv_bfloat16>(R * d.H) : nullptr;
+    tt.Whb[l] = bf ? a.take<__nv_bfloat16>((size_t)4 * d.H * d.H) : nullptr;
+    tt.Wxb[l] = (bf && l >= 1) ? a.take<__nv_bfloat16>((size_t)4 * d.H * d.H) : nullptr;
+  }
   if (t) *t = tt;
   return align_up(a.off, 256);
 }
@@ -55,9 +65,10 @@ struct EncScratch {
   float* dh_rec[2]; // [B,H]
   float* dc;        // [B,H]
   float* dtable0;   // [V,4H]
+  __nv_bfloat16* dAb;   // [T*B,4H] bf16 copy of the pre-activation gradients (tensor-core operand)
 };
 
-static size_t enc_scratch_layout(const arcvae_dims& d, int B, int T, void* base, size_t cap, EncScratch* s) {
+static size_t enc_scratch_layout(const arcvae_dims& d, int B, int T, int prec, void* base, size_t cap, EncScratch* s) {
   Arena a(base, cap);
   EncScratch ss;
   ss.dmu_raw = a.take<float>((size_t)B * d.L);
@@ -69,6 +80,7 @@ static size_t enc_scratch_layout(const arcvae_dims& d, int B, int T, void* base,
   ss.dh_rec[1] = a.take<float>((size_t)B * d.H);
   ss.dc = a.take<float>((size_t)B * d.H);
   ss.dtable0 = a.take<float>((size_t)d.V * 4 * d.H);
+  ss.dAb = (prec == ARCVAE_PREC_BF16) ? a.take<__nv_bfloat16>((size_t)T * B * 4 * d.H) : nullptr;
   if (s) *s = ss;
   return align_up(a.off, 256);
 }
@@ -84,13 +96,14 @@ static int check_dims(const arcvae_dims* d) {
 
 using namespace arcvae;
 
+// sized for the larger (bf16) layout so one buffer serves either precision
 extern "C" size_t arcvae_encoder_tape_bytes(const arcvae_dims* d, int B, int T) {
   if (!d) return 0;
-  return enc_tape_layout(*d, B, T, nullptr, 0, nullptr);
+  return enc_tape_layout(*d, B, T, ARCVAE_PREC_BF16, nullptr, 0, nullptr);
 }
 extern "C" size_t arcvae_encoder_scratch_bytes(const arcvae_dims* d, int B, int T) {
   if (!d) return 0;
-  return enc_scratch_layout(*d, B, T, nullptr, 0, nullptr);
+  return enc_scratch_layout(*d, B, T, ARCVAE_PREC_BF16, nullptr, 0, nullptr);
 }
 
 extern "C" int arcvae_encoder_forward(const arcvae_dims* d, const arcvae_encoder_params* p, const int32_t* x,
@@ -98,10 +111,10 @@ extern "C" int arcvae_encoder_forward(const arcvae_dims* d, const arcvae_encoder
                                       size_t tape_bytes, int precision, void* stream) {
   ARCVAE_TRY(check_dims(d));
   ARCVAE_REQUIRE(B > 0 && T > 0, "empty batch / sequence");
-  ARCVAE_REQUIRE(precision == ARCVAE_PREC_FP32, "encoder: only ARCVAE_PREC_FP32 is built in this version");
+  ARCVAE_REQUIRE(precision == ARCVAE_PREC_FP32 || precision == ARCVAE_PREC_BF16, "precision");
   cudaStream_t st = (cudaStream_t)stream;
   EncTape tp;
-  size_t need = enc_tape_layout(*d, B, T, tape, tape_bytes, &tp);
+  size_t need = enc_tape_layout(*d, B, T, precision, tape, tape_bytes, &tp);
   ARCVAE_REQUIRE(tape != nullptr && need <= tape_bytes, "encoder tape too small");
   const int H = d->H, G4 = 4 * d->H;
   const long R = (long)T * B;
@@ -110,21 +123,33 @@ extern "C" int arcvae_encoder_forward(const arcvae_dims* d, const arcvae_encoder
   ARCVAE_TRY(transpose_tokens(x, B, T, tp.xT, st));
   // table0[v,:] = Emb[v,:] @ Wx0^T + b0   (encoder.py:93 gather + nn.LSTM's addmm folded: rows are tokens)
   ARCVAE_TRY(gemm_f32(0, 1, d->V, G4, d->E, p->embedding, d->E, p->Wx[0], d->E, tp.table0, G4, p->bias[0], false, id, 1, st));
+  const bool bf = precision == ARCVAE_PREC_BF16;
+  if (bf) {
+    for (int l = 0; l < d->NL; l++) {
+      ARCVAE_TRY(f32_to_bf16(p->Wh[l], tp.Whb[l], (long)G4 * H, st));
+      if (l >= 1) ARCVAE_TRY(f32_to_bf16(p->Wx[l], tp.Wxb[l], (long)G4 * H, st));
+    }
+  }
   for (int l = 0; l < d->NL; l++) {
     if (l == 0) {
       ARCVAE_TRY(gather_rows(tp.table0, tp.xT, (int)R, G4, tp.gates[0], st));
     } else {
-      ARCVAE_TRY(gemm_f32(0, 1, (int)R, G4, H, tp.h[l - 1], H, p->Wx[l], H, tp.gates[l], G4, p->bias[l], false, id, 1, st));
+      // time-parallel input projection of layer l: all T*B rows at once
+      ARCVAE_TRY(gemm_any(precision, 0, 1, (int)R, G4, H, Mat{tp.h[l - 1], tp.hb[l - 1], H}, Mat{p->Wx[l], tp.Wxb[l], H},
+                          tp.gates[l], G4, p->bias[l], false, id, R, st));
     }
+    TimeScope ts(TIME_RECURRENCE, st);
     for (int t = 0; t < T; t++) {
       float* g_t = tp.gates[l] + (long)t * B * G4;
       float* c_t = tp.c[l] + (long)t * B * H;
       float* h_t = tp.h[l] + (long)t * B * H;
+      __nv_bfloat16* hb_t = bf ? tp.hb[l] + (long)t * B * H : nullptr;
       if (t > 0) {
         // gates_t += h_{t-1} @ Wh^T   (nn.LSTM: `ifgo = ifgo + hidden @ Wh.T` once hidden is not None)
-        ARCVAE_TRY(gemm_f32(0, 1, B, G4, H, h_t - (long)B * H, H, p->Wh[l], H, g_t, G4, nullptr, true, id, 1, st));
+        ARCVAE_TRY(gemm_any(precision, 0, 1, B, G4, H, Mat{h_t - (long)B * H, bf ? hb_t - (long)B * H : nullptr, H},
+                            Mat{p->Wh[l], tp.Whb[l], H}, g_t, G4, nullptr, true, id, B, st));
       }
-      ARCVAE_TRY(lstm_cell_fwd(g_t, t > 0 ? c_t - (long)B * H : nullptr, c_t, h_t, B, H, st));
+      ARCVAE_TRY(lstm_cell_fwd(g_t, t > 0 ? c_t - (long)B * H : nullptr, c_t, h_t, hb_t, B, H, st));
     }
   }
   // head (encoder.py:106-130)
@@ -145,18 +170,19 @@ extern "C" int arcvae_encoder_backward(const arcvae_dims* d, const arcvae_encode
                                        const arcvae_encoder_params* g, void* scratch, size_t scratch_bytes,
                                        int precision, void* stream) {
   ARCVAE_TRY(check_dims(d));
-  ARCVAE_REQUIRE(precision == ARCVAE_PREC_FP32, "encoder: only ARCVAE_PREC_FP32 is built in this version");
+  ARCVAE_REQUIRE(precision == ARCVAE_PREC_FP32 || precision == ARCVAE_PREC_BF16, "precision");
   ARCVAE_REQUIRE(g != nullptr && dmu != nullptr && dlogvar != nullptr, "grad pointers");
   cudaStream_t st = (cudaStream_t)stream;
   EncTape tp;
-  size_t need = enc_tape_layout(*d, B, T, tape, tape_bytes, &tp);
+  size_t need = enc_tape_layout(*d, B, T, precision, tape, tape_bytes, &tp);
   ARCVAE_REQUIRE(tape != nullptr && need <= tape_bytes, "encoder tape too small");
   EncScratch sc;
-  size_t need_s = enc_scratch_layout(*d, B, T, scratch, scratch_bytes, &sc);
+  size_t need_s = enc_scratch_layout(*d, B, T, precision, scratch, scratch_bytes, &sc);
   ARCVAE_REQUIRE(scratch != nullptr && need_s <= scratch_bytes, "encoder scratch too small");
   const int H = d->H, G4 = 4 * d->H, L = d->L, H2 = 2 * d->H;
   const long R = (long)T * B;
   RowMap id{nullptr, 1};
+  const bool bf = precision == ARCVAE_PREC_BF16;
 
   // ---- head backward
   ARCVAE_TRY(head_bound_bwd(tp.mu, tp.logvar, dmu, dlogvar, (long)B * L, sc.dmu_raw, sc.dlv_raw, st));
@@ -181,6 +207,7 @@ extern "C" int arcvae_encoder_backward(const arcvae_dims* d, const arcvae_encode
   for (int l = d->NL - 1; l >= 0; l--) {
     ARCVAE_CUDA(cudaMemsetAsync(sc.dc, 0, (size_t)B * H * sizeof(float), st));
     const bool top = (l == d->NL - 1);
+    timing_begin(TIME_RECURRENCE, st);
     for (int t = T - 1; t >= 0; t--) {
       float* g_t = tp.gates[l] + (long)t * B * G4;
       const float* c_t = tp.c[l] + (long)t * B * H;
@@ -199,23 +226,29 @@ extern "C" int arcvae_encoder_backward(const arcvae_dims* d, const arcvae_encode
         dh_ext = sc.dX + (long)t * B * H;
       }
       const float* dh_rec = (t == T - 1) ? nullptr : sc.dh_rec[0];
-      ARCVAE_TRY(lstm_cell_bwd(g_t, c_t, t > 0 ? c_t - (long)B * H : nullptr, dh_ext, dh_rec, sc.dc, B, H, st));
+      __nv_bfloat16* dAb_t = bf ? sc.dAb + (long)t * B * G4 : nullptr;
+      ARCVAE_TRY(lstm_cell_bwd(g_t, c_t, t > 0 ? c_t - (long)B * H : nullptr, dh_ext, dh_rec, sc.dc, dAb_t, B, H, st));
       if (t > 0) {
         // d h_{t-1} (recurrent part) = dA_t @ Wh
-        ARCVAE_TRY(gemm_f32(0, 0, B, H, G4, g_t, G4, p->Wh[l], H, sc.dh_rec[0], H, nullptr, false, id, 1, st));
+        ARCVAE_TRY(gemm_any(precision, 0, 0, B, H, G4, Mat{g_t, dAb_t, G4}, Mat{p->Wh[l], tp.Whb[l], H}, sc.dh_rec[0], H,
+                            nullptr, false, id, B, st));
       }
     }
+    timing_end(TIME_RECURRENCE, st);
     float* dA = tp.gates[l];
     // dWh += dA[1:]^T @ h[:-1]
     if (T > 1) {
       long K = (long)(T - 1) * B;
-      ARCVAE_TRY(gemm_f32(1, 0, G4, H, (int)K, dA + (long)B * G4, G4, tp.h[l], H, g->Wh[l], H, nullptr, true, id, pick_splitk(G4, H, (int)K), st));
+      ARCVAE_TRY(gemm_any(precision, 1, 0, G4, H, (int)K, Mat{dA + (long)B * G4, bf ? sc.dAb + (long)B * G4 : nullptr, G4},
+                          Mat{tp.h[l], tp.hb[l], H}, g->Wh[l], H, nullptr, true, id, K, st));
     }
     if (l > 0) {
       ARCVAE_TRY(colsum(dA, R, G4, G4, g->bias[l], st));
       // dWx += dA^T @ h_{l-1} ; dX = dA @ Wx
-      ARCVAE_TRY(gemm_f32(1, 0, G4, H, (int)R, dA, G4, tp.h[l - 1], H, g->Wx[l], H, nullptr, true, id, pick_splitk(G4, H, (int)R), st));
-      ARCVAE_TRY(gemm_f32(0, 0, (int)R, H, G4, dA, G4, p->Wx[l], H, sc.dX, H, nullptr, false, id, 1, st));
+      ARCVAE_TRY(gemm_any(precision, 1, 0, G4, H, (int)R, Mat{dA, sc.dAb, G4}, Mat{tp.h[l - 1], tp.hb[l - 1], H}, g->Wx[l], H,
+                          nullptr, true, id, R, st));
+      ARCVAE_TRY(gemm_any(precision, 0, 0, (int)R, H, G4, Mat{dA, sc.dAb, G4}, Mat{p->Wx[l], tp.Wxb[l], H}, sc.dX, H, nullptr,
+                          false, id, R, st));
     } else {
       // layer 0: P0 = table0[x]  ->  dtable0 = onehot(x)^T @ dA ; table0 = Emb @ Wx0^T + b0
       ARCVAE_CUDA(cudaMemsetAsync(sc.dtable0, 0, (size_t)d->V * G4 * sizeof(float), st));

@@ -194,7 +194,7 @@ int gemm_f32(int transA, int transB, int M, int N, int K, const float* A, int ld
 // pick a split-K factor so that a weight-gradient shaped GEMM (few output tiles, long K) fills the 148 SMs
 int pick_splitk(int M, int N, int K) {
   long tiles = (long)cdiv(M, BM) * cdiv(N, BN);
-  if (tiles >= 2 * 148 || K <= 4 * BK) return 1;
+  if (tiles >= 148 || K <= 4 * BK) return 1;
   long want = (2 * 148 + tiles - 1) / tiles;
   long maxs = K / (8 * BK);
   if (maxs < 1) maxs = 1;

@@ -286,6 +286,8 @@ static int pick_bn(int N) {
   return ((N + 15) / 16) * 16;
 }
 
+int pick_splitk_tc(int M, int N, int K);
+
 int gemm_tc(const TcGemm& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return 0;
   ARCVAE_REQUIRE(g.C != nullptr || g.Cb != nullptr, "gemm_tc needs an output");
@@ -344,6 +346,32 @@ int gemm_tc(const TcGemm& g, cudaStream_t st) {
   gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, p);
   ARCVAE_LAUNCHED();
   return 0;
+}
+
+// precision dispatch: tensor cores when asked for and the operands fit the TMA constraints, else fp32 FFMA tiles
+static bool tma_ok(const void* p, int ld) { return p != nullptr && (ld % 8) == 0 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0); }
+
+int gemm_any(int precision, int transA, int transB, int M, int N, int K, Mat A, Mat B, float* C, int ldc,
+             const float* bias, bool accumulate, RowMap rm, long a_rows_total, cudaStream_t st) {
+  ARCVAE_REQUIRE(!(transA && transB), "gemm_any: (T,T) not supported");
+  bool tcok = precision == ARCVAE_PREC_BF16 && tma_ok(A.b, A.ld) && tma_ok(B.b, B.ld);
+  const bool b_mn = (transB == 0);
+  const bool a_mn = (transA != 0);
+  if (tcok && b_mn && !(N % 64 == 0 || N < 64)) tcok = false;
+  if (tcok && rm.tlist != nullptr && (rm.Bt % TC_BM) != 0) tcok = false;
+  if (tcok) {
+    TcGemm g;
+    g.M = M; g.N = N; g.K = K;
+    g.A = A.b; g.lda = A.ld; g.a_mn = a_mn;
+    g.B = B.b; g.ldb = B.ld; g.b_mn = b_mn;
+    g.C = C; g.ldc = ldc; g.Cb = nullptr; g.ldcb = 0; g.bias = bias; g.accumulate = accumulate;
+    g.splitk = accumulate ? pick_splitk_tc(M, N, K) : 1;
+    g.rm = rm; g.a_rows_total = a_rows_total;
+    return gemm_tc(g, st);
+  }
+  ARCVAE_REQUIRE(A.f != nullptr && B.f != nullptr, "gemm_any: fp32 operands missing for the fp32 path");
+  int sk = accumulate ? pick_splitk(M, N, K) : 1;
+  return gemm_f32(transA, transB, M, N, K, A.f, A.ld, B.f, B.ld, C, ldc, bias, accumulate, rm, sk, st);
 }
 
 // split-K factor for weight-gradient shapes: enough (tile, split) work items for ~2 per SM

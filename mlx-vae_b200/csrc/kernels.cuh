@@ -14,20 +14,20 @@ int gather_rows(const float* table, const int32_t* tok, int R, int N, float* out
 
 // LSTM cell, forward, in place: gates [Bn,4H] holds pre-activations (i,f,g,o) and receives the activated gates
 // (sigmoid(i), sigmoid(f), tanh(g), sigmoid(o)); c = f*c_prev + i*g (c_prev == nullptr: c = i*g); h = o*tanh(c)
-int lstm_cell_fwd(float* gates, const float* c_prev, float* c, float* h, int Bn, int H, cudaStream_t st);
+int lstm_cell_fwd(float* gates, const float* c_prev, float* c, float* h, __nv_bfloat16* hb, int Bn, int H, cudaStream_t st);
 // reverse of one step: gates (activated, in) -> dA (pre-activation grads, out, in place).
 // dh = dh_ext + dh_rec (either may be null); dc (in/out, [Bn,H]) carries dL/dc_t in and dL/dc_{t-1} out.
 int lstm_cell_bwd(float* gates, const float* c, const float* c_prev, const float* dh_ext, const float* dh_rec,
-                  float* dc, int Bn, int H, cudaStream_t st);
+                  float* dc, __nv_bfloat16* dAb, int Bn, int H, cudaStream_t st);
 
 // decoder cells (zero state: c = i*g, h = o*tanh(c); forget gate unused) on COMPACT gate layout [.., 3H] = (i,g,o)
 // layer 0: a = table[tok[r]] + cond[r % B] @ wc^T   (table [V,3H], wc [3H,C]); rows r = rm(i), i < R
 int dec_cell0_fwd(const float* table, const float* wc, const int32_t* tok, const float* cond, int B, int C, int H,
-                  int R, RowMap rm, float* h, cudaStream_t st);
+                  int R, RowMap rm, float* h, __nv_bfloat16* hb, cudaStream_t st);
 // layers >= 1: G [.,3H] pre-activation -> activated in place; h out
-int dec_cell_fwd(float* G, float* h, int H, int R, RowMap rm, cudaStream_t st);
+int dec_cell_fwd(float* G, float* h, __nv_bfloat16* hb, int H, int R, RowMap rm, cudaStream_t st);
 // backward: G activated (in) -> dG (out, in place) given dh [.,H]
-int dec_cell_bwd(float* G, const float* dh, int H, long R, cudaStream_t st);
+int dec_cell_bwd(float* G, const float* dh, __nv_bfloat16* dGb, int H, long R, cudaStream_t st);
 // layer 0 backward with recompute of the gates from the table: dG0 [R,3H] out
 int dec_cell0_bwd(const float* table, const float* wc, const int32_t* tok, const float* cond, int B, int C, int H,
                   long R, const float* dh, float* dG, cudaStream_t st);
@@ -83,6 +83,17 @@ int gemm_tc(const TcGemm& g, cudaStream_t st);
 int pick_splitk_tc(int M, int N, int K);
 int f32_to_bf16(const float* src, __nv_bfloat16* dst, long n, cudaStream_t st);
 int transpose_to_bf16(const float* src, int R, int C, __nv_bfloat16* dst, cudaStream_t st);   // dst[c*R+r] = src[r*C+c]
+
+// the same logical matrix in fp32 and (optionally) bf16; gemm_any picks the tensor-core kernel when precision is bf16
+// and the operands satisfy the TMA constraints, else the fp32 FFMA kernel on the fp32 copies
+struct Mat {
+  const float* f;
+  const __nv_bfloat16* b;
+  int ld;
+};
+// C[M,N] (+)= op(A) op(B) + bias; transA/transB as gemm_f32.  (1,1) is not supported.
+int gemm_any(int precision, int transA, int transB, int M, int N, int K, Mat A, Mat B, float* C, int ldc,
+             const float* bias, bool accumulate, RowMap rm, long a_rows_total, cudaStream_t st);
 
 // Philox4x32-10: 4 x uint32 for (seed, counter = (offset + idx))
 __device__ __forceinline__ void philox4x32(uint64_t seed, uint64_t ctr_lo, uint64_t ctr_hi, uint32_t out[4]) {

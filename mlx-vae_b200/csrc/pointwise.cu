@@ -50,7 +50,7 @@ int gather_rows(const float* table, const int32_t* tok, int R, int N, float* out
 
 // ------------------------------------------------------------------------------------------------
 __global__ void k_lstm_cell_fwd(float* __restrict__ gates, const float* __restrict__ c_prev, float* __restrict__ c,
-                                float* __restrict__ h, int Bn, int H) {
+                                float* __restrict__ h, __nv_bfloat16* __restrict__ hb, int Bn, int H) {
   long total = (long)Bn * H;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
     long b = idx / H;
@@ -64,18 +64,21 @@ __global__ void k_lstm_cell_fwd(float* __restrict__ gates, const float* __restri
     if (c_prev != nullptr) cn = fmaf(f_, c_prev[idx], cn);
     g[j] = i_; g[H + j] = f_; g[2 * H + j] = g_; g[3 * H + j] = o_;
     c[idx] = cn;
-    h[idx] = o_ * tanhf_(cn);
+    float hv = o_ * tanhf_(cn);
+    h[idx] = hv;
+    if (hb != nullptr) hb[idx] = __float2bfloat16(hv);
   }
 }
-int lstm_cell_fwd(float* gates, const float* c_prev, float* c, float* h, int Bn, int H, cudaStream_t st) {
-  k_lstm_cell_fwd<<<grid_for((long)Bn * H, 256), 256, 0, st>>>(gates, c_prev, c, h, Bn, H);
+int lstm_cell_fwd(float* gates, const float* c_prev, float* c, float* h, __nv_bfloat16* hb, int Bn, int H,
+                  cudaStream_t st) {
+  k_lstm_cell_fwd<<<grid_for((long)Bn * H, 256), 256, 0, st>>>(gates, c_prev, c, h, hb, Bn, H);
   ARCVAE_LAUNCHED();
   return 0;
 }
 
 __global__ void k_lstm_cell_bwd(float* __restrict__ gates, const float* __restrict__ c, const float* __restrict__ c_prev,
                                 const float* __restrict__ dh_ext, const float* __restrict__ dh_rec,
-                                float* __restrict__ dc, int Bn, int H) {
+                                float* __restrict__ dc, __nv_bfloat16* __restrict__ dAb, int Bn, int H) {
   long total = (long)Bn * H;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
     long b = idx / H;
@@ -92,16 +95,20 @@ __global__ void k_lstm_cell_bwd(float* __restrict__ gates, const float* __restri
     float d_i = dct * g_;
     float d_g = dct * i_;
     float d_f = dct * cp;
-    g[j] = d_i * i_ * (1.f - i_);
-    g[H + j] = d_f * f_ * (1.f - f_);
-    g[2 * H + j] = d_g * (1.f - g_ * g_);
-    g[3 * H + j] = d_o * o_ * (1.f - o_);
+    float a_i = d_i * i_ * (1.f - i_), a_f = d_f * f_ * (1.f - f_), a_g = d_g * (1.f - g_ * g_),
+          a_o = d_o * o_ * (1.f - o_);
+    g[j] = a_i; g[H + j] = a_f; g[2 * H + j] = a_g; g[3 * H + j] = a_o;
+    if (dAb != nullptr) {
+      __nv_bfloat16* gb = dAb + b * 4L * H;
+      gb[j] = __float2bfloat16(a_i); gb[H + j] = __float2bfloat16(a_f);
+      gb[2 * H + j] = __float2bfloat16(a_g); gb[3 * H + j] = __float2bfloat16(a_o);
+    }
     dc[idx] = dct * f_;
   }
 }
 int lstm_cell_bwd(float* gates, const float* c, const float* c_prev, const float* dh_ext, const float* dh_rec,
-                  float* dc, int Bn, int H, cudaStream_t st) {
-  k_lstm_cell_bwd<<<grid_for((long)Bn * H, 256), 256, 0, st>>>(gates, c, c_prev, dh_ext, dh_rec, dc, Bn, H);
+                  float* dc, __nv_bfloat16* dAb, int Bn, int H, cudaStream_t st) {
+  k_lstm_cell_bwd<<<grid_for((long)Bn * H, 256), 256, 0, st>>>(gates, c, c_prev, dh_ext, dh_rec, dc, dAb, Bn, H);
   ARCVAE_LAUNCHED();
   return 0;
 }
@@ -123,7 +130,7 @@ __device__ __forceinline__ void dec0_preact(const float* __restrict__ table, con
 
 __global__ void k_dec_cell0_fwd(const float* __restrict__ table, const float* __restrict__ wc,
                                 const int32_t* __restrict__ tok, const float* __restrict__ cond, int B, int C, int H,
-                                int R, RowMap rm, float* __restrict__ h) {
+                                int R, RowMap rm, float* __restrict__ h, __nv_bfloat16* __restrict__ hb) {
   long total = (long)R * H;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
     int i = (int)(idx / H);
@@ -133,18 +140,21 @@ __global__ void k_dec_cell0_fwd(const float* __restrict__ table, const float* __
     float ai, ag, ao;
     dec0_preact(table, wc, cond + (long)b * C, tok[r], C, H, j, ai, ag, ao);
     float cc = sigmoidf_(ai) * tanhf_(ag);
-    h[r * H + j] = sigmoidf_(ao) * tanhf_(cc);
+    float hv = sigmoidf_(ao) * tanhf_(cc);
+    h[r * H + j] = hv;
+    if (hb != nullptr) hb[r * H + j] = __float2bfloat16(hv);
   }
 }
 int dec_cell0_fwd(const float* table, const float* wc, const int32_t* tok, const float* cond, int B, int C, int H,
-                  int R, RowMap rm, float* h, cudaStream_t st) {
+                  int R, RowMap rm, float* h, __nv_bfloat16* hb, cudaStream_t st) {
   if (R <= 0) return 0;
-  k_dec_cell0_fwd<<<grid_for((long)R * H, 256), 256, 0, st>>>(table, wc, tok, cond, B, C, H, R, rm, h);
+  k_dec_cell0_fwd<<<grid_for((long)R * H, 256), 256, 0, st>>>(table, wc, tok, cond, B, C, H, R, rm, h, hb);
   ARCVAE_LAUNCHED();
   return 0;
 }
 
-__global__ void k_dec_cell_fwd(float* __restrict__ G, float* __restrict__ h, int H, int R, RowMap rm) {
+__global__ void k_dec_cell_fwd(float* __restrict__ G, float* __restrict__ h, __nv_bfloat16* __restrict__ hb, int H,
+                               int R, RowMap rm) {
   long total = (long)R * H;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
     int i = (int)(idx / H);
@@ -153,12 +163,14 @@ __global__ void k_dec_cell_fwd(float* __restrict__ G, float* __restrict__ h, int
     float* g = G + r * 3L * H;
     float i_ = sigmoidf_(g[j]), g_ = tanhf_(g[H + j]), o_ = sigmoidf_(g[2 * H + j]);
     g[j] = i_; g[H + j] = g_; g[2 * H + j] = o_;
-    h[r * H + j] = o_ * tanhf_(i_ * g_);
+    float hv = o_ * tanhf_(i_ * g_);
+    h[r * H + j] = hv;
+    if (hb != nullptr) hb[r * H + j] = __float2bfloat16(hv);
   }
 }
-int dec_cell_fwd(float* G, float* h, int H, int R, RowMap rm, cudaStream_t st) {
+int dec_cell_fwd(float* G, float* h, __nv_bfloat16* hb, int H, int R, RowMap rm, cudaStream_t st) {
   if (R <= 0) return 0;
-  k_dec_cell_fwd<<<grid_for((long)R * H, 256), 256, 0, st>>>(G, h, H, R, rm);
+  k_dec_cell_fwd<<<grid_for((long)R * H, 256), 256, 0, st>>>(G, h, hb, H, R, rm);
   ARCVAE_LAUNCHED();
   return 0;
 }
@@ -173,7 +185,8 @@ __device__ __forceinline__ void dec_cell_grads(float i_, float g_, float o_, flo
   dag = dcc * i_ * (1.f - g_ * g_);
 }
 
-__global__ void k_dec_cell_bwd(float* __restrict__ G, const float* __restrict__ dh, int H, long R) {
+__global__ void k_dec_cell_bwd(float* __restrict__ G, const float* __restrict__ dh, __nv_bfloat16* __restrict__ dGb,
+                               int H, long R) {
   long total = R * H;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
     long r = idx / H;
@@ -182,10 +195,14 @@ __global__ void k_dec_cell_bwd(float* __restrict__ G, const float* __restrict__ 
     float dai, dag, dao;
     dec_cell_grads(g[j], g[H + j], g[2 * H + j], dh[idx], dai, dag, dao);
     g[j] = dai; g[H + j] = dag; g[2 * H + j] = dao;
+    if (dGb != nullptr) {
+      __nv_bfloat16* gb = dGb + r * 3L * H;
+      gb[j] = __float2bfloat16(dai); gb[H + j] = __float2bfloat16(dag); gb[2 * H + j] = __float2bfloat16(dao);
+    }
   }
 }
-int dec_cell_bwd(float* G, const float* dh, int H, long R, cudaStream_t st) {
-  k_dec_cell_bwd<<<grid_for(R * H, 256), 256, 0, st>>>(G, dh, H, R);
+int dec_cell_bwd(float* G, const float* dh, __nv_bfloat16* dGb, int H, long R, cudaStream_t st) {
+  k_dec_cell_bwd<<<grid_for(R * H, 256), 256, 0, st>>>(G, dh, dGb, H, R);
   ARCVAE_LAUNCHED();
   return 0;
 }

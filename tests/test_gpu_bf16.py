@@ -1,0 +1,117 @@
+"""GPU tests of precision='bf16' (tcgen05 tensor-core contractions with bf16 operands, fp32 accumulation; all
+pointwise math, the loss and Adam stay fp32).
+
+STATED bf16 TOLERANCE (north_star: "a stated bf16 tolerance applies to the tensor-core projections"):
+  logits, mu/logvar, loss scalars : 2e-2 relative to the largest magnitude of the tensor (measured ~3e-3)
+  gradients                       : 5e-2 relative to the largest magnitude of the tensor (measured ~1e-2)
+Operands are rounded to bf16 (2^-9 relative) before each contraction; accumulation is fp32."""
+import numpy as np
+import pytest
+import torch
+
+import arcvae_oracle as O
+from _util import golden_cfg, golden_hyper, golden_params, load_golden, model_kwargs, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL_FWD, TOL_GRAD = 2e-2, 5e-2
+
+
+@pytest.fixture(scope="module")
+def M():
+    import mlx_vae_b200
+    return mlx_vae_b200
+
+
+def cuda(a):
+    return torch.as_tensor(np.asarray(a)).cuda()
+
+
+@pytest.mark.parametrize("name", ["default_b8", "default_b8_sharp"])
+def test_bf16_step_within_stated_tolerance_of_fp64_fixture(M, name):
+    g = load_golden(name)
+    cfg = golden_cfg(g); p = golden_params(g); kw = model_kwargs(cfg); hyper = golden_hyper(g)
+    enc = M.MLXEncoder(**kw, precision="bf16").load_parameters(p["encoder"])
+    dec = M.MLXAutoregressiveDecoder(**kw, precision="bf16").load_parameters(p["decoder"])
+    x, c, e = cuda(g["x"]), cuda(g["cond"]), cuda(g["eps"])
+    # teacher-forced everywhere: greedy feedback on bf16 logits may legitimately flip near-ties (checked separately)
+    mask = np.ones(int(g["T"]), dtype=bool)
+    xt = torch.as_tensor(g["x"]); ct = torch.as_tensor(g["cond"]).double(); et = torch.as_tensor(g["eps"]).double()
+    vals, (ge, gd) = O.loss_and_grads(p, xt, ct, cfg.num_layers, et, mask, **hyper)
+    d, (g_enc, g_dec) = M.loss_and_grad(enc, dec, None, x, c, eps=e, tf_mask=mask, **hyper)
+    errs = {}
+    for k in ("total_loss", "recon_loss", "kl_loss", "mutual_info"):
+        errs[k] = abs(float(d[k]) - float(vals[k])) / max(abs(float(vals[k])), 1e-3)
+        assert errs[k] < TOL_FWD, (k, errs[k])
+    errs["mu"] = rel_err(d["mu"].cpu(), vals["mu"]); assert errs["mu"] < TOL_FWD
+    for tree, ref, tag in ((g_enc, ge, "enc"), (g_dec, gd, "dec")):
+        for mod, leaves in ref.items():
+            for leaf, r in leaves.items():
+                got = tree[mod][leaf].double().cpu()
+                scale = float(r.abs().max())
+                if scale == 0.0:
+                    assert float(got.abs().max()) == 0.0, (mod, leaf)
+                    continue
+                err = float((got - r).abs().max()) / scale
+                errs[f"{tag}.{mod}.{leaf}"] = err
+                assert err < TOL_GRAD, (tag, mod, leaf, err)
+    print("bf16 errors vs fp64 oracle:", {k: f"{v:.2e}" for k, v in sorted(errs.items(), key=lambda kv: -kv[1])[:8]})
+    lg = dec(None, c, target_seq=x, tf_mask=mask)
+    ref_lg = O.decoder_forward(p["decoder"], None if False else torch.zeros(1), ct, cfg.num_layers, target_seq=xt, tf_mask=mask) \
+        if False else vals["logits"]
+    assert rel_err(lg.cpu(), ref_lg) < TOL_FWD
+
+
+def test_bf16_matches_fp32_path_at_tile_aligned_batch(M):
+    """B multiple of 128 so the row-mapped decoder levels also run on the tensor cores; includes greedy feedback."""
+    cfg = O.Config()
+    B, T = 256, 24
+    x, cond, eps, tf_mask = O.synthetic_batch(B, T, cfg, seed=5, tf_ratio=0.7)
+    p = O.init_params(cfg, seed=9, dtype=torch.float32)
+    p["decoder"] = O.tree_map(lambda t: t * 4.0, p["decoder"])
+    kw = model_kwargs(cfg)
+    hyper = dict(beta=0.05, lambda_prop=0.1, lambda_collapse=0.001, free_bits=1.0, lambda_mi=0.01, target_mi=4.85)
+    out = {}
+    for prec in ("fp32", "bf16"):
+        enc = M.MLXEncoder(**kw, precision=prec).load_parameters(p["encoder"])
+        dec = M.MLXAutoregressiveDecoder(**kw, precision=prec).load_parameters(p["decoder"])
+        d, (ge, gd) = M.loss_and_grad(enc, dec, None, cuda(x), cuda(cond), eps=cuda(eps), tf_mask=tf_mask, **hyper)
+        lg = dec(None, cuda(cond), target_seq=cuda(x), tf_mask=tf_mask).clone()
+        out[prec] = (d, {k: v.clone() for k, v in O.tree_flatten({"e": ge, "d": gd}).items()}, lg, dec.last_inputs.clone())
+    d32, g32, l32, i32 = out["fp32"]; d16, g16, l16, i16 = out["bf16"]
+    agree = float((i32 == i16).float().mean())
+    assert agree > 0.99, f"decoder input tokens agree on {agree:.4f}"
+    same = (i32 == i16).all(dim=1)
+    # compare logits on positions whose input token agrees
+    m = (i32 == i16).unsqueeze(-1)
+    assert float(((l32 - l16).abs() * m).max()) / float(l32.abs().max()) < TOL_FWD
+    for k in ("total_loss", "recon_loss", "kl_loss"):
+        assert abs(float(d32[k]) - float(d16[k])) / abs(float(d32[k])) < TOL_FWD
+    worst = 0.0
+    for n in g32:
+        s = float(g32[n].abs().max())
+        if s == 0.0:
+            assert float(g16[n].abs().max()) == 0.0
+            continue
+        worst = max(worst, float((g32[n] - g16[n]).abs().max()) / s)
+    assert worst < 2 * TOL_GRAD, worst     # a few flipped feedback tokens move the decoder gradients slightly
+    print("bf16 vs fp32 worst gradient rel err:", worst, "token agreement:", agree)
+
+
+def test_bf16_full_size_step_runs_and_is_sane(M):
+    cfg = O.Config()
+    B, T = 4096, 128
+    x, cond, eps, tf_mask = O.synthetic_batch(B, T, cfg, seed=67, tf_ratio=0.9)
+    kw = model_kwargs(cfg)
+    res = {}
+    for prec in ("fp32", "bf16"):
+        enc = M.MLXEncoder(**kw, seed=1, precision=prec); dec = M.MLXAutoregressiveDecoder(**kw, seed=2, precision=prec)
+        d, (ge, gd) = M.loss_and_grad(enc, dec, None, cuda(x), cuda(cond), eps=cuda(eps), tf_mask=tf_mask, beta=0.05,
+                                      lambda_collapse=0.001, free_bits=1.0, lambda_mi=0.01)
+        res[prec] = ({k: float(d[k]) for k in M._lib.LOSS_KEYS}, ge["lstm_layer_0"]["Wh"].clone(), gd["fc_out"]["weight"].clone(),
+                     ge["embedding"]["weight"].clone())
+    for k in ("total_loss", "recon_loss", "kl_loss", "mutual_info"):
+        a, b = res["fp32"][0][k], res["bf16"][0][k]
+        assert abs(a - b) / max(abs(a), 1e-3) < TOL_FWD, (k, a, b)
+    for i in (1, 2, 3):
+        a, b = res["fp32"][i], res["bf16"][i]
+        assert float((a - b).abs().max()) / float(a.abs().max()) < TOL_GRAD, i
