@@ -135,7 +135,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--precision", default=os.environ.get("ARCVAE_PRECISION", "fp32"))
+    ap.add_argument("--precision", default=os.environ.get("ARCVAE_PRECISION", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
