@@ -116,6 +116,10 @@ int arcvae_encoder_backward(const arcvae_dims* d, const arcvae_encoder_params* p
                             const arcvae_encoder_params* g, void* scratch, size_t scratch_bytes, int precision,
                             void* stream);
 
+/* returns non-zero if a persistent cluster kernel of the last forward/backward hit a barrier time-out
+ * (bounded waits instead of hangs).  Synchronises the stream.  Test / debug aid. */
+int arcvae_encoder_check(const arcvae_dims* d, int B, int T, void* tape, size_t tape_bytes, int precision, void* stream);
+
 /* ---- reparameterize: models/encoder.py:134-155 ---------------------------------------------- */
 /* z = mu + eps*exp(0.5*logvar); eps==NULL draws N(0,1) from Philox4x32-10(seed, offset) */
 int arcvae_reparameterize(const float* mu, const float* logvar, const float* eps, int B, int L, uint64_t seed,

@@ -3,55 +3,86 @@
 // Internal layout is TIME-MAJOR: row r = t*B + b, so the rows of one timestep are contiguous.
 //   layer 0 input projection  = gather of table0 = Emb @ Wx0^T + b0  ([V,4H]; V=80 rows make the product a table)
 //   layer l>0 input projection = H_{l-1} @ Wx_l^T + b_l               (time-parallel GEMM over all T*B rows)
-//   recurrence                 = per step: gates_t += h_{t-1} @ Wh^T, LSTM cell (MLX nn.LSTM semantics: zero initial
-//                                state, gate order i,f,g,o, c_0 = i*g)
+//   recurrence                 = MLX nn.LSTM semantics: zero initial state, gate order i,f,g,o, c_0 = i*g
 //   head                       = [h_T ; Linear(cond)] -> fc_mu / fc_logvar(_hidden) -> tanh bounds
-// precision == ARCVAE_PREC_FP32 runs every contraction as fp32 FFMA tiles (gemm_f32.cu).
+// Three execution paths, same math:
+//   ARCVAE_PREC_FP32            per-step fp32 FFMA GEMM + cell kernels (reference precision)
+//   ARCVAE_PREC_BF16, H != 256  per-step tcgen05 GEMM + cell kernels
+//   ARCVAE_PREC_BF16, H == 256  persistent cluster kernel per layer and direction (lstm_cluster.cu): W_hh resident in
+//                               shared memory for all T steps, bf16 tape (gates, h, dA), fp32 cell state
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace arcvae {
 
+using bf16 = __nv_bfloat16;
+
+enum { PATH_STEP_F32 = 0, PATH_STEP_BF16 = 1, PATH_CLUSTER = 2 };
+
+static int pick_path(const arcvae_dims& d, int precision) {
+  if (precision != ARCVAE_PREC_BF16) return PATH_STEP_F32;
+  const bool no_cluster = std::getenv("ARCVAE_NO_CLUSTER") != nullptr;   // read per call: tests flip it
+  if (lstm_cluster_supported(d.H) && !no_cluster) return PATH_CLUSTER;
+  return PATH_STEP_BF16;
+}
+
 struct EncTape {
   int32_t* xT;       // [T,B]
   float* table0;     // [V,4H]
-  float* gates[ARCVAE_MAX_LAYERS];  // [T*B,4H]  activated gates after forward, dA after backward
-  float* c[ARCVAE_MAX_LAYERS];      // [T*B,H]
-  float* h[ARCVAE_MAX_LAYERS];      // [T*B,H]
   float* u;          // [B,2H]
   float* lvh;        // [B,2H]  tanh(fc_logvar_hidden(u))
   float* mu_raw;     // [B,L]
   float* lv_raw;     // [B,L]
   float* mu;         // [B,L]
   float* logvar;     // [B,L]
-  // bf16 copies for the tensor-core path (precision == ARCVAE_PREC_BF16)
-  __nv_bfloat16* hb[ARCVAE_MAX_LAYERS];    // [T*B,H]
-  __nv_bfloat16* Whb[ARCVAE_MAX_LAYERS];   // [4H,H]
-  __nv_bfloat16* Wxb[ARCVAE_MAX_LAYERS];   // [4H,H], l >= 1
+  float* h_last;     // [B,H]   h_{T-1} of the top layer (cluster path)
+  int* err;          // device flag raised by the cluster kernels' bounded waits
+  float* c[ARCVAE_MAX_LAYERS];      // [T*B,H] fp32 cell state (all paths)
+  // per-step paths
+  float* gates[ARCVAE_MAX_LAYERS];  // [T*B,4H]  activated gates after forward, dA after backward
+  float* h[ARCVAE_MAX_LAYERS];      // [T*B,H]
+  // bf16 paths
+  bf16* hb[ARCVAE_MAX_LAYERS];      // [T*B,H]
+  bf16* Whb[ARCVAE_MAX_LAYERS];     // [4H,H]
+  bf16* Wxb[ARCVAE_MAX_LAYERS];     // [4H,H], l >= 1
+  // cluster path
+  bf16* gates_b[ARCVAE_MAX_LAYERS]; // [T*B,4H] activated gates
+  bf16* WhTb[ARCVAE_MAX_LAYERS];    // [H,4H]
+  bf16* Pb;                         // [T*B,4H] input projection of the layer being run (reused)
 };
 
-static size_t enc_tape_layout(const arcvae_dims& d, int B, int T, int prec, void* base, size_t cap, EncTape* t) {
+static size_t enc_tape_layout(const arcvae_dims& d, int B, int T, int path, void* base, size_t cap, EncTape* t) {
   Arena a(base, cap);
-  size_t R = (size_t)T * B;
-  EncTape tt;
+  const size_t R = (size_t)T * B, H = d.H;
+  EncTape tt{};
   tt.xT = a.take<int32_t>(R);
-  tt.table0 = a.take<float>((size_t)d.V * 4 * d.H);
-  for (int l = 0; l < d.NL; l++) {
-    tt.gates[l] = a.take<float>(R * 4 * d.H);
-    tt.c[l] = a.take<float>(R * d.H);
-    tt.h[l] = a.take<float>(R * d.H);
-  }
-  tt.u = a.take<float>((size_t)B * 2 * d.H);
-  tt.lvh = a.take<float>((size_t)B * 2 * d.H);
+  tt.table0 = a.take<float>((size_t)d.V * 4 * H);
+  tt.u = a.take<float>((size_t)B * 2 * H);
+  tt.lvh = a.take<float>((size_t)B * 2 * H);
   tt.mu_raw = a.take<float>((size_t)B * d.L);
   tt.lv_raw = a.take<float>((size_t)B * d.L);
   tt.mu = a.take<float>((size_t)B * d.L);
   tt.logvar = a.take<float>((size_t)B * d.L);
+  tt.h_last = a.take<float>((size_t)B * H);
+  tt.err = a.take<int>(4);
   for (int l = 0; l < d.NL; l++) {
-    const bool bf = prec == ARCVAE_PREC_BF16;
-    tt.hb[l] = bf ? a.take<__nv_bfloat16>(R * d.H) : nullptr;
-    tt.Whb[l] = bf ? a.take<__nv_bfloat16>((size_t)4 * d.H * d.H) : nullptr;
-    tt.Wxb[l] = (bf && l >= 1) ? a.take<__nv_bfloat16>((size_t)4 * d.H * d.H) : nullptr;
+    tt.c[l] = a.take<float>(R * H);
+    if (path != PATH_CLUSTER) {
+      tt.gates[l] = a.take<float>(R * 4 * H);
+      tt.h[l] = a.take<float>(R * H);
+    }
+    if (path != PATH_STEP_F32) {
+      tt.hb[l] = a.take<bf16>(R * H);
+      tt.Whb[l] = a.take<bf16>(4 * H * H);
+      if (l >= 1) tt.Wxb[l] = a.take<bf16>(4 * H * H);
+    }
+    if (path == PATH_CLUSTER) {
+      tt.gates_b[l] = a.take<bf16>(R * 4 * H);
+      tt.WhTb[l] = a.take<bf16>(4 * H * H);
+    }
   }
+  if (path == PATH_CLUSTER) tt.Pb = a.take<bf16>(R * 4 * H);
   if (t) *t = tt;
   return align_up(a.off, 256);
 }
@@ -65,12 +96,12 @@ struct EncScratch {
   float* dh_rec[2]; // [B,H]
   float* dc;        // [B,H]
   float* dtable0;   // [V,4H]
-  __nv_bfloat16* dAb;   // [T*B,4H] bf16 copy of the pre-activation gradients (tensor-core operand)
+  bf16* dAb;        // [T*B,4H] bf16 pre-activation gradients (tensor-core operand / cluster exchange)
 };
 
-static size_t enc_scratch_layout(const arcvae_dims& d, int B, int T, int prec, void* base, size_t cap, EncScratch* s) {
+static size_t enc_scratch_layout(const arcvae_dims& d, int B, int T, int path, void* base, size_t cap, EncScratch* s) {
   Arena a(base, cap);
-  EncScratch ss;
+  EncScratch ss{};
   ss.dmu_raw = a.take<float>((size_t)B * d.L);
   ss.dlv_raw = a.take<float>((size_t)B * d.L);
   ss.dlvh = a.take<float>((size_t)B * 2 * d.H);
@@ -80,7 +111,7 @@ static size_t enc_scratch_layout(const arcvae_dims& d, int B, int T, int prec, v
   ss.dh_rec[1] = a.take<float>((size_t)B * d.H);
   ss.dc = a.take<float>((size_t)B * d.H);
   ss.dtable0 = a.take<float>((size_t)d.V * 4 * d.H);
-  ss.dAb = (prec == ARCVAE_PREC_BF16) ? a.take<__nv_bfloat16>((size_t)T * B * 4 * d.H) : nullptr;
+  ss.dAb = (path != PATH_STEP_F32) ? a.take<bf16>((size_t)T * B * 4 * d.H) : nullptr;
   if (s) *s = ss;
   return align_up(a.off, 256);
 }
@@ -92,99 +123,28 @@ static int check_dims(const arcvae_dims* d) {
   return 0;
 }
 
-}  // namespace arcvae
-
-using namespace arcvae;
-
-// sized for the larger (bf16) layout so one buffer serves either precision
-extern "C" size_t arcvae_encoder_tape_bytes(const arcvae_dims* d, int B, int T) {
-  if (!d) return 0;
-  return enc_tape_layout(*d, B, T, ARCVAE_PREC_BF16, nullptr, 0, nullptr);
-}
-extern "C" size_t arcvae_encoder_scratch_bytes(const arcvae_dims* d, int B, int T) {
-  if (!d) return 0;
-  return enc_scratch_layout(*d, B, T, ARCVAE_PREC_BF16, nullptr, 0, nullptr);
-}
-
-extern "C" int arcvae_encoder_forward(const arcvae_dims* d, const arcvae_encoder_params* p, const int32_t* x,
-                                      const float* cond, int B, int T, float* mu, float* logvar, void* tape,
-                                      size_t tape_bytes, int precision, void* stream) {
-  ARCVAE_TRY(check_dims(d));
-  ARCVAE_REQUIRE(B > 0 && T > 0, "empty batch / sequence");
-  ARCVAE_REQUIRE(precision == ARCVAE_PREC_FP32 || precision == ARCVAE_PREC_BF16, "precision");
-  cudaStream_t st = (cudaStream_t)stream;
-  EncTape tp;
-  size_t need = enc_tape_layout(*d, B, T, precision, tape, tape_bytes, &tp);
-  ARCVAE_REQUIRE(tape != nullptr && need <= tape_bytes, "encoder tape too small");
-  const int H = d->H, G4 = 4 * d->H;
-  const long R = (long)T * B;
+// ---- head: encoder.py:106-130 and its reverse ----------------------------------------------------------------------
+static int head_forward(const arcvae_dims& d, const arcvae_encoder_params* p, const EncTape& tp, const float* h_last,
+                        const float* cond, int B, float* mu, float* logvar, cudaStream_t st) {
+  const int H = d.H;
   RowMap id{nullptr, 1};
-
-  ARCVAE_TRY(transpose_tokens(x, B, T, tp.xT, st));
-  // table0[v,:] = Emb[v,:] @ Wx0^T + b0   (encoder.py:93 gather + nn.LSTM's addmm folded: rows are tokens)
-  ARCVAE_TRY(gemm_f32(0, 1, d->V, G4, d->E, p->embedding, d->E, p->Wx[0], d->E, tp.table0, G4, p->bias[0], false, id, 1, st));
-  const bool bf = precision == ARCVAE_PREC_BF16;
-  if (bf) {
-    for (int l = 0; l < d->NL; l++) {
-      ARCVAE_TRY(f32_to_bf16(p->Wh[l], tp.Whb[l], (long)G4 * H, st));
-      if (l >= 1) ARCVAE_TRY(f32_to_bf16(p->Wx[l], tp.Wxb[l], (long)G4 * H, st));
-    }
-  }
-  for (int l = 0; l < d->NL; l++) {
-    if (l == 0) {
-      ARCVAE_TRY(gather_rows(tp.table0, tp.xT, (int)R, G4, tp.gates[0], st));
-    } else {
-      // time-parallel input projection of layer l: all T*B rows at once
-      ARCVAE_TRY(gemm_any(precision, 0, 1, (int)R, G4, H, Mat{tp.h[l - 1], tp.hb[l - 1], H}, Mat{p->Wx[l], tp.Wxb[l], H},
-                          tp.gates[l], G4, p->bias[l], false, id, R, st));
-    }
-    TimeScope ts(TIME_RECURRENCE, st);
-    for (int t = 0; t < T; t++) {
-      float* g_t = tp.gates[l] + (long)t * B * G4;
-      float* c_t = tp.c[l] + (long)t * B * H;
-      float* h_t = tp.h[l] + (long)t * B * H;
-      __nv_bfloat16* hb_t = bf ? tp.hb[l] + (long)t * B * H : nullptr;
-      if (t > 0) {
-        // gates_t += h_{t-1} @ Wh^T   (nn.LSTM: `ifgo = ifgo + hidden @ Wh.T` once hidden is not None)
-        ARCVAE_TRY(gemm_any(precision, 0, 1, B, G4, H, Mat{h_t - (long)B * H, bf ? hb_t - (long)B * H : nullptr, H},
-                            Mat{p->Wh[l], tp.Whb[l], H}, g_t, G4, nullptr, true, id, B, st));
-      }
-      ARCVAE_TRY(lstm_cell_fwd(g_t, t > 0 ? c_t - (long)B * H : nullptr, c_t, h_t, hb_t, B, H, st));
-    }
-  }
-  // head (encoder.py:106-130)
-  const float* h_last = tp.h[d->NL - 1] + (long)(T - 1) * B * H;
-  ARCVAE_TRY(head_build_u(h_last, cond, p->condition_fc_w, p->condition_fc_b, B, H, d->C, tp.u, st));
-  ARCVAE_TRY(gemm_f32(0, 1, B, d->L, 2 * H, tp.u, 2 * H, p->fc_mu_w, 2 * H, tp.mu_raw, d->L, p->fc_mu_b, false, id, 1, st));
+  ARCVAE_TRY(head_build_u(h_last, cond, p->condition_fc_w, p->condition_fc_b, B, H, d.C, tp.u, st));
+  ARCVAE_TRY(gemm_f32(0, 1, B, d.L, 2 * H, tp.u, 2 * H, p->fc_mu_w, 2 * H, tp.mu_raw, d.L, p->fc_mu_b, false, id, 1, st));
   ARCVAE_TRY(gemm_f32(0, 1, B, 2 * H, 2 * H, tp.u, 2 * H, p->fc_logvar_hidden_w, 2 * H, tp.lvh, 2 * H, p->fc_logvar_hidden_b, false, id, 1, st));
   ARCVAE_TRY(tanh_inplace(tp.lvh, (long)B * 2 * H, st));
-  ARCVAE_TRY(gemm_f32(0, 1, B, d->L, 2 * H, tp.lvh, 2 * H, p->fc_logvar_w, 2 * H, tp.lv_raw, d->L, p->fc_logvar_b, false, id, 1, st));
-  ARCVAE_TRY(head_bound(tp.mu_raw, tp.lv_raw, (long)B * d->L, tp.mu, tp.logvar, st));
-  if (mu) ARCVAE_CUDA(cudaMemcpyAsync(mu, tp.mu, (size_t)B * d->L * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  if (logvar) ARCVAE_CUDA(cudaMemcpyAsync(logvar, tp.logvar, (size_t)B * d->L * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  ARCVAE_TRY(gemm_f32(0, 1, B, d.L, 2 * H, tp.lvh, 2 * H, p->fc_logvar_w, 2 * H, tp.lv_raw, d.L, p->fc_logvar_b, false, id, 1, st));
+  ARCVAE_TRY(head_bound(tp.mu_raw, tp.lv_raw, (long)B * d.L, tp.mu, tp.logvar, st));
+  if (mu) ARCVAE_CUDA(cudaMemcpyAsync(mu, tp.mu, (size_t)B * d.L * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (logvar) ARCVAE_CUDA(cudaMemcpyAsync(logvar, tp.logvar, (size_t)B * d.L * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 
-extern "C" int arcvae_encoder_backward(const arcvae_dims* d, const arcvae_encoder_params* p, const float* cond, int B,
-                                       int T, const float* dmu, const float* dlogvar, void* tape, size_t tape_bytes,
-                                       const arcvae_encoder_params* g, void* scratch, size_t scratch_bytes,
-                                       int precision, void* stream) {
-  ARCVAE_TRY(check_dims(d));
-  ARCVAE_REQUIRE(precision == ARCVAE_PREC_FP32 || precision == ARCVAE_PREC_BF16, "precision");
-  ARCVAE_REQUIRE(g != nullptr && dmu != nullptr && dlogvar != nullptr, "grad pointers");
-  cudaStream_t st = (cudaStream_t)stream;
-  EncTape tp;
-  size_t need = enc_tape_layout(*d, B, T, precision, tape, tape_bytes, &tp);
-  ARCVAE_REQUIRE(tape != nullptr && need <= tape_bytes, "encoder tape too small");
-  EncScratch sc;
-  size_t need_s = enc_scratch_layout(*d, B, T, precision, scratch, scratch_bytes, &sc);
-  ARCVAE_REQUIRE(scratch != nullptr && need_s <= scratch_bytes, "encoder scratch too small");
-  const int H = d->H, G4 = 4 * d->H, L = d->L, H2 = 2 * d->H;
-  const long R = (long)T * B;
+// leaves d h_T in sc.du[:, 0:H] (row pitch 2H)
+static int head_backward(const arcvae_dims& d, const arcvae_encoder_params* p, const arcvae_encoder_params* g,
+                         const EncTape& tp, const EncScratch& sc, const float* cond, int B, const float* dmu,
+                         const float* dlogvar, cudaStream_t st) {
+  const int H = d.H, L = d.L, H2 = 2 * d.H;
   RowMap id{nullptr, 1};
-  const bool bf = precision == ARCVAE_PREC_BF16;
-
-  // ---- head backward
   ARCVAE_TRY(head_bound_bwd(tp.mu, tp.logvar, dmu, dlogvar, (long)B * L, sc.dmu_raw, sc.dlv_raw, st));
   // fc_logvar: lv_raw = lvh @ Wlv^T + b
   ARCVAE_TRY(gemm_f32(1, 0, L, H2, B, sc.dlv_raw, L, tp.lvh, H2, g->fc_logvar_w, H2, nullptr, true, id, pick_splitk(L, H2, B), st));
@@ -200,10 +160,162 @@ extern "C" int arcvae_encoder_backward(const arcvae_dims* d, const arcvae_encode
   ARCVAE_TRY(colsum(sc.dmu_raw, B, L, L, g->fc_mu_b, st));
   ARCVAE_TRY(gemm_f32(0, 0, B, H2, L, sc.dmu_raw, L, p->fc_mu_w, H2, sc.du, H2, nullptr, true, id, 1, st));
   // condition_fc: cproj = cond @ Wc^T + bc ; d cproj = du[:, H:2H]
-  ARCVAE_TRY(gemm_f32(1, 0, H, d->C, B, sc.du + H, H2, cond, d->C, g->condition_fc_w, d->C, nullptr, true, id, pick_splitk(H, d->C, B), st));
+  ARCVAE_TRY(gemm_f32(1, 0, H, d.C, B, sc.du + H, H2, cond, d.C, g->condition_fc_w, d.C, nullptr, true, id, pick_splitk(H, d.C, B), st));
   ARCVAE_TRY(colsum(sc.du + H, B, H, H2, g->condition_fc_b, st));
+  return 0;
+}
 
-  // ---- BPTT, top layer first
+// layer 0: P0 = table0[x]  ->  dtable0 = onehot(x)^T @ dA ; table0 = Emb @ Wx0^T + b0
+static int layer0_input_backward(const arcvae_dims& d, const arcvae_encoder_params* p, const arcvae_encoder_params* g,
+                                 const EncScratch& sc, cudaStream_t st) {
+  const int G4 = 4 * d.H;
+  RowMap id{nullptr, 1};
+  ARCVAE_TRY(colsum(sc.dtable0, d.V, G4, G4, g->bias[0], st));
+  ARCVAE_TRY(gemm_f32(0, 0, d.V, d.E, G4, sc.dtable0, G4, p->Wx[0], d.E, g->embedding, d.E, nullptr, true, id, 1, st));
+  ARCVAE_TRY(gemm_f32(1, 0, G4, d.E, d.V, sc.dtable0, G4, p->embedding, d.E, g->Wx[0], d.E, nullptr, true, id, 1, st));
+  return 0;
+}
+
+}  // namespace arcvae
+
+using namespace arcvae;
+
+// sized for the largest layout so one buffer serves every precision / path
+extern "C" size_t arcvae_encoder_tape_bytes(const arcvae_dims* d, int B, int T) {
+  if (!d) return 0;
+  size_t m = 0;
+  for (int path = 0; path < 3; path++) {
+    size_t s = enc_tape_layout(*d, B, T, path, nullptr, 0, nullptr);
+    if (s > m) m = s;
+  }
+  return m;
+}
+extern "C" size_t arcvae_encoder_scratch_bytes(const arcvae_dims* d, int B, int T) {
+  if (!d) return 0;
+  return enc_scratch_layout(*d, B, T, PATH_STEP_BF16, nullptr, 0, nullptr);
+}
+
+extern "C" int arcvae_encoder_forward(const arcvae_dims* d, const arcvae_encoder_params* p, const int32_t* x,
+                                      const float* cond, int B, int T, float* mu, float* logvar, void* tape,
+                                      size_t tape_bytes, int precision, void* stream) {
+  ARCVAE_TRY(check_dims(d));
+  ARCVAE_REQUIRE(B > 0 && T > 0, "empty batch / sequence");
+  ARCVAE_REQUIRE(precision == ARCVAE_PREC_FP32 || precision == ARCVAE_PREC_BF16, "precision");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int path = pick_path(*d, precision);
+  EncTape tp;
+  size_t need = enc_tape_layout(*d, B, T, path, tape, tape_bytes, &tp);
+  ARCVAE_REQUIRE(tape != nullptr && need <= tape_bytes, "encoder tape too small");
+  const int H = d->H, G4 = 4 * d->H;
+  const long R = (long)T * B;
+  RowMap id{nullptr, 1};
+  const bool bf = path != PATH_STEP_F32;
+
+  ARCVAE_TRY(transpose_tokens(x, B, T, tp.xT, st));
+  // table0[v,:] = Emb[v,:] @ Wx0^T + b0   (encoder.py:93 gather + nn.LSTM's addmm folded: rows are tokens)
+  ARCVAE_TRY(gemm_f32(0, 1, d->V, G4, d->E, p->embedding, d->E, p->Wx[0], d->E, tp.table0, G4, p->bias[0], false, id, 1, st));
+  if (bf) {
+    for (int l = 0; l < d->NL; l++) {
+      ARCVAE_TRY(f32_to_bf16(p->Wh[l], tp.Whb[l], (long)G4 * H, st));
+      if (l >= 1) ARCVAE_TRY(f32_to_bf16(p->Wx[l], tp.Wxb[l], (long)G4 * H, st));
+    }
+  }
+
+  if (path == PATH_CLUSTER) {
+    ARCVAE_CUDA(cudaMemsetAsync(tp.err, 0, sizeof(int), st));
+    for (int l = 0; l < d->NL; l++) {
+      if (l >= 1) {
+        // time-parallel input projection, bf16 out (bias included): Pb = hb_{l-1} @ Wx_l^T + b_l
+        TcGemm g{};
+        g.M = (int)R; g.N = G4; g.K = H;
+        g.A = tp.hb[l - 1]; g.lda = H; g.a_mn = false;
+        g.B = tp.Wxb[l]; g.ldb = H; g.b_mn = false;
+        g.C = nullptr; g.ldc = 0; g.Cb = tp.Pb; g.ldcb = G4; g.bias = p->bias[l]; g.accumulate = false; g.splitk = 1;
+        g.rm = id; g.a_rows_total = R;
+        ARCVAE_TRY(gemm_tc(g, st));
+      }
+      ARCVAE_TRY(lstm_cluster_forward(B, T, H, tp.Whb[l], tp.xT, l == 0 ? tp.table0 : nullptr, l == 0 ? nullptr : tp.Pb,
+                                      tp.hb[l], tp.gates_b[l], tp.c[l], l == d->NL - 1 ? tp.h_last : nullptr, tp.err, st));
+    }
+    return head_forward(*d, p, tp, tp.h_last, cond, B, mu, logvar, st);
+  }
+
+  for (int l = 0; l < d->NL; l++) {
+    if (l == 0) {
+      ARCVAE_TRY(gather_rows(tp.table0, tp.xT, (int)R, G4, tp.gates[0], st));
+    } else {
+      // time-parallel input projection of layer l: all T*B rows at once
+      ARCVAE_TRY(gemm_any(precision, 0, 1, (int)R, G4, H, Mat{tp.h[l - 1], tp.hb[l - 1], H}, Mat{p->Wx[l], tp.Wxb[l], H},
+                          tp.gates[l], G4, p->bias[l], false, id, R, st));
+    }
+    TimeScope ts(TIME_RECURRENCE, st);
+    for (int t = 0; t < T; t++) {
+      float* g_t = tp.gates[l] + (long)t * B * G4;
+      float* c_t = tp.c[l] + (long)t * B * H;
+      float* h_t = tp.h[l] + (long)t * B * H;
+      bf16* hb_t = bf ? tp.hb[l] + (long)t * B * H : nullptr;
+      if (t > 0) {
+        // gates_t += h_{t-1} @ Wh^T   (nn.LSTM: `ifgo = ifgo + hidden @ Wh.T` once hidden is not None)
+        ARCVAE_TRY(gemm_any(precision, 0, 1, B, G4, H, Mat{h_t - (long)B * H, bf ? hb_t - (long)B * H : nullptr, H},
+                            Mat{p->Wh[l], tp.Whb[l], H}, g_t, G4, nullptr, true, id, B, st));
+      }
+      ARCVAE_TRY(lstm_cell_fwd(g_t, t > 0 ? c_t - (long)B * H : nullptr, c_t, h_t, hb_t, B, H, st));
+    }
+  }
+  const float* h_last = tp.h[d->NL - 1] + (long)(T - 1) * B * H;
+  return head_forward(*d, p, tp, h_last, cond, B, mu, logvar, st);
+}
+
+extern "C" int arcvae_encoder_backward(const arcvae_dims* d, const arcvae_encoder_params* p, const float* cond, int B,
+                                       int T, const float* dmu, const float* dlogvar, void* tape, size_t tape_bytes,
+                                       const arcvae_encoder_params* g, void* scratch, size_t scratch_bytes,
+                                       int precision, void* stream) {
+  ARCVAE_TRY(check_dims(d));
+  ARCVAE_REQUIRE(precision == ARCVAE_PREC_FP32 || precision == ARCVAE_PREC_BF16, "precision");
+  ARCVAE_REQUIRE(g != nullptr && dmu != nullptr && dlogvar != nullptr, "grad pointers");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int path = pick_path(*d, precision);
+  EncTape tp;
+  size_t need = enc_tape_layout(*d, B, T, path, tape, tape_bytes, &tp);
+  ARCVAE_REQUIRE(tape != nullptr && need <= tape_bytes, "encoder tape too small");
+  EncScratch sc;
+  size_t need_s = enc_scratch_layout(*d, B, T, path, scratch, scratch_bytes, &sc);
+  ARCVAE_REQUIRE(scratch != nullptr && need_s <= scratch_bytes, "encoder scratch too small");
+  const int H = d->H, G4 = 4 * d->H, H2 = 2 * d->H;
+  const long R = (long)T * B;
+  RowMap id{nullptr, 1};
+  const bool bf = path != PATH_STEP_F32;
+
+  ARCVAE_TRY(head_backward(*d, p, g, tp, sc, cond, B, dmu, dlogvar, st));
+
+  if (path == PATH_CLUSTER) {
+    for (int l = d->NL - 1; l >= 0; l--) {
+      const bool top = (l == d->NL - 1);
+      ARCVAE_TRY(transpose_to_bf16(p->Wh[l], G4, H, tp.WhTb[l], st));          // WhT[h][gate] = Wh[gate][h]
+      ARCVAE_TRY(lstm_cluster_backward(B, T, H, tp.WhTb[l], tp.gates_b[l], tp.c[l], top ? nullptr : sc.dX,
+                                       top ? sc.du : nullptr, H2, sc.dAb, tp.err, st));
+      // dWh += dA[1:]^T @ h[:-1]
+      if (T > 1) {
+        long K = (long)(T - 1) * B;
+        ARCVAE_TRY(gemm_any(precision, 1, 0, G4, H, (int)K, Mat{nullptr, sc.dAb + (long)B * G4, G4}, Mat{nullptr, tp.hb[l], H},
+                            g->Wh[l], H, nullptr, true, id, K, st));
+      }
+      if (l > 0) {
+        ARCVAE_TRY(colsum_bf16(sc.dAb, R, G4, G4, g->bias[l], st));
+        ARCVAE_TRY(gemm_any(precision, 1, 0, G4, H, (int)R, Mat{nullptr, sc.dAb, G4}, Mat{nullptr, tp.hb[l - 1], H},
+                            g->Wx[l], H, nullptr, true, id, R, st));
+        ARCVAE_TRY(gemm_any(precision, 0, 0, (int)R, H, G4, Mat{nullptr, sc.dAb, G4}, Mat{nullptr, tp.Wxb[l], H}, sc.dX, H,
+                            nullptr, false, id, R, st));
+      } else {
+        ARCVAE_CUDA(cudaMemsetAsync(sc.dtable0, 0, (size_t)d->V * G4 * sizeof(float), st));
+        ARCVAE_TRY(scatter_rows_by_token_bf16(sc.dAb, tp.xT, R, G4, d->V, sc.dtable0, st));
+        ARCVAE_TRY(layer0_input_backward(*d, p, g, sc, st));
+      }
+    }
+    return 0;
+  }
+
+  // ---- BPTT, per-step paths, top layer first
   for (int l = d->NL - 1; l >= 0; l--) {
     ARCVAE_CUDA(cudaMemsetAsync(sc.dc, 0, (size_t)B * H * sizeof(float), st));
     const bool top = (l == d->NL - 1);
@@ -212,21 +324,19 @@ extern "C" int arcvae_encoder_backward(const arcvae_dims* d, const arcvae_encode
       float* g_t = tp.gates[l] + (long)t * B * G4;
       const float* c_t = tp.c[l] + (long)t * B * H;
       const float* dh_ext;
-      float* dh_ext_tmp = nullptr;
       if (top) {
-        dh_ext = nullptr;  // only t = T-1 receives d h_T = du[:, 0:H] (strided), handled below
+        dh_ext = nullptr;  // only t = T-1 receives d h_T = du[:, 0:H] (strided)
         if (t == T - 1) {
           // copy du[:, 0:H] into a dense [B,H] buffer (dh_rec[1] is free at the first step)
-          dh_ext_tmp = sc.dh_rec[1];
-          ARCVAE_CUDA(cudaMemcpy2DAsync(dh_ext_tmp, (size_t)H * sizeof(float), sc.du, (size_t)H2 * sizeof(float),
+          ARCVAE_CUDA(cudaMemcpy2DAsync(sc.dh_rec[1], (size_t)H * sizeof(float), sc.du, (size_t)H2 * sizeof(float),
                                         (size_t)H * sizeof(float), B, cudaMemcpyDeviceToDevice, st));
-          dh_ext = dh_ext_tmp;
+          dh_ext = sc.dh_rec[1];
         }
       } else {
         dh_ext = sc.dX + (long)t * B * H;
       }
       const float* dh_rec = (t == T - 1) ? nullptr : sc.dh_rec[0];
-      __nv_bfloat16* dAb_t = bf ? sc.dAb + (long)t * B * G4 : nullptr;
+      bf16* dAb_t = bf ? sc.dAb + (long)t * B * G4 : nullptr;
       ARCVAE_TRY(lstm_cell_bwd(g_t, c_t, t > 0 ? c_t - (long)B * H : nullptr, dh_ext, dh_rec, sc.dc, dAb_t, B, H, st));
       if (t > 0) {
         // d h_{t-1} (recurrent part) = dA_t @ Wh
@@ -250,13 +360,25 @@ extern "C" int arcvae_encoder_backward(const arcvae_dims* d, const arcvae_encode
       ARCVAE_TRY(gemm_any(precision, 0, 0, (int)R, H, G4, Mat{dA, sc.dAb, G4}, Mat{p->Wx[l], tp.Wxb[l], H}, sc.dX, H, nullptr,
                           false, id, R, st));
     } else {
-      // layer 0: P0 = table0[x]  ->  dtable0 = onehot(x)^T @ dA ; table0 = Emb @ Wx0^T + b0
       ARCVAE_CUDA(cudaMemsetAsync(sc.dtable0, 0, (size_t)d->V * G4 * sizeof(float), st));
       ARCVAE_TRY(scatter_rows_by_token(dA, tp.xT, R, G4, d->V, sc.dtable0, nullptr, B, d->C, nullptr, st));
-      ARCVAE_TRY(colsum(sc.dtable0, d->V, G4, G4, g->bias[0], st));
-      ARCVAE_TRY(gemm_f32(0, 0, d->V, d->E, G4, sc.dtable0, G4, p->Wx[0], d->E, g->embedding, d->E, nullptr, true, id, 1, st));
-      ARCVAE_TRY(gemm_f32(1, 0, G4, d->E, d->V, sc.dtable0, G4, p->embedding, d->E, g->Wx[0], d->E, nullptr, true, id, 1, st));
+      ARCVAE_TRY(layer0_input_backward(*d, p, g, sc, st));
     }
   }
+  return 0;
+}
+
+// raised by the cluster kernels' bounded waits (0 = healthy).  Synchronises the stream.
+extern "C" int arcvae_encoder_check(const arcvae_dims* d, int B, int T, void* tape, size_t tape_bytes, int precision,
+                                    void* stream) {
+  ARCVAE_TRY(check_dims(d));
+  const int path = pick_path(*d, precision);
+  if (path != PATH_CLUSTER) return 0;
+  EncTape tp;
+  enc_tape_layout(*d, B, T, path, tape, tape_bytes, &tp);
+  int flag = 0;
+  ARCVAE_CUDA(cudaMemcpyAsync(&flag, tp.err, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  ARCVAE_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  ARCVAE_REQUIRE(flag == 0, "cluster recurrence kernel reported a barrier time-out");
   return 0;
 }

@@ -263,7 +263,7 @@ static int get_encode() {
 }
 
 // row-major bf16 matrix [rows, cols] with pitch ld (elements); box {box_cols (inner), box_rows}
-static int make_tmap(CUtensorMap* m, const bf16* ptr, long rows, long cols, long ld, int box_cols, int box_rows) {
+int make_tmap_bf16(CUtensorMap* m, const bf16* ptr, long rows, long cols, long ld, int box_cols, int box_rows) {
   ARCVAE_TRY(get_encode());
   ARCVAE_REQUIRE((ld % 8) == 0 && ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0),
                  "TMA operands need 16-byte aligned base and pitch (ld multiple of 8 bf16)");
@@ -323,12 +323,12 @@ int gemm_tc(const TcGemm& g, cudaStream_t st) {
   if (!g.a_mn) {
     // rows of A may be reached through the row map -> describe the whole allocation the map can touch
     long rows = g.rm.tlist ? g.a_rows_total : g.M;
-    ARCVAE_TRY(make_tmap(&tmA, g.A, rows, g.K, g.lda, TC_BK, TC_BM));
+    ARCVAE_TRY(make_tmap_bf16(&tmA, g.A, rows, g.K, g.lda, TC_BK, TC_BM));
   } else {
-    ARCVAE_TRY(make_tmap(&tmA, g.A, g.K, g.M, g.lda, 64, TC_BK));
+    ARCVAE_TRY(make_tmap_bf16(&tmA, g.A, g.K, g.M, g.lda, 64, TC_BK));
   }
-  if (!g.b_mn) ARCVAE_TRY(make_tmap(&tmB, g.B, g.N, g.K, g.ldb, TC_BK, p.BN));
-  else ARCVAE_TRY(make_tmap(&tmB, g.B, g.K, g.N, g.ldb, 64, TC_BK));
+  if (!g.b_mn) ARCVAE_TRY(make_tmap_bf16(&tmB, g.B, g.N, g.K, g.ldb, TC_BK, p.BN));
+  else ARCVAE_TRY(make_tmap_bf16(&tmB, g.B, g.K, g.N, g.ldb, 64, TC_BK));
 
   static int num_sms = 0;
   static bool attr = false;

@@ -84,6 +84,18 @@ int pick_splitk_tc(int M, int N, int K);
 int f32_to_bf16(const float* src, __nv_bfloat16* dst, long n, cudaStream_t st);
 int transpose_to_bf16(const float* src, int R, int C, __nv_bfloat16* dst, cudaStream_t st);   // dst[c*R+r] = src[r*C+c]
 
+// persistent cluster LSTM recurrence (lstm_cluster.cu), H == 256
+bool lstm_cluster_supported(int H);
+int lstm_cluster_forward(int B, int T, int H, const __nv_bfloat16* Whb, const int32_t* xT, const float* table0,
+                         const __nv_bfloat16* Pb, __nv_bfloat16* hb, __nv_bfloat16* gates_b, float* c, float* h_last,
+                         int* err_flag, cudaStream_t st);
+int lstm_cluster_backward(int B, int T, int H, const __nv_bfloat16* WhTb, const __nv_bfloat16* gates_b, const float* c,
+                          const float* dh_ext, const float* dh_last, int dh_last_ld, __nv_bfloat16* dAb, int* err_flag,
+                          cudaStream_t st);
+int colsum_bf16(const __nv_bfloat16* X, long R, int N, int ldx, float* out, cudaStream_t st);
+int scatter_rows_by_token_bf16(const __nv_bfloat16* X, const int32_t* tok, long R, int N, int V, float* dtable,
+                               cudaStream_t st);
+
 // the same logical matrix in fp32 and (optionally) bf16; gemm_any picks the tensor-core kernel when precision is bf16
 // and the operands satisfy the TMA constraints, else the fp32 FFMA kernel on the fp32 copies
 struct Mat {

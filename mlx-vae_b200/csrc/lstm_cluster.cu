@@ -1,0 +1,439 @@
+// lstm_cluster.cu — the encoder LSTM recurrence (models/encoder.py:98-101; MLX nn.LSTM loop) as ONE persistent
+// thread-block-cluster kernel per layer and direction: all T timesteps inside the kernel, W_hh resident in shared
+// memory for the whole sequence, h_t / dA_t exchanged between the CTAs of a cluster by TMA multicast into every
+// peer's shared memory (distributed shared memory), gate math fused into the accumulator read-out.
+//
+// Decomposition (H = 256): a cluster of 4 CTAs owns a tile of 128 batch rows; CTA r owns hidden units [64r, 64r+64).
+//   forward   acc[128 x 256] = h_{t-1}[128 x 256] . Wh[rows {g*H + 64r + u}, :]^T        (4 gates x 64 units)
+//             W slice 256 x 256 bf16 = 128 KB resident; K = 256 arrives as 4 chunks of 64 (one per source CTA)
+//   backward  acc[128 x 64]  = dA_{t+1}[128 x 1024] . Wh[:, 64r .. 64r+63]                (this CTA's units)
+//             W^T slice 64 x 1024 bf16 = 128 KB resident; K = 1024 arrives as 16 chunks of 64 (4 per source CTA)
+// Every chunk is a [128 rows x 64] bf16 tile that its producer CTA has just written to HBM (the tape needs it anyway:
+// h for the next layer / weight gradients, dA for the weight gradients) and then multicasts from L2 into the same
+// 4-stage ring slot of all 4 CTAs with ONE cp.async.bulk.tensor ...multicast::cluster; the ring's `full` mbarriers
+// count the bytes, its `empty` mbarriers are signalled cluster-wide by tcgen05.commit ...multicast::cluster.
+// Roles per CTA (320 threads): warp 0 MMA/control thread, warp 1 sender thread (+ TMEM alloc), warps 2-9 epilogue
+// (thread = batch row; two warps per TMEM lane quarter, 32 hidden units each; c_t / dc_t live in registers across
+// the whole sequence).
+#include <cooperative_groups.h>
+
+#include "kernels.cuh"
+#include "tc_common.cuh"
+
+namespace arcvae {
+
+using bf16 = __nv_bfloat16;
+
+constexpr int RC_CL = 4;
+constexpr int RC_ROWS = 128;
+constexpr int RC_NSTG = 4;
+constexpr int RC_THREADS = 320;
+constexpr int RC_STAGE_BYTES = RC_ROWS * 64 * 2;   // 16 KB
+constexpr int RC_W_BYTES = 128 * 1024;
+constexpr long RC_SPIN_LIMIT = 1L << 24;           // bounded waits: a protocol bug must not hang the GPU
+
+struct __align__(8) RecShared {
+  uint64_t full[RC_NSTG];
+  uint64_t empty[RC_NSTG];
+  uint64_t w_ready, acc_full, epi_done;
+  uint32_t tmem_base;
+  int failed;
+};
+
+struct RecParams {
+  int B, T, H;
+  // forward
+  const int32_t* xT;      // [T,B] tokens (table mode)
+  const float* table0;    // [V,4H] fp32: P_t = table0[x_t]   (layer 0)   -- or --
+  const bf16* Pb;         // [T*B,4H] bf16 pre-activations incl. bias (layers >= 1)
+  bf16* hb;               // [T*B,H]  h_t, bf16 (exchange + tape)
+  bf16* gates_b;          // [T*B,4H] activated gates, bf16 (tape)
+  float* c;               // [T*B,H]  cell state, fp32 (tape)
+  float* h_last;          // [B,H]    h_{T-1}, fp32 (encoder head)
+  // backward
+  const float* dh_ext;    // [T*B,H] gradient from the layer above (or null)
+  const float* dh_last;   // [B, dh_last_ld] gradient into h_{T-1} from the head (or null)
+  int dh_last_ld;
+  bf16* dAb;              // [T*B,4H] pre-activation gradients, bf16 (exchange + tape)
+  int* err_flag;
+};
+
+namespace rc {
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(tc::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1),
+        "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(tc::smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// bounded wait; returns false (and flags the failure) if the barrier never flips
+__device__ __forceinline__ bool wait_or_fail(uint64_t* bar, uint32_t parity, RecShared* sh) {
+  for (long i = 0; i < RC_SPIN_LIMIT; i++) {
+    if (tc::mbar_try_wait(bar, parity)) return true;
+    if ((i & 1023) == 1023 && *(volatile int*)&sh->failed) return false;
+  }
+  *(volatile int*)&sh->failed = 1;
+  return false;
+}
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    float2 t = __bfloat1622float2(p[i]);
+    f[2 * i] = t.x; f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 v;
+  __nv_bfloat162* p = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; i++) p[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return v;
+}
+}  // namespace rc
+
+template <bool BWD>
+__global__ void __launch_bounds__(RC_THREADS, 1)
+lstm_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, const RecParams p) {
+  constexpr int NCH = BWD ? 16 : 4;        // 64-wide K chunks per step
+  constexpr int BN = BWD ? 64 : 256;       // accumulator columns = MMA N
+  constexpr int WPANEL = BN * 128;         // bytes of one K-panel of the resident weight slice
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* Wsm = smem;
+  uint8_t* ring = smem + RC_W_BYTES;
+  RecShared* sh = reinterpret_cast<RecShared*>(ring + RC_NSTG * RC_STAGE_BYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)rc::cluster_ctarank();
+  const int tile = blockIdx.x / RC_CL;
+  const int row0 = tile * RC_ROWS;
+  const int B = p.B, T = p.T, H = p.H;
+  const uint16_t ALL = (uint16_t)((1u << RC_CL) - 1);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < RC_NSTG; s++) {
+      tc::mbar_init(&sh->full[s], 1);
+      tc::mbar_init(&sh->empty[s], RC_CL);
+    }
+    tc::mbar_init(&sh->w_ready, 1);
+    tc::mbar_init(&sh->acc_full, 1);
+    tc::mbar_init(&sh->epi_done, 8);
+    sh->failed = 0;
+    tc::fence_barrier_init();
+    tc::prefetch_tmap(&tmW);
+    tc::prefetch_tmap(&tmX);
+  }
+  if (warp == 1) tc::tmem_alloc(&sh->tmem_base, BN);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  rc::cluster_sync_all();                    // every CTA's barriers exist before any multicast / remote arrive
+  const uint32_t tmem_base = sh->tmem_base;
+
+  if (warp == 0) {
+    // =========================================================== control: weights once, then the MMAs of every step
+    if (lane == 0) {
+      tc::mbar_expect_tx(&sh->w_ready, RC_W_BYTES);
+      if (!BWD) {
+        for (int kp = 0; kp < 4; kp++)
+          for (int g = 0; g < 4; g++)
+            tc::tma_load_2d(Wsm + kp * WPANEL + g * 8192, &tmW, &sh->w_ready, 64 * kp, g * H + 64 * rank);
+      } else {
+        for (int kq = 0; kq < 16; kq++) tc::tma_load_2d(Wsm + kq * WPANEL, &tmW, &sh->w_ready, 64 * kq, 64 * rank);
+      }
+      bool ok = rc::wait_or_fail(&sh->w_ready, 0, sh);
+      const uint32_t idesc = tc::make_idesc_bf16(RC_ROWS, BN, false, false);
+      uint32_t use[RC_NSTG] = {0, 0, 0, 0};
+      for (int it = 1; it < T && ok; it++) {
+        for (int kq = 0; kq < NCH && ok; kq++) {
+          const int s = kq % RC_NSTG;
+          tc::mbar_expect_tx(&sh->full[s], RC_STAGE_BYTES);          // arm this use (bytes may already have landed)
+          ok = rc::wait_or_fail(&sh->full[s], use[s] & 1, sh);
+          if (!ok) break;
+          tc::tc_fence_after();
+          const uint32_t a_addr = tc::smem_u32(ring + s * RC_STAGE_BYTES);
+          const uint32_t b_addr = tc::smem_u32(Wsm + kq * WPANEL);
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+            tc::mma_bf16(tmem_base, tc::make_smem_desc(a_addr + 32 * j, 16, 1024),
+                         tc::make_smem_desc(b_addr + 32 * j, 16, 1024), idesc, (kq > 0 || j > 0) ? 1u : 0u);
+          rc::mma_commit_mc(&sh->empty[s], ALL);                     // slot free in ALL CTAs once these MMAs retire
+          use[s]++;
+        }
+        if (ok) tc::mma_commit(&sh->acc_full);
+      }
+    }
+  } else if (warp == 1) {
+    // =========================================================== sender: multicast this CTA's fresh chunk(s)
+    if (lane == 0) {
+      uint32_t sent = 0;
+      bool ok = true;
+      for (int it = 0; it < T - 1 && ok; it++) {
+        ok = rc::wait_or_fail(&sh->epi_done, it & 1, sh);
+        if (!ok) break;
+        const int t = BWD ? (T - 1 - it) : it;
+        for (int g = 0; g < NCH / RC_CL && ok; g++) {
+          if (sent > 0) ok = rc::wait_or_fail(&sh->empty[rank], (sent - 1) & 1, sh);
+          if (!ok) break;
+          const int col = (BWD ? g * H : 0) + 64 * rank;
+          rc::tma_load_2d_mc(ring + rank * RC_STAGE_BYTES, &tmX, &sh->full[rank], col, t * B + row0, ALL);
+          sent++;
+        }
+      }
+    }
+  } else {
+    // =========================================================== epilogue: gate math, state in registers
+    const int q = warp & 3;                  // TMEM lane quarter this warp may read
+    const int hs = (warp - 2) >> 2;          // which 32 of the CTA's 64 hidden units
+    const int row = row0 + q * 32 + lane;
+    const bool valid = row < B;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    float state[32];                         // forward: c_{t-1}; backward: dL/dc_t carried to t-1
+#pragma unroll
+    for (int i = 0; i < 32; i++) state[i] = 0.f;
+    bool ok = true;
+    for (int it = 0; it < T && ok; it++) {
+      const int t = BWD ? (T - 1 - it) : it;
+      const long r = (long)t * B + row;
+      if (it > 0) {
+        ok = rc::wait_or_fail(&sh->acc_full, (it - 1) & 1, sh);
+        if (!ok) break;
+        tc::tc_fence_after();
+      }
+#pragma unroll
+      for (int cu = 0; cu < 4; cu++) {
+        const int u0 = hs * 32 + cu * 8;             // unit offset inside the CTA's 64
+        const int ug = 64 * rank + u0;               // global hidden-unit index
+        if (!BWD) {
+          float a[4][8];
+          if (it > 0) {
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+              uint32_t rr[8];
+              rc::tmem_ld8(taddr + (uint32_t)(g * 64 + u0), rr);
+#pragma unroll
+              for (int j = 0; j < 8; j++) a[g][j] = __uint_as_float(rr[j]);
+            }
+            tc::tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int g = 0; g < 4; g++)
+#pragma unroll
+              for (int j = 0; j < 8; j++) a[g][j] = 0.f;
+          }
+          if (valid) {
+            if (p.table0 != nullptr) {
+              const float* trow = p.table0 + (long)p.xT[r] * 4 * H + ug;
+#pragma unroll
+              for (int g = 0; g < 4; g++) {
+                const float4 v0 = __ldg(reinterpret_cast<const float4*>(trow + g * H));
+                const float4 v1 = __ldg(reinterpret_cast<const float4*>(trow + g * H + 4));
+                a[g][0] += v0.x; a[g][1] += v0.y; a[g][2] += v0.z; a[g][3] += v0.w;
+                a[g][4] += v1.x; a[g][5] += v1.y; a[g][6] += v1.z; a[g][7] += v1.w;
+              }
+            } else {
+              const bf16* prow = p.Pb + r * 4 * H + ug;
+#pragma unroll
+              for (int g = 0; g < 4; g++) {
+                float f[8];
+                rc::unpack8(__ldg(reinterpret_cast<const uint4*>(prow + g * H)), f);
+#pragma unroll
+                for (int j = 0; j < 8; j++) a[g][j] += f[j];
+              }
+            }
+            float hv[8], gi[8], gf[8], gg[8], go[8], cv[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              gi[j] = sigmoidf_(a[0][j]);
+              gf[j] = sigmoidf_(a[1][j]);
+              gg[j] = tanhf_(a[2][j]);
+              go[j] = sigmoidf_(a[3][j]);
+              const float cn = fmaf(gf[j], state[cu * 8 + j], gi[j] * gg[j]);   // t = 0: state = 0 -> c = i*g
+              state[cu * 8 + j] = cn;
+              cv[j] = cn;
+              hv[j] = go[j] * tanhf_(cn);
+            }
+            *reinterpret_cast<uint4*>(p.hb + r * H + ug) = rc::pack8(hv);
+            bf16* grow = p.gates_b + r * 4 * H + ug;
+            *reinterpret_cast<uint4*>(grow) = rc::pack8(gi);
+            *reinterpret_cast<uint4*>(grow + H) = rc::pack8(gf);
+            *reinterpret_cast<uint4*>(grow + 2 * H) = rc::pack8(gg);
+            *reinterpret_cast<uint4*>(grow + 3 * H) = rc::pack8(go);
+            float* crow = p.c + r * H + ug;
+            *reinterpret_cast<float4*>(crow) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+            *reinterpret_cast<float4*>(crow + 4) = make_float4(cv[4], cv[5], cv[6], cv[7]);
+            if (t == T - 1 && p.h_last != nullptr) {
+              float* hl = p.h_last + (long)row * H + ug;
+              *reinterpret_cast<float4*>(hl) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+              *reinterpret_cast<float4*>(hl + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
+            }
+          }
+        } else {
+          float dh[8];
+          if (it > 0) {
+            uint32_t rr[8];
+            rc::tmem_ld8(taddr + (uint32_t)u0, rr);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; j++) dh[j] = __uint_as_float(rr[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) dh[j] = 0.f;
+          }
+          if (valid) {
+            if (p.dh_ext != nullptr) {
+              const float* e = p.dh_ext + r * H + ug;
+              const float4 v0 = __ldg(reinterpret_cast<const float4*>(e));
+              const float4 v1 = __ldg(reinterpret_cast<const float4*>(e + 4));
+              dh[0] += v0.x; dh[1] += v0.y; dh[2] += v0.z; dh[3] += v0.w;
+              dh[4] += v1.x; dh[5] += v1.y; dh[6] += v1.z; dh[7] += v1.w;
+            }
+            if (t == T - 1 && p.dh_last != nullptr) {
+              const float* e = p.dh_last + (long)row * p.dh_last_ld + ug;
+#pragma unroll
+              for (int j = 0; j < 8; j++) dh[j] += e[j];
+            }
+            float gi[8], gf[8], gg[8], go[8], ct[8], cp[8];
+            const bf16* grow = p.gates_b + r * 4 * H + ug;
+            rc::unpack8(__ldg(reinterpret_cast<const uint4*>(grow)), gi);
+            rc::unpack8(__ldg(reinterpret_cast<const uint4*>(grow + H)), gf);
+            rc::unpack8(__ldg(reinterpret_cast<const uint4*>(grow + 2 * H)), gg);
+            rc::unpack8(__ldg(reinterpret_cast<const uint4*>(grow + 3 * H)), go);
+            {
+              const float* crow = p.c + r * H + ug;
+              const float4 v0 = __ldg(reinterpret_cast<const float4*>(crow));
+              const float4 v1 = __ldg(reinterpret_cast<const float4*>(crow + 4));
+              ct[0] = v0.x; ct[1] = v0.y; ct[2] = v0.z; ct[3] = v0.w; ct[4] = v1.x; ct[5] = v1.y; ct[6] = v1.z; ct[7] = v1.w;
+            }
+            if (t > 0) {
+              const float* crow = p.c + (r - B) * H + ug;
+              const float4 v0 = __ldg(reinterpret_cast<const float4*>(crow));
+              const float4 v1 = __ldg(reinterpret_cast<const float4*>(crow + 4));
+              cp[0] = v0.x; cp[1] = v0.y; cp[2] = v0.z; cp[3] = v0.w; cp[4] = v1.x; cp[5] = v1.y; cp[6] = v1.z; cp[7] = v1.w;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; j++) cp[j] = 0.f;
+            }
+            float ai[8], af[8], ag[8], ao[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              const float tcv = tanhf_(ct[j]);
+              const float dct = state[cu * 8 + j] + dh[j] * go[j] * (1.f - tcv * tcv);
+              ao[j] = dh[j] * tcv * go[j] * (1.f - go[j]);
+              ai[j] = dct * gg[j] * gi[j] * (1.f - gi[j]);
+              ag[j] = dct * gi[j] * (1.f - gg[j] * gg[j]);
+              af[j] = dct * cp[j] * gf[j] * (1.f - gf[j]);
+              state[cu * 8 + j] = dct * gf[j];
+            }
+            bf16* drow = p.dAb + r * 4 * H + ug;
+            *reinterpret_cast<uint4*>(drow) = rc::pack8(ai);
+            *reinterpret_cast<uint4*>(drow + H) = rc::pack8(af);
+            *reinterpret_cast<uint4*>(drow + 2 * H) = rc::pack8(ag);
+            *reinterpret_cast<uint4*>(drow + 3 * H) = rc::pack8(ao);
+          }
+        }
+      }
+      // publish: generic-proxy global writes -> visible to the TMA (async proxy) issued by the sender thread
+      rc::fence_proxy_async_all();
+      __threadfence();
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&sh->epi_done);
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0 && sh->failed && p.err_flag != nullptr) atomicExch(p.err_flag, 1);
+  rc::cluster_sync_all();                    // nobody exits while a peer may still multicast into / arrive on its smem
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// ---- host ---------------------------------------------------------------------------------------------------------
+int make_tmap_bf16(CUtensorMap* m, const bf16* ptr, long rows, long cols, long ld, int box_cols, int box_rows);
+
+static int launch_rec(bool bwd, const CUtensorMap& tmW, const CUtensorMap& tmX, const RecParams& p, cudaStream_t st) {
+  const size_t smem = RC_W_BYTES + RC_NSTG * RC_STAGE_BYTES + sizeof(RecShared) + 1024;
+  static bool attr = false;
+  if (!attr) {
+    ARCVAE_CUDA(cudaFuncSetAttribute(lstm_rec_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ARCVAE_CUDA(cudaFuncSetAttribute(lstm_rec_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  const int tiles = cdiv(p.B, RC_ROWS);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(tiles * RC_CL);
+  cfg.blockDim = dim3(RC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = RC_CL;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  TimeScope ts(TIME_RECURRENCE, st);
+  if (!bwd) ARCVAE_CUDA(cudaLaunchKernelEx(&cfg, lstm_rec_kernel<false>, tmW, tmX, p));
+  else ARCVAE_CUDA(cudaLaunchKernelEx(&cfg, lstm_rec_kernel<true>, tmW, tmX, p));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+bool lstm_cluster_supported(int H) { return H == 256; }
+
+int lstm_cluster_forward(int B, int T, int H, const bf16* Whb, const int32_t* xT, const float* table0, const bf16* Pb,
+                         bf16* hb, bf16* gates_b, float* c, float* h_last, int* err_flag, cudaStream_t st) {
+  ARCVAE_REQUIRE(lstm_cluster_supported(H), "cluster recurrence kernel is built for hidden_dim 256");
+  CUtensorMap tmW, tmX;
+  ARCVAE_TRY(make_tmap_bf16(&tmW, Whb, 4L * H, H, H, 64, 64));
+  ARCVAE_TRY(make_tmap_bf16(&tmX, hb, (long)T * B, H, H, 64, RC_ROWS));
+  RecParams p{};
+  p.B = B; p.T = T; p.H = H;
+  p.xT = xT; p.table0 = table0; p.Pb = Pb; p.hb = hb; p.gates_b = gates_b; p.c = c; p.h_last = h_last;
+  p.err_flag = err_flag;
+  return launch_rec(false, tmW, tmX, p, st);
+}
+
+int lstm_cluster_backward(int B, int T, int H, const bf16* WhTb, const bf16* gates_b, const float* c,
+                          const float* dh_ext, const float* dh_last, int dh_last_ld, bf16* dAb, int* err_flag,
+                          cudaStream_t st) {
+  ARCVAE_REQUIRE(lstm_cluster_supported(H), "cluster recurrence kernel is built for hidden_dim 256");
+  CUtensorMap tmW, tmX;
+  ARCVAE_TRY(make_tmap_bf16(&tmW, WhTb, H, 4L * H, 4L * H, 64, 64));
+  ARCVAE_TRY(make_tmap_bf16(&tmX, dAb, (long)T * B, 4L * H, 4L * H, 64, RC_ROWS));
+  RecParams p{};
+  p.B = B; p.T = T; p.H = H;
+  p.gates_b = const_cast<bf16*>(gates_b); p.c = const_cast<float*>(c);
+  p.dh_ext = dh_ext; p.dh_last = dh_last; p.dh_last_ld = dh_last_ld; p.dAb = dAb; p.err_flag = err_flag;
+  return launch_rec(true, tmW, tmX, p, st);
+}
+
+}  // namespace arcvae

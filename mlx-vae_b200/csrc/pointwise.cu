@@ -308,7 +308,11 @@ int head_bound_bwd(const float* mu, const float* logvar, const float* dmu, const
 
 // ------------------------------------------------------------------------------------------------
 // column sums: block = 32 x 8 (32 columns, 8 row lanes), rows strided over grid.y
-__global__ void k_colsum(const float* __restrict__ X, long R, int N, int ldx, float* __restrict__ out,
+__device__ __forceinline__ float ldf(const float* p) { return *p; }
+__device__ __forceinline__ float ldf(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+template <typename TIn>
+__global__ void k_colsum(const TIn* __restrict__ X, long R, int N, int ldx, float* __restrict__ out,
                          long rows_per_block) {
   __shared__ float red[8][33];
   int n = blockIdx.x * 32 + threadIdx.x;
@@ -317,7 +321,7 @@ __global__ void k_colsum(const float* __restrict__ X, long R, int N, int ldx, fl
   if (r1 > R) r1 = R;
   float acc = 0.f;
   if (n < N)
-    for (long r = r0 + threadIdx.y; r < r1; r += 8) acc += X[r * ldx + n];
+    for (long r = r0 + threadIdx.y; r < r1; r += 8) acc += ldf(X + r * ldx + n);
   red[threadIdx.y][threadIdx.x] = acc;
   __syncthreads();
   if (threadIdx.y == 0 && n < N) {
@@ -327,22 +331,28 @@ __global__ void k_colsum(const float* __restrict__ X, long R, int N, int ldx, fl
     atomicAdd(out + n, s);
   }
 }
-int colsum(const float* X, long R, int N, int ldx, float* out, cudaStream_t st) {
+template <typename TIn>
+static int colsum_t(const TIn* X, long R, int N, int ldx, float* out, cudaStream_t st) {
   if (R <= 0 || N <= 0) return 0;
   int gx = cdiv(N, 32);
   long want = (148L * 8 + gx - 1) / gx;
   long rpb = (R + want - 1) / want;
   if (rpb < 64) rpb = 64;
   int gy = cdiv(R, rpb);
-  k_colsum<<<dim3(gx, gy), dim3(32, 8), 0, st>>>(X, R, N, ldx, out, rpb);
+  k_colsum<TIn><<<dim3(gx, gy), dim3(32, 8), 0, st>>>(X, R, N, ldx, out, rpb);
   ARCVAE_LAUNCHED();
   return 0;
+}
+int colsum(const float* X, long R, int N, int ldx, float* out, cudaStream_t st) { return colsum_t(X, R, N, ldx, out, st); }
+int colsum_bf16(const __nv_bfloat16* X, long R, int N, int ldx, float* out, cudaStream_t st) {
+  return colsum_t(X, R, N, ldx, out, st);
 }
 
 // scatter rows by token with an smem accumulator: block = 128 threads (one per column of a 128-wide slab),
 // each block walks `rows_per_block` rows; thread j owns column j so the smem adds are conflict-free and
 // un-contended.  V*128 floats of smem (V=80: 40 KB).
-__global__ void k_scatter_rows_by_token(const float* __restrict__ X, const int32_t* __restrict__ tok, long R, int N,
+template <typename TIn>
+__global__ void k_scatter_rows_by_token(const TIn* __restrict__ X, const int32_t* __restrict__ tok, long R, int N,
                                         int V, float* __restrict__ dtable, const float* __restrict__ cond, int B, int C,
                                         float* __restrict__ dwc, long rows_per_block) {
   extern __shared__ float acc[];  // [V][128]
@@ -355,7 +365,7 @@ __global__ void k_scatter_rows_by_token(const float* __restrict__ X, const int32
   float wacc[4] = {0.f, 0.f, 0.f, 0.f};
   if (n < N) {
     for (long r = r0; r < r1; r++) {
-      float x = X[r * N + n];
+      float x = ldf(X + r * N + n);
       acc[tok[r] * 128 + j] += x;
       if (dwc != nullptr) {
         const float* cr = cond + (r % B) * C;
@@ -370,15 +380,16 @@ __global__ void k_scatter_rows_by_token(const float* __restrict__ X, const int32
       for (int c = 0; c < C && c < 4; c++) atomicAdd(dwc + (long)n * C + c, wacc[c]);
   }
 }
-int scatter_rows_by_token(const float* X, const int32_t* tok, long R, int N, int V, float* dtable, const float* cond,
-                          int B, int C, float* dwc, cudaStream_t st) {
+template <typename TIn>
+static int scatter_t(const TIn* X, const int32_t* tok, long R, int N, int V, float* dtable, const float* cond,
+                     int B, int C, float* dwc, cudaStream_t st) {
   if (R <= 0) return 0;
   ARCVAE_REQUIRE(dwc == nullptr || C <= 4, "num_conditions > 4 not supported by the fused cond-weight reduction");
   size_t smem = (size_t)V * 128 * sizeof(float);
   ARCVAE_REQUIRE(smem <= 200 * 1024, "vocab too large for the smem scatter accumulator");
   static bool attr_set = false;
   if (!attr_set) {
-    ARCVAE_CUDA(cudaFuncSetAttribute(k_scatter_rows_by_token, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    ARCVAE_CUDA(cudaFuncSetAttribute(k_scatter_rows_by_token<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   int gx = cdiv(N, 128);
@@ -386,9 +397,17 @@ int scatter_rows_by_token(const float* X, const int32_t* tok, long R, int N, int
   long rpb = (R + want - 1) / want;
   if (rpb < 256) rpb = 256;
   int gy = cdiv(R, rpb);
-  k_scatter_rows_by_token<<<dim3(gx, gy), 128, smem, st>>>(X, tok, R, N, V, dtable, cond, B, C, dwc, rpb);
+  k_scatter_rows_by_token<TIn><<<dim3(gx, gy), 128, smem, st>>>(X, tok, R, N, V, dtable, cond, B, C, dwc, rpb);
   ARCVAE_LAUNCHED();
   return 0;
+}
+int scatter_rows_by_token(const float* X, const int32_t* tok, long R, int N, int V, float* dtable, const float* cond,
+                          int B, int C, float* dwc, cudaStream_t st) {
+  return scatter_t(X, tok, R, N, V, dtable, cond, B, C, dwc, st);
+}
+int scatter_rows_by_token_bf16(const __nv_bfloat16* X, const int32_t* tok, long R, int N, int V, float* dtable,
+                               cudaStream_t st) {
+  return scatter_t(X, tok, R, N, V, dtable, nullptr, 1, 1, nullptr, st);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -28,6 +28,7 @@ class MLXEncoder(Module):
                     dict(V=vocab_size, E=embedding_dim, H=hidden_dim, L=latent_dim, C=num_conditions, NL=num_layers,
                          pad_token=0, end_token=2), device, seed, precision)
         self._ctx = None
+        self._last_bt = None
 
     def __call__(self, x: torch.Tensor, conditions: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         lib = _lib.load()
@@ -44,6 +45,7 @@ class MLXEncoder(Module):
                                               mu.data_ptr(), logvar.data_ptr(), tape.data_ptr(), tape.numel(),
                                               self.precision, _lib.stream_ptr()))
         self._ctx = (B, T, cond, tape)
+        self._last_bt = (B, T)
         return mu, logvar
 
     def backward(self, dmu: torch.Tensor, dlogvar: torch.Tensor):
@@ -59,6 +61,16 @@ class MLXEncoder(Module):
                                                dlogvar.data_ptr(), tape.data_ptr(), tape.numel(), self._cgrads,
                                                scratch.data_ptr(), scratch.numel(), self.precision, _lib.stream_ptr()))
         self._ctx = None
+
+    def check(self):
+        """Raise if a persistent cluster kernel of the last forward/backward reported a barrier time-out (the kernels use
+        bounded waits instead of hanging).  Synchronises the stream; for tests and debugging."""
+        tape = self.ws.bufs.get("tape")
+        if tape is None or self._last_bt is None:
+            return
+        B, T = self._last_bt
+        _lib.check(_lib.load().arcvae_encoder_check(self._dims, B, T, tape.data_ptr(), tape.numel(), self.precision,
+                                                    _lib.stream_ptr()))
 
     @staticmethod
     def reparameterize(mu: torch.Tensor, logvar: torch.Tensor, eps: Optional[torch.Tensor] = None, *,
