@@ -120,6 +120,9 @@ int arcvae_encoder_backward(const arcvae_dims* d, const arcvae_encoder_params* p
  * (bounded waits instead of hangs).  Synchronises the stream.  Test / debug aid. */
 int arcvae_encoder_check(const arcvae_dims* d, int B, int T, void* tape, size_t tape_bytes, int precision, void* stream);
 
+/* debug aid: clock64 stamps of CTA 0 of the cluster kernels into buf[64*16] (device, int64); NULL switches it off */
+int arcvae_debug_set_rc_stamps(long long* buf);
+
 /* ---- reparameterize: models/encoder.py:134-155 ---------------------------------------------- */
 /* z = mu + eps*exp(0.5*logvar); eps==NULL draws N(0,1) from Philox4x32-10(seed, offset) */
 int arcvae_reparameterize(const float* mu, const float* logvar, const float* eps, int B, int L, uint64_t seed,

@@ -67,6 +67,7 @@ SIGNATURES = {
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(EncoderParams),
                                           C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "arcvae_encoder_check": (C.c_int, [C.POINTER(Dims), C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "arcvae_debug_set_rc_stamps": (C.c_int, [C.c_void_p]),
     "arcvae_reparameterize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint64,
                                         C.c_void_p, C.c_void_p]),
     "arcvae_decoder_tape_bytes": (C.c_size_t, [C.POINTER(Dims), C.c_int, C.c_int]),

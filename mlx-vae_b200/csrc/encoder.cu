@@ -50,6 +50,7 @@ struct EncTape {
   bf16* gates_b[ARCVAE_MAX_LAYERS]; // [T*B,4H] activated gates
   bf16* WhTb[ARCVAE_MAX_LAYERS];    // [H,4H]
   bf16* Pb;                         // [T*B,4H] input projection of the layer being run (reused)
+  bf16* table0b;                    // [V,4H] bf16 copy of table0
 };
 
 static size_t enc_tape_layout(const arcvae_dims& d, int B, int T, int path, void* base, size_t cap, EncTape* t) {
@@ -66,8 +67,9 @@ static size_t enc_tape_layout(const arcvae_dims& d, int B, int T, int path, void
   tt.logvar = a.take<float>((size_t)B * d.L);
   tt.h_last = a.take<float>((size_t)B * H);
   tt.err = a.take<int>(4);
+  const size_t Rpad = (size_t)T * (((size_t)B + 127) / 128 * 128);   // cluster path: tile-padded, thread-friendly tape
   for (int l = 0; l < d.NL; l++) {
-    tt.c[l] = a.take<float>(R * H);
+    tt.c[l] = a.take<float>((path == PATH_CLUSTER ? Rpad : R) * H);
     if (path != PATH_CLUSTER) {
       tt.gates[l] = a.take<float>(R * 4 * H);
       tt.h[l] = a.take<float>(R * H);
@@ -78,11 +80,14 @@ static size_t enc_tape_layout(const arcvae_dims& d, int B, int T, int path, void
       if (l >= 1) tt.Wxb[l] = a.take<bf16>(4 * H * H);
     }
     if (path == PATH_CLUSTER) {
-      tt.gates_b[l] = a.take<bf16>(R * 4 * H);
+      tt.gates_b[l] = a.take<bf16>(Rpad * 4 * H);
       tt.WhTb[l] = a.take<bf16>(4 * H * H);
     }
   }
-  if (path == PATH_CLUSTER) tt.Pb = a.take<bf16>(R * 4 * H);
+  if (path == PATH_CLUSTER) {
+    tt.Pb = a.take<bf16>(R * 4 * H);
+    tt.table0b = a.take<bf16>((size_t)d.V * 4 * H);
+  }
   if (t) *t = tt;
   return align_up(a.off, 256);
 }
@@ -223,6 +228,7 @@ extern "C" int arcvae_encoder_forward(const arcvae_dims* d, const arcvae_encoder
 
   if (path == PATH_CLUSTER) {
     ARCVAE_CUDA(cudaMemsetAsync(tp.err, 0, sizeof(int), st));
+    ARCVAE_TRY(f32_to_bf16(tp.table0, tp.table0b, (long)d->V * G4, st));
     for (int l = 0; l < d->NL; l++) {
       if (l >= 1) {
         // time-parallel input projection, bf16 out (bias included): Pb = hb_{l-1} @ Wx_l^T + b_l
@@ -234,7 +240,7 @@ extern "C" int arcvae_encoder_forward(const arcvae_dims* d, const arcvae_encoder
         g.rm = id; g.a_rows_total = R;
         ARCVAE_TRY(gemm_tc(g, st));
       }
-      ARCVAE_TRY(lstm_cluster_forward(B, T, H, tp.Whb[l], tp.xT, l == 0 ? tp.table0 : nullptr, l == 0 ? nullptr : tp.Pb,
+      ARCVAE_TRY(lstm_cluster_forward(B, T, H, tp.Whb[l], tp.xT, l == 0 ? tp.table0b : nullptr, l == 0 ? nullptr : tp.Pb,
                                       tp.hb[l], tp.gates_b[l], tp.c[l], l == d->NL - 1 ? tp.h_last : nullptr, tp.err, st));
     }
     return head_forward(*d, p, tp, tp.h_last, cond, B, mu, logvar, st);

@@ -86,7 +86,7 @@ int transpose_to_bf16(const float* src, int R, int C, __nv_bfloat16* dst, cudaSt
 
 // persistent cluster LSTM recurrence (lstm_cluster.cu), H == 256
 bool lstm_cluster_supported(int H);
-int lstm_cluster_forward(int B, int T, int H, const __nv_bfloat16* Whb, const int32_t* xT, const float* table0,
+int lstm_cluster_forward(int B, int T, int H, const __nv_bfloat16* Whb, const int32_t* xT, const __nv_bfloat16* table0b,
                          const __nv_bfloat16* Pb, __nv_bfloat16* hb, __nv_bfloat16* gates_b, float* c, float* h_last,
                          int* err_flag, cudaStream_t st);
 int lstm_cluster_backward(int B, int T, int H, const __nv_bfloat16* WhTb, const __nv_bfloat16* gates_b, const float* c,
