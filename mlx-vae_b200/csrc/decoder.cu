@@ -12,6 +12,7 @@
 // its timesteps (time-major rows r = t*B + b, reached through a RowMap).
 //   layer 0  : gather of table = Emb @ Wx0[:, :E]^T + b0 (rows i,g,o only) + cond (x) Wx0[:, E:]  — no GEMM needed
 //   layer l>0: GEMM [rows,H] x [H,3H] on the compacted (i,g,o) weight rows
+#include <cstdlib>
 #include <vector>
 
 #include "kernels.cuh"
@@ -25,12 +26,29 @@ struct DecPrep {
   float* wc;                      // [3H,C]
   __nv_bfloat16* Wxcb[ARCVAE_MAX_LAYERS];  // bf16 [3H,H], l >= 1
   __nv_bfloat16* Woutb;                    // bf16 [V,H]
+  // fused path: tile-permuted compact gates (row p = j*192 + gi*64 + u), so that one 192-wide GEMM tile holds
+  // i, g, o of the same 64 hidden units and the cell can run in the GEMM epilogue
+  float* Wxp[ARCVAE_MAX_LAYERS];           // fp32 [3H,H], l >= 1
+  float* bp[ARCVAE_MAX_LAYERS];            // fp32 [3H]
+  __nv_bfloat16* Wxpb[ARCVAE_MAX_LAYERS];  // bf16 [3H,H]
 };
+
+static bool dec_fused_ok(const arcvae_dims& d, int precision, int B, bool row_mapped) {
+  if (precision != ARCVAE_PREC_BF16 || d.H % 64 != 0 || d.NL < 1) return false;
+  if (row_mapped && (B % 128) != 0) return false;
+  return std::getenv("ARCVAE_NO_FUSED_DEC") == nullptr;
+}
 
 static void dec_prep_layout(const arcvae_dims& d, Arena& a, DecPrep* p) {
   for (int l = 0; l < ARCVAE_MAX_LAYERS; l++) p->Wxcb[l] = nullptr;
   for (int l = 1; l < d.NL; l++) p->Wxcb[l] = a.take<__nv_bfloat16>((size_t)3 * d.H * d.H);
   p->Woutb = a.take<__nv_bfloat16>((size_t)d.V * d.H);
+  for (int l = 0; l < ARCVAE_MAX_LAYERS; l++) { p->Wxp[l] = nullptr; p->bp[l] = nullptr; p->Wxpb[l] = nullptr; }
+  for (int l = 1; l < d.NL; l++) {
+    p->Wxp[l] = a.take<float>((size_t)3 * d.H * d.H);
+    p->bp[l] = a.take<float>((size_t)3 * d.H);
+    p->Wxpb[l] = a.take<__nv_bfloat16>((size_t)3 * d.H * d.H);
+  }
   for (int l = 0; l < d.NL; l++) {
     int D = (l == 0) ? d.E + d.C : d.H;
     p->Wxc[l] = a.take<float>((size_t)3 * d.H * D);
@@ -55,6 +73,13 @@ static int dec_prepare(const arcvae_dims& d, const arcvae_decoder_params* p, con
   if (precision == ARCVAE_PREC_BF16) {
     for (int l = 1; l < d.NL; l++) ARCVAE_TRY(f32_to_bf16(pr.Wxc[l], pr.Wxcb[l], (long)H3 * H, st));
     ARCVAE_TRY(f32_to_bf16(p->fc_out_w, pr.Woutb, (long)d.V * H, st));
+    if (d.H % 64 == 0) {
+      for (int l = 1; l < d.NL; l++) {
+        ARCVAE_TRY(compact_perm_gates(p->Wx[l], H, H, pr.Wxp[l], st));
+        ARCVAE_TRY(compact_perm_gates(p->bias[l], H, 1, pr.bp[l], st));
+        ARCVAE_TRY(f32_to_bf16(pr.Wxp[l], pr.Wxpb[l], (long)H3 * H, st));
+      }
+    }
   }
   return 0;
 }
@@ -67,6 +92,7 @@ struct DecTape {
   int* tlists;                       // [2T] level lists + feedback lists
   uint8_t* mask;                     // [T]
   __nv_bfloat16* hdb[ARCVAE_MAX_LAYERS];   // bf16 [R,H] copies (tensor-core operands)
+  __nv_bfloat16* gates_b[ARCVAE_MAX_LAYERS];   // fused path: bf16 [R,3H] activated gates, tile-permuted, l >= 1
 };
 
 static size_t dec_tape_layout(const arcvae_dims& d, int B, int T, void* base, size_t cap, DecTape* t) {
@@ -82,6 +108,7 @@ static size_t dec_tape_layout(const arcvae_dims& d, int B, int T, void* base, si
   tt.tlists = a.take<int>((size_t)2 * T + 2);
   tt.mask = a.take<uint8_t>((size_t)T + 16);
   for (int l = 0; l < d.NL; l++) tt.hdb[l] = a.take<__nv_bfloat16>(R * d.H);
+  for (int l = 0; l < d.NL; l++) tt.gates_b[l] = (l >= 1) ? a.take<__nv_bfloat16>(R * 3 * d.H) : nullptr;
   if (t) *t = tt;
   return align_up(a.off, 256);
 }
@@ -95,6 +122,7 @@ struct DecScratch {
   float* dwc;                         // [3H,C]
   __nv_bfloat16* dlb;                 // bf16 [R,V] copy of dlogits
   __nv_bfloat16* dGb;                 // bf16 [R,3H] copy of the pre-activation gradients
+  __nv_bfloat16* dGb2;                // fused path: second [R,3H] buffer (ping-pong between layers, layer-0 dG)
 };
 
 static size_t dec_scratch_layout(const arcvae_dims& d, int B, int T, void* base, size_t cap, DecScratch* s) {
@@ -113,6 +141,7 @@ static size_t dec_scratch_layout(const arcvae_dims& d, int B, int T, void* base,
   ss.dwc = a.take<float>((size_t)3 * d.H * d.C);
   ss.dlb = a.take<__nv_bfloat16>(R * d.V);
   ss.dGb = a.take<__nv_bfloat16>(R * 3 * d.H);
+  ss.dGb2 = a.take<__nv_bfloat16>(R * 3 * d.H);
   if (s) *s = ss;
   return align_up(a.off, 256);
 }
@@ -132,16 +161,29 @@ __global__ void k_init_dec_inputs(const int32_t* __restrict__ target, const uint
 // one batched pass of the decoder stack over the rows selected by `rm`
 static int dec_stack_forward(const arcvae_dims& d, const arcvae_decoder_params* p, const DecPrep& pr, const float* cond,
                              const int32_t* in_tok, int B, int nrows, RowMap rm, long rows_total, float* const* hd,
-                             __nv_bfloat16* const* hdb, float* const* G, float* logits, int precision, cudaStream_t st) {
+                             __nv_bfloat16* const* hdb, float* const* G, __nv_bfloat16* const* gates_b, float* logits,
+                             int precision, bool fused, cudaStream_t st) {
   const int H = d.H, H3 = 3 * d.H;
   const bool bf = precision == ARCVAE_PREC_BF16;
-  ARCVAE_TRY(dec_cell0_fwd(pr.table, pr.wc, in_tok, cond, B, d.C, H, nrows, rm, hd[0], bf ? hdb[0] : nullptr, st));
+  ARCVAE_TRY(dec_cell0_fwd(pr.table, pr.wc, in_tok, cond, B, d.C, H, nrows, rm, fused ? nullptr : hd[0],
+                           bf ? hdb[0] : nullptr, st));
   for (int l = 1; l < d.NL; l++) {
-    ARCVAE_TRY(gemm_any(precision, 0, 1, nrows, H3, H, Mat{hd[l - 1], bf ? hdb[l - 1] : nullptr, H},
-                        Mat{pr.Wxc[l], pr.Wxcb[l], H}, G[l], H3, pr.bc[l], false, rm, rows_total, st));
-    ARCVAE_TRY(dec_cell_fwd(G[l], hd[l], bf ? hdb[l] : nullptr, H, nrows, rm, st));
+    if (fused) {
+      // GEMM + zero-state cell in the epilogue: h_{l-1} @ Wxp_l^T + bp_l -> (i,g,o) -> h_l ; gates saved as bf16
+      TcGemm g{};
+      g.M = nrows; g.N = H3; g.K = H;
+      g.A = hdb[l - 1]; g.lda = H; g.a_mn = false;
+      g.B = pr.Wxpb[l]; g.ldb = H; g.b_mn = false;
+      g.bias = pr.bp[l]; g.accumulate = false; g.splitk = 1; g.rm = rm; g.a_rows_total = rows_total;
+      g.epi = TC_EPI_DEC_CELL_FWD; g.gates_b = gates_b[l]; g.hb_out = hdb[l]; g.Hh = H;
+      ARCVAE_TRY(gemm_tc(g, st));
+    } else {
+      ARCVAE_TRY(gemm_any(precision, 0, 1, nrows, H3, H, Mat{hd[l - 1], bf ? hdb[l - 1] : nullptr, H},
+                          Mat{pr.Wxc[l], pr.Wxcb[l], H}, G[l], H3, pr.bc[l], false, rm, rows_total, st));
+      ARCVAE_TRY(dec_cell_fwd(G[l], hd[l], bf ? hdb[l] : nullptr, H, nrows, rm, st));
+    }
   }
-  ARCVAE_TRY(gemm_any(precision, 0, 1, nrows, d.V, H, Mat{hd[d.NL - 1], bf ? hdb[d.NL - 1] : nullptr, H},
+  ARCVAE_TRY(gemm_any(precision, 0, 1, nrows, d.V, H, Mat{fused ? nullptr : hd[d.NL - 1], bf ? hdb[d.NL - 1] : nullptr, H},
                       Mat{p->fc_out_w, pr.Woutb, H}, logits, d.V, p->fc_out_b, false, rm, rows_total, st));
   return 0;
 }
@@ -217,7 +259,7 @@ extern "C" int arcvae_decoder_forward(const arcvae_dims* d, const arcvae_decoder
     RowMap rm{tp.tlists + off_t[lv], B};
     int nrows = n_t[lv] * B;
     ARCVAE_TRY(dec_stack_forward(*d, p, tp.prep, cond, tp.in_tok, B, nrows, rm, (long)T * B, tp.hd, tp.hdb, tp.G,
-                                 logits_tm, precision, st));
+                                 tp.gates_b, logits_tm, precision, dec_fused_ok(*d, precision, B, true), st));
     ARCVAE_TRY(argmax_feedback(logits_tm, tp.tlists + off_f[lv], n_f[lv], B, d->V, tp.in_tok, st));
   }
   if (dec_inputs_tm != nullptr)
@@ -245,13 +287,54 @@ extern "C" int arcvae_decoder_backward(const arcvae_dims* d, const arcvae_decode
   const int top = d->NL - 1;
 
   const bool bf = precision == ARCVAE_PREC_BF16;
+  const bool fused = dec_fused_ok(*d, precision, B, true);
   if (bf) ARCVAE_TRY(f32_to_bf16(dlogits_tm, sc.dlb, R * V, st));
   // fc_out: logits = h_top @ Wout^T + b
   ARCVAE_TRY(gemm_any(precision, 1, 0, V, H, (int)R, Mat{dlogits_tm, bf ? sc.dlb : nullptr, V},
-                      Mat{tp.hd[top], bf ? tp.hdb[top] : nullptr, H}, g->fc_out_w, H, nullptr, true, id, R, st));
+                      Mat{fused ? nullptr : tp.hd[top], bf ? tp.hdb[top] : nullptr, H}, g->fc_out_w, H, nullptr, true, id, R, st));
   ARCVAE_TRY(colsum(dlogits_tm, R, V, V, g->fc_out_b, st));
   float* dh = sc.dh[0];
   float* dh_next = sc.dh[1];
+
+  if (fused) {
+    // every "d h = dG_upper @ W" GEMM runs the cell-backward of the layer below in its epilogue; only bf16 dG is stored
+    auto fused_gemm = [&](const __nv_bfloat16* A, int K, const __nv_bfloat16* Bw, int layer_below,
+                          __nv_bfloat16* out) -> int {
+      TcGemm q{};
+      q.M = (int)R; q.N = H; q.K = K;
+      q.A = A; q.lda = K; q.a_mn = false;
+      q.B = Bw; q.ldb = H; q.b_mn = true;                       // B[k*H + n]: row-major [K,H]
+      q.accumulate = false; q.splitk = 1; q.rm = id; q.a_rows_total = R; q.Hh = H; q.dg_out = out;
+      if (layer_below >= 1) {
+        q.epi = TC_EPI_DEC_CELL_BWD; q.gates_b = tp.gates_b[layer_below];
+      } else {
+        q.epi = TC_EPI_DEC_CELL0_BWD; q.table = tp.prep.table; q.wc = tp.prep.wc; q.tok = tp.in_tok; q.cond = cond;
+        q.Bt = B; q.Cc = C;
+      }
+      return gemm_tc(q, st);
+    };
+    __nv_bfloat16* cur = sc.dGb;
+    __nv_bfloat16* nxt = sc.dGb2;
+    ARCVAE_TRY(fused_gemm(sc.dlb, V, tp.prep.Woutb, top, cur));   // d h_top = dlogits @ Wout, then cell backward of `top`
+    for (int l = top; l >= 1; l--) {
+      // cur = dG_l (tile-permuted compact layout)
+      ARCVAE_CUDA(cudaMemsetAsync(sc.dWxc[l], 0, (size_t)H3 * H * sizeof(float), st));
+      ARCVAE_CUDA(cudaMemsetAsync(sc.dbc[l], 0, (size_t)H3 * sizeof(float), st));
+      ARCVAE_TRY(gemm_any(precision, 1, 0, H3, H, (int)R, Mat{nullptr, cur, H3}, Mat{nullptr, tp.hdb[l - 1], H}, sc.dWxc[l], H,
+                          nullptr, true, id, R, st));
+      ARCVAE_TRY(colsum_bf16(cur, R, H3, H3, sc.dbc[l], st));
+      ARCVAE_TRY(fused_gemm(cur, H3, tp.prep.Wxpb[l], l - 1, nxt));
+      ARCVAE_TRY(expand_perm_gates_add(sc.dWxc[l], H, H, g->Wx[l], st));
+      ARCVAE_TRY(expand_perm_gates_add(sc.dbc[l], H, 1, g->bias[l], st));
+      __nv_bfloat16* tmp = cur; cur = nxt; nxt = tmp;
+    }
+    // cur = dG_0 in the natural compact (i|g|o) layout
+    ARCVAE_CUDA(cudaMemsetAsync(sc.dtable, 0, (size_t)V * H3 * sizeof(float), st));
+    ARCVAE_CUDA(cudaMemsetAsync(sc.dwc, 0, (size_t)H3 * C * sizeof(float), st));
+    ARCVAE_CUDA(cudaMemsetAsync(sc.dWxc[0], 0, (size_t)H3 * (E + C) * sizeof(float), st));
+    ARCVAE_CUDA(cudaMemsetAsync(sc.dbc[0], 0, (size_t)H3 * sizeof(float), st));
+    ARCVAE_TRY(scatter_rows_by_token_bf16_w(cur, tp.in_tok, R, H3, V, sc.dtable, cond, B, C, sc.dwc, st));
+  } else {
   ARCVAE_TRY(gemm_any(precision, 0, 0, (int)R, H, V, Mat{dlogits_tm, bf ? sc.dlb : nullptr, V},
                       Mat{p->fc_out_w, tp.prep.Woutb, H}, dh, H, nullptr, false, id, R, st));
 
@@ -275,6 +358,7 @@ extern "C" int arcvae_decoder_backward(const arcvae_dims* d, const arcvae_decode
   ARCVAE_CUDA(cudaMemsetAsync(sc.dWxc[0], 0, (size_t)H3 * (E + C) * sizeof(float), st));
   ARCVAE_CUDA(cudaMemsetAsync(sc.dbc[0], 0, (size_t)H3 * sizeof(float), st));
   ARCVAE_TRY(scatter_rows_by_token(sc.dG0, tp.in_tok, R, H3, V, sc.dtable, cond, B, C, sc.dwc, st));
+  }
   ARCVAE_TRY(colsum(sc.dtable, V, H3, H3, sc.dbc[0], st));
   // table = Emb @ Wx0c[:, :E]^T + b0c
   ARCVAE_TRY(gemm_f32(0, 0, V, E, H3, sc.dtable, H3, tp.prep.Wxc[0], E + C, g->embedding, E, nullptr, true, id, 1, st));
@@ -296,6 +380,7 @@ struct SamplerWs {
   float* G[ARCVAE_MAX_LAYERS];   // [B,3H]
   float* logits;     // [B,V]
   __nv_bfloat16* hdb[ARCVAE_MAX_LAYERS];  // bf16 [B,H]
+  __nv_bfloat16* gates_b[ARCVAE_MAX_LAYERS];  // bf16 [B,3H] (fused path scratch)
 };
 static size_t sampler_layout(const arcvae_dims& d, int B, void* base, size_t cap, SamplerWs* w) {
   Arena a(base, cap);
@@ -310,6 +395,7 @@ static size_t sampler_layout(const arcvae_dims& d, int B, void* base, size_t cap
   }
   ww.logits = a.take<float>((size_t)B * d.V);
   for (int l = 0; l < d.NL; l++) ww.hdb[l] = a.take<__nv_bfloat16>((size_t)B * d.H);
+  for (int l = 0; l < d.NL; l++) ww.gates_b[l] = (l >= 1) ? a.take<__nv_bfloat16>((size_t)B * 3 * d.H) : nullptr;
   if (w) *w = ww;
   return align_up(a.off, 256);
 }
@@ -343,7 +429,8 @@ extern "C" int arcvae_sample(const arcvae_dims* d, const arcvae_decoder_params* 
     // the reference checks `early_stopping and all(has_ended)` BEFORE each step (:87-88); the device records the first
     // such step in *t_stop and the host slices; later columns are scratch
     if (early_stopping && t > 0) ARCVAE_TRY(sampler_check_stop(ws.ended_count, B, t, t_stop, st));
-    ARCVAE_TRY(dec_stack_forward(*d, p, ws.prep, cond, ws.cur, B, B, id, B, ws.hd, ws.hdb, ws.G, ws.logits, precision, st));
+    ARCVAE_TRY(dec_stack_forward(*d, p, ws.prep, cond, ws.cur, B, B, id, B, ws.hd, ws.hdb, ws.G, ws.gates_b, ws.logits,
+                                 precision, dec_fused_ok(*d, precision, B, false), st));
     ARCVAE_TRY(select_token(ws.logits, B, d->V, temperature, multinomial, seed, t, max_length, d->end_token, tokens,
                             ws.cur, ws.ended, ws.ended_count, st));
   }

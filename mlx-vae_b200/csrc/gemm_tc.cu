@@ -36,7 +36,51 @@ struct TcParams {
   const float* bias;
   int accumulate;
   RowMap rm;
+  // fused decoder epilogues
+  int epi;
+  bf16* gates_b; bf16* hb_out; bf16* dg_out;
+  const float* table; const float* wc; const int32_t* tok; const float* cond;
+  int Bt, Cc, Hh;
 };
+
+__device__ __forceinline__ float tanh_fast_(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_fast_(float x) { return fmaf(tanh_fast_(0.5f * x), 0.5f, 0.5f); }
+__device__ __forceinline__ void store16_bf16(bf16* dst, const float (&v)[16]) {
+  uint32_t pk[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    pk[j] = *reinterpret_cast<uint32_t*>(&t);
+  }
+  *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  *reinterpret_cast<uint4*>(dst + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+}
+__device__ __forceinline__ void load16_bf16(const bf16* src, float (&v)[16]) {
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(src));
+  const uint4 b = __ldg(reinterpret_cast<const uint4*>(src + 8));
+  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    float2 t = __bfloat1622float2(pa[j]);
+    v[2 * j] = t.x; v[2 * j + 1] = t.y;
+    float2 w = __bfloat1622float2(pb[j]);
+    v[8 + 2 * j] = w.x; v[8 + 2 * j + 1] = w.y;
+  }
+}
+// zero-state decoder cell backward: (i, g, o activated, dh) -> pre-activation gradients
+__device__ __forceinline__ void dec_cell_grads_fast(float i_, float g_, float o_, float dh, float& dai, float& dag,
+                                                    float& dao) {
+  const float tcv = tanh_fast_(i_ * g_);
+  const float dcc = dh * o_ * (1.f - tcv * tcv);
+  dao = dh * tcv * o_ * (1.f - o_);
+  dai = dcc * g_ * i_ * (1.f - i_);
+  dag = dcc * i_ * (1.f - g_ * g_);
+}
 
 struct __align__(8) TcShared {
   uint64_t full[TC_MAX_STAGES];
@@ -173,6 +217,80 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
       const bool atomic = p.splitk > 1;
       const bool add_bias = p.bias != nullptr && (tile / (p.mt * p.nt)) == 0;
+      if (p.epi == TC_EPI_DEC_CELL_FWD) {
+        // accumulator columns of this 192-wide tile: [0,64) = i, [64,128) = g, [128,192) = o of units 64*ni .. 64*ni+63
+        const int H = p.Hh;
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+          uint32_t ri[16], rg[16], ro[16];
+          tc::tmem_ld16(taddr + c0, ri);
+          tc::tmem_ld16(taddr + 64 + c0, rg);
+          tc::tmem_ld16(taddr + 128 + c0, ro);
+          tc::tmem_ld_wait();
+          if (row_ok) {
+            float gi[16], gg[16], go[16], hv[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+              gi[k] = sigmoid_fast_(__uint_as_float(ri[k]) + p.bias[n0 + c0 + k]);
+              gg[k] = tanh_fast_(__uint_as_float(rg[k]) + p.bias[n0 + 64 + c0 + k]);
+              go[k] = sigmoid_fast_(__uint_as_float(ro[k]) + p.bias[n0 + 128 + c0 + k]);
+              hv[k] = go[k] * tanh_fast_(gi[k] * gg[k]);
+            }
+            store16_bf16(p.hb_out + grow * H + ni * 64 + c0, hv);
+            bf16* gb = p.gates_b + grow * 3L * H + n0 + c0;
+            store16_bf16(gb, gi);
+            store16_bf16(gb + 64, gg);
+            store16_bf16(gb + 128, go);
+          }
+        }
+      } else if (p.epi == TC_EPI_DEC_CELL_BWD || p.epi == TC_EPI_DEC_CELL0_BWD) {
+        // accumulator = d h for units n0 + c; emit the pre-activation gradients of the zero-state cell
+        const int H = p.Hh;
+        int tokv = 0;
+        const float* crow = nullptr;
+        if (p.epi == TC_EPI_DEC_CELL0_BWD && row_ok) {
+          tokv = p.tok[grow];
+          crow = p.cond + (grow % p.Bt) * p.Cc;
+        }
+        for (int c0 = 0; c0 < p.BN; c0 += 16) {
+          uint32_t r[16];
+          tc::tmem_ld16(taddr + c0, r);
+          tc::tmem_ld_wait();
+          const int n = n0 + c0;                       // first unit of this chunk (16 units, same 64-block)
+          if (row_ok && n < H) {
+            float dai[16], dag[16], dao[16];
+            if (p.epi == TC_EPI_DEC_CELL_BWD) {
+              const long off = grow * 3L * H + (n / 64) * 192 + (n % 64);
+              float gi[16], gg[16], go[16];
+              load16_bf16(p.gates_b + off, gi);
+              load16_bf16(p.gates_b + off + 64, gg);
+              load16_bf16(p.gates_b + off + 128, go);
+#pragma unroll
+              for (int k = 0; k < 16; k++) dec_cell_grads_fast(gi[k], gg[k], go[k], __uint_as_float(r[k]), dai[k], dag[k], dao[k]);
+              store16_bf16(p.dg_out + off, dai);
+              store16_bf16(p.dg_out + off + 64, dag);
+              store16_bf16(p.dg_out + off + 128, dao);
+            } else {
+              const float* trow = p.table + (long)tokv * 3 * H + n;
+#pragma unroll
+              for (int k = 0; k < 16; k++) {
+                float ai = __ldg(trow + k), ag = __ldg(trow + H + k), ao = __ldg(trow + 2 * H + k);
+                for (int c = 0; c < p.Cc; c++) {
+                  const float cv = crow[c];
+                  ai = fmaf(cv, __ldg(p.wc + (long)(n + k) * p.Cc + c), ai);
+                  ag = fmaf(cv, __ldg(p.wc + (long)(H + n + k) * p.Cc + c), ag);
+                  ao = fmaf(cv, __ldg(p.wc + (long)(2 * H + n + k) * p.Cc + c), ao);
+                }
+                dec_cell_grads_fast(sigmoid_fast_(ai), tanh_fast_(ag), sigmoid_fast_(ao), __uint_as_float(r[k]), dai[k],
+                                    dag[k], dao[k]);
+              }
+              bf16* dst = p.dg_out + grow * 3L * H + n;
+              store16_bf16(dst, dai);
+              store16_bf16(dst + H, dag);
+              store16_bf16(dst + 2 * H, dao);
+            }
+          }
+        }
+      } else {
       for (int c0 = 0; c0 < p.BN; c0 += 16) {
         uint32_t r[16];
         tc::tmem_ld16(taddr + c0, r);
@@ -225,6 +343,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
+      }
       }
       tc::tc_fence_before();
       __syncwarp();
@@ -290,7 +409,7 @@ int pick_splitk_tc(int M, int N, int K);
 
 int gemm_tc(const TcGemm& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return 0;
-  ARCVAE_REQUIRE(g.C != nullptr || g.Cb != nullptr, "gemm_tc needs an output");
+  ARCVAE_REQUIRE(g.C != nullptr || g.Cb != nullptr || g.epi != TC_EPI_PLAIN, "gemm_tc needs an output");
   ARCVAE_REQUIRE(!(g.a_mn && g.rm.tlist != nullptr), "row map needs a K-major A");
   ARCVAE_REQUIRE(g.rm.tlist == nullptr || (g.rm.Bt % TC_BM) == 0, "row-mapped tiles must not straddle timesteps");
   TcParams p;
@@ -311,6 +430,17 @@ int gemm_tc(const TcGemm& g, cudaStream_t st) {
                  "split-K accumulates with fp32 atomics into C");
   p.C = g.C; p.ldc = g.ldc; p.Cb = g.Cb; p.ldcb = g.ldcb; p.bias = g.bias; p.accumulate = g.accumulate ? 1 : 0;
   p.rm = g.rm;
+  p.epi = g.epi; p.gates_b = g.gates_b; p.hb_out = g.hb_out; p.dg_out = g.dg_out;
+  p.table = g.table; p.wc = g.wc; p.tok = g.tok; p.cond = g.cond; p.Bt = g.Bt; p.Cc = g.Cc; p.Hh = g.Hh;
+  if (g.epi == TC_EPI_DEC_CELL_FWD) {
+    ARCVAE_REQUIRE(g.N % 192 == 0 && g.Hh * 3 == g.N && !g.b_mn && g.bias != nullptr && g.gates_b && g.hb_out,
+                   "fused decoder cell (forward): N = 3H tile-permuted, K-major B, bias");
+    p.BN = 192; p.nt = g.N / 192;
+  } else if (g.epi == TC_EPI_DEC_CELL_BWD || g.epi == TC_EPI_DEC_CELL0_BWD) {
+    ARCVAE_REQUIRE(g.N == g.Hh && g.Hh % 64 == 0 && g.dg_out != nullptr && p.splitk == 1, "fused decoder cell (backward): N = H");
+    ARCVAE_REQUIRE(g.epi != TC_EPI_DEC_CELL_BWD || g.gates_b != nullptr, "saved gates");
+    ARCVAE_REQUIRE(g.epi != TC_EPI_DEC_CELL0_BWD || (g.table && g.wc && g.tok && g.cond), "layer-0 recompute inputs");
+  }
   const size_t stage_bytes = (size_t)TC_BM * TC_BK * 2 + (size_t)p.BN * TC_BK * 2;
   int stages = (int)((200 * 1024) / stage_bytes);
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
@@ -360,7 +490,7 @@ int gemm_any(int precision, int transA, int transB, int M, int N, int K, Mat A, 
   if (tcok && b_mn && !(N % 64 == 0 || N < 64)) tcok = false;
   if (tcok && rm.tlist != nullptr && (rm.Bt % TC_BM) != 0) tcok = false;
   if (tcok) {
-    TcGemm g;
+    TcGemm g{};
     g.M = M; g.N = N; g.K = K;
     g.A = A.b; g.lda = A.ld; g.a_mn = a_mn;
     g.B = B.b; g.ldb = B.ld; g.b_mn = b_mn;
@@ -433,7 +563,7 @@ extern "C" int arcvae_gemm_bf16(int a_mn, int b_mn, int M, int N, int K, const v
                                 float* C, int ldc, void* Cb, int ldcb, const float* bias, int accumulate, int splitk,
                                 void* stream) {
   using namespace arcvae;
-  TcGemm g;
+  TcGemm g{};
   g.M = M; g.N = N; g.K = K;
   g.A = (const bf16*)A; g.lda = lda; g.a_mn = a_mn != 0;
   g.B = (const bf16*)B; g.ldb = ldb; g.b_mn = b_mn != 0;

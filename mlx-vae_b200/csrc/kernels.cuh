@@ -53,6 +53,9 @@ int scatter_rows_by_token(const float* X, const int32_t* tok, long R, int N, int
 int compact_gates(const float* full, int H, int D, float* compact, cudaStream_t st);
 int expand_gates_add(const float* compact, int H, int D, float* full, cudaStream_t st);
 // strided add: dst[r*ldd + c] += src[r*lds + c], r<R, c<Cn
+// tile-permuted compact gates: row p = j*192 + gi*64 + u  <-  full row gate(gi)*H + j*64 + u, gate(0,1,2) = (i,g,o) = (0,2,3)
+int compact_perm_gates(const float* full, int H, int D, float* perm, cudaStream_t st);
+int expand_perm_gates_add(const float* perm, int H, int D, float* full, cudaStream_t st);
 int add_strided(const float* src, int lds, float* dst, int ldd, int R, int Cn, cudaStream_t st);
 
 // greedy feedback (decoder.py:185): tok_next[t+1 rows] = argmax(logits[t rows]) for t in tlist (device list, n entries),
@@ -78,7 +81,18 @@ struct TcGemm {
   int splitk;
   RowMap rm;                                    // rows of A (K-major) and C; rm.Bt must be a multiple of 128
   long a_rows_total;                            // rows of the allocation behind A when rm is used
+  // fused decoder epilogues (zero-state LSTM cell on compact, tile-permuted gates; see decoder.cu)
+  int epi = 0;                                  // TC_EPI_*
+  __nv_bfloat16* gates_b = nullptr;             // [rows,3H] activated gates (written by CELL_FWD, read by CELL_BWD)
+  __nv_bfloat16* hb_out = nullptr;              // [rows,H]  CELL_FWD: h
+  __nv_bfloat16* dg_out = nullptr;              // [rows,3H] CELL_BWD / CELL0_BWD: pre-activation gradients
+  const float* table = nullptr;                 // CELL0_BWD: [V,3H] layer-0 table (i|g|o)
+  const float* wc = nullptr;                    // CELL0_BWD: [3H,C]
+  const int32_t* tok = nullptr;                 // CELL0_BWD: [rows] tokens fed
+  const float* cond = nullptr;                  // CELL0_BWD: [Bt,C]
+  int Bt = 1, Cc = 0, Hh = 0;
 };
+enum { TC_EPI_PLAIN = 0, TC_EPI_DEC_CELL_FWD = 1, TC_EPI_DEC_CELL_BWD = 2, TC_EPI_DEC_CELL0_BWD = 3 };
 int gemm_tc(const TcGemm& g, cudaStream_t st);
 int pick_splitk_tc(int M, int N, int K);
 int f32_to_bf16(const float* src, __nv_bfloat16* dst, long n, cudaStream_t st);
@@ -95,6 +109,9 @@ int lstm_cluster_backward(int B, int T, int H, const __nv_bfloat16* WhTb, const 
 int colsum_bf16(const __nv_bfloat16* X, long R, int N, int ldx, float* out, cudaStream_t st);
 int scatter_rows_by_token_bf16(const __nv_bfloat16* X, const int32_t* tok, long R, int N, int V, float* dtable,
                                cudaStream_t st);
+
+int scatter_rows_by_token_bf16_w(const __nv_bfloat16* X, const int32_t* tok, long R, int N, int V, float* dtable,
+                                 const float* cond, int B, int C, float* dwc, cudaStream_t st);
 
 // the same logical matrix in fp32 and (optionally) bf16; gemm_any picks the tensor-core kernel when precision is bf16
 // and the operands satisfy the TMA constraints, else the fp32 FFMA kernel on the fp32 copies

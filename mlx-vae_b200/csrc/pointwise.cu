@@ -141,7 +141,7 @@ __global__ void k_dec_cell0_fwd(const float* __restrict__ table, const float* __
     dec0_preact(table, wc, cond + (long)b * C, tok[r], C, H, j, ai, ag, ao);
     float cc = sigmoidf_(ai) * tanhf_(ag);
     float hv = sigmoidf_(ao) * tanhf_(cc);
-    h[r * H + j] = hv;
+    if (h != nullptr) h[r * H + j] = hv;
     if (hb != nullptr) hb[r * H + j] = __float2bfloat16(hv);
   }
 }
@@ -409,6 +409,10 @@ int scatter_rows_by_token_bf16(const __nv_bfloat16* X, const int32_t* tok, long 
                                cudaStream_t st) {
   return scatter_t(X, tok, R, N, V, dtable, nullptr, 1, 1, nullptr, st);
 }
+int scatter_rows_by_token_bf16_w(const __nv_bfloat16* X, const int32_t* tok, long R, int N, int V, float* dtable,
+                                 const float* cond, int B, int C, float* dwc, cudaStream_t st) {
+  return scatter_t(X, tok, R, N, V, dtable, cond, B, C, dwc, st);
+}
 
 // ------------------------------------------------------------------------------------------------
 __global__ void k_compact_gates(const float* __restrict__ full, int H, int D, float* __restrict__ compact) {
@@ -436,6 +440,38 @@ __global__ void k_expand_gates_add(const float* __restrict__ compact, int H, int
 }
 int expand_gates_add(const float* compact, int H, int D, float* full, cudaStream_t st) {
   k_expand_gates_add<<<grid_for(3L * H * D, 256), 256, 0, st>>>(compact, H, D, full);
+  ARCVAE_LAUNCHED();
+  return 0;
+}
+__device__ __forceinline__ long perm_to_full_row(long prow, int H) {
+  int j = (int)(prow / 192), rem = (int)(prow % 192);
+  int gi = rem / 64, u = rem % 64;
+  int gate = gi == 0 ? 0 : (gi == 1 ? 2 : 3);
+  return (long)gate * H + j * 64 + u;
+}
+__global__ void k_compact_perm_gates(const float* __restrict__ full, int H, int D, float* __restrict__ perm) {
+  long total = 3L * H * D;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long row = i / D;
+    int c = (int)(i - row * D);
+    perm[i] = full[perm_to_full_row(row, H) * D + c];
+  }
+}
+int compact_perm_gates(const float* full, int H, int D, float* perm, cudaStream_t st) {
+  k_compact_perm_gates<<<grid_for(3L * H * D, 256), 256, 0, st>>>(full, H, D, perm);
+  ARCVAE_LAUNCHED();
+  return 0;
+}
+__global__ void k_expand_perm_gates_add(const float* __restrict__ perm, int H, int D, float* __restrict__ full) {
+  long total = 3L * H * D;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long row = i / D;
+    int c = (int)(i - row * D);
+    full[perm_to_full_row(row, H) * D + c] += perm[i];
+  }
+}
+int expand_perm_gates_add(const float* perm, int H, int D, float* full, cudaStream_t st) {
+  k_expand_perm_gates_add<<<grid_for(3L * H * D, 256), 256, 0, st>>>(perm, H, D, full);
   ARCVAE_LAUNCHED();
   return 0;
 }
