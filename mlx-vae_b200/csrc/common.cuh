@@ -89,6 +89,15 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf
 // tanh with full fp32 accuracy (tanhf is ~1 ulp; the fast-math version is not used: parity is fp32)
 __device__ __forceinline__ float tanhf_(float x) { return tanhf(x); }
 
+// MUFU.TANH based activations (abs error ~2^-11): bf16 paths only, where every gate is rounded to bf16 (2^-9) before
+// it is stored or fed back through the tensor core anyway
+__device__ __forceinline__ float tanh_approx_(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_approx_(float x) { return fmaf(tanh_approx_(0.5f * x), 0.5f, 0.5f); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

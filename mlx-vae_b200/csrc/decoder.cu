@@ -116,13 +116,14 @@ static size_t dec_tape_layout(const arcvae_dims& d, int B, int T, void* base, si
 struct DecScratch {
   float* dh[2];                       // [R,H]
   float* dG0;                         // [R,3H]
-  float* dtable;                      // [V,3H]
+  float* dtable;                      // [max(V, SCATTER_NW),3H]  (rows >= V: scratch of the one-hot GEMM)
   float* dWxc[ARCVAE_MAX_LAYERS];     // compact weight grads
   float* dbc[ARCVAE_MAX_LAYERS];
   float* dwc;                         // [3H,C]
   __nv_bfloat16* dlb;                 // bf16 [R,V] copy of dlogits
   __nv_bfloat16* dGb;                 // bf16 [R,3H] copy of the pre-activation gradients
   __nv_bfloat16* dGb2;                // fused path: second [R,3H] buffer (ping-pong between layers, layer-0 dG)
+  __nv_bfloat16* onehot;              // fused path: [R,SCATTER_NW] one-hot of the fed tokens + cond hi/lo columns
 };
 
 static size_t dec_scratch_layout(const arcvae_dims& d, int B, int T, void* base, size_t cap, DecScratch* s) {
@@ -132,7 +133,7 @@ static size_t dec_scratch_layout(const arcvae_dims& d, int B, int T, void* base,
   ss.dh[0] = a.take<float>(R * d.H);
   ss.dh[1] = a.take<float>(R * d.H);
   ss.dG0 = a.take<float>(R * 3 * d.H);
-  ss.dtable = a.take<float>((size_t)d.V * 3 * d.H);
+  ss.dtable = a.take<float>((size_t)(d.V > SCATTER_NW ? d.V : SCATTER_NW) * 3 * d.H);
   for (int l = 0; l < d.NL; l++) {
     int D = (l == 0) ? d.E + d.C : d.H;
     ss.dWxc[l] = a.take<float>((size_t)3 * d.H * D);
@@ -142,6 +143,7 @@ static size_t dec_scratch_layout(const arcvae_dims& d, int B, int T, void* base,
   ss.dlb = a.take<__nv_bfloat16>(R * d.V);
   ss.dGb = a.take<__nv_bfloat16>(R * 3 * d.H);
   ss.dGb2 = a.take<__nv_bfloat16>(R * 3 * d.H);
+  ss.onehot = a.take<__nv_bfloat16>(R * SCATTER_NW);
   if (s) *s = ss;
   return align_up(a.off, 256);
 }
@@ -329,11 +331,15 @@ extern "C" int arcvae_decoder_backward(const arcvae_dims* d, const arcvae_decode
       __nv_bfloat16* tmp = cur; cur = nxt; nxt = tmp;
     }
     // cur = dG_0 in the natural compact (i|g|o) layout
-    ARCVAE_CUDA(cudaMemsetAsync(sc.dtable, 0, (size_t)V * H3 * sizeof(float), st));
     ARCVAE_CUDA(cudaMemsetAsync(sc.dwc, 0, (size_t)H3 * C * sizeof(float), st));
     ARCVAE_CUDA(cudaMemsetAsync(sc.dWxc[0], 0, (size_t)H3 * (E + C) * sizeof(float), st));
     ARCVAE_CUDA(cudaMemsetAsync(sc.dbc[0], 0, (size_t)H3 * sizeof(float), st));
-    ARCVAE_TRY(scatter_rows_by_token_bf16_w(cur, tp.in_tok, R, H3, V, sc.dtable, cond, B, C, sc.dwc, st));
+    if (scatter_onehot_supported(H3, V, C)) {
+      ARCVAE_TRY(scatter_rows_onehot_tc(cur, tp.in_tok, R, H3, V, sc.onehot, sc.dtable, cond, B, C, sc.dwc, st));
+    } else {
+      ARCVAE_CUDA(cudaMemsetAsync(sc.dtable, 0, (size_t)V * H3 * sizeof(float), st));
+      ARCVAE_TRY(scatter_rows_by_token_bf16_w(cur, tp.in_tok, R, H3, V, sc.dtable, cond, B, C, sc.dwc, st));
+    }
   } else {
   ARCVAE_TRY(gemm_any(precision, 0, 0, (int)R, H, V, Mat{dlogits_tm, bf ? sc.dlb : nullptr, V},
                       Mat{p->fc_out_w, tp.prep.Woutb, H}, dh, H, nullptr, false, id, R, st));
@@ -361,7 +367,8 @@ extern "C" int arcvae_decoder_backward(const arcvae_dims* d, const arcvae_decode
   }
   ARCVAE_TRY(colsum(sc.dtable, V, H3, H3, sc.dbc[0], st));
   // table = Emb @ Wx0c[:, :E]^T + b0c
-  ARCVAE_TRY(gemm_f32(0, 0, V, E, H3, sc.dtable, H3, tp.prep.Wxc[0], E + C, g->embedding, E, nullptr, true, id, 1, st));
+  ARCVAE_TRY(gemm_f32(0, 0, V, E, H3, sc.dtable, H3, tp.prep.Wxc[0], E + C, g->embedding, E, nullptr, true, id,
+                      pick_splitk(V, E, H3), st));
   ARCVAE_TRY(gemm_f32(1, 0, H3, E, V, sc.dtable, H3, p->embedding, E, sc.dWxc[0], E + C, nullptr, true, id, 1, st));
   ARCVAE_TRY(add_strided(sc.dwc, C, sc.dWxc[0] + E, E + C, H3, C, st));
   ARCVAE_TRY(expand_gates_add(sc.dWxc[0], H, E + C, g->Wx[0], st));

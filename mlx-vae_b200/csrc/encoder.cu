@@ -100,8 +100,9 @@ struct EncScratch {
   float* dX;        // [T*B,H]  gradient w.r.t. a layer's input sequence (from the layer above)
   float* dh_rec[2]; // [B,H]
   float* dc;        // [B,H]
-  float* dtable0;   // [V,4H]
+  float* dtable0;   // [max(V, SCATTER_NW),4H]  (rows >= V: scratch of the one-hot GEMM)
   bf16* dAb;        // [T*B,4H] bf16 pre-activation gradients (tensor-core operand / cluster exchange)
+  bf16* onehot;     // [T*B,SCATTER_NW] one-hot tokens (tensor-core scatter)
 };
 
 static size_t enc_scratch_layout(const arcvae_dims& d, int B, int T, int path, void* base, size_t cap, EncScratch* s) {
@@ -115,8 +116,9 @@ static size_t enc_scratch_layout(const arcvae_dims& d, int B, int T, int path, v
   ss.dh_rec[0] = a.take<float>((size_t)B * d.H);
   ss.dh_rec[1] = a.take<float>((size_t)B * d.H);
   ss.dc = a.take<float>((size_t)B * d.H);
-  ss.dtable0 = a.take<float>((size_t)d.V * 4 * d.H);
+  ss.dtable0 = a.take<float>((size_t)(d.V > SCATTER_NW ? d.V : SCATTER_NW) * 4 * d.H);
   ss.dAb = (path != PATH_STEP_F32) ? a.take<bf16>((size_t)T * B * 4 * d.H) : nullptr;
+  ss.onehot = (path != PATH_STEP_F32) ? a.take<bf16>((size_t)T * B * SCATTER_NW) : nullptr;
   if (s) *s = ss;
   return align_up(a.off, 256);
 }
@@ -176,7 +178,8 @@ static int layer0_input_backward(const arcvae_dims& d, const arcvae_encoder_para
   const int G4 = 4 * d.H;
   RowMap id{nullptr, 1};
   ARCVAE_TRY(colsum(sc.dtable0, d.V, G4, G4, g->bias[0], st));
-  ARCVAE_TRY(gemm_f32(0, 0, d.V, d.E, G4, sc.dtable0, G4, p->Wx[0], d.E, g->embedding, d.E, nullptr, true, id, 1, st));
+  ARCVAE_TRY(gemm_f32(0, 0, d.V, d.E, G4, sc.dtable0, G4, p->Wx[0], d.E, g->embedding, d.E, nullptr, true, id,
+                      pick_splitk(d.V, d.E, G4), st));
   ARCVAE_TRY(gemm_f32(1, 0, G4, d.E, d.V, sc.dtable0, G4, p->embedding, d.E, g->Wx[0], d.E, nullptr, true, id, 1, st));
   return 0;
 }
@@ -313,8 +316,12 @@ extern "C" int arcvae_encoder_backward(const arcvae_dims* d, const arcvae_encode
         ARCVAE_TRY(gemm_any(precision, 0, 0, (int)R, H, G4, Mat{nullptr, sc.dAb, G4}, Mat{nullptr, tp.Wxb[l], H}, sc.dX, H,
                             nullptr, false, id, R, st));
       } else {
-        ARCVAE_CUDA(cudaMemsetAsync(sc.dtable0, 0, (size_t)d->V * G4 * sizeof(float), st));
-        ARCVAE_TRY(scatter_rows_by_token_bf16(sc.dAb, tp.xT, R, G4, d->V, sc.dtable0, st));
+        if (scatter_onehot_supported(G4, d->V, 0)) {
+          ARCVAE_TRY(scatter_rows_onehot_tc(sc.dAb, tp.xT, R, G4, d->V, sc.onehot, sc.dtable0, nullptr, B, 0, nullptr, st));
+        } else {
+          ARCVAE_CUDA(cudaMemsetAsync(sc.dtable0, 0, (size_t)d->V * G4 * sizeof(float), st));
+          ARCVAE_TRY(scatter_rows_by_token_bf16(sc.dAb, tp.xT, R, G4, d->V, sc.dtable0, st));
+        }
         ARCVAE_TRY(layer0_input_backward(*d, p, g, sc, st));
       }
     }

@@ -1,11 +1,12 @@
 // gemm_tc.cu — bf16 tensor-core GEMM for the time-parallel contractions of the AR-CVAE step:
 //   D[M,N] (+)= A[M,K] * B[K,N] (+ bias), bf16 operands, fp32 accumulation in TMEM, fp32 and/or bf16 output.
 //
-// sm_100a structure (one CTA per SM, persistent over output tiles, 192 threads):
+// sm_100a structure (one CTA per SM, persistent over output tiles, 320 threads):
 //   warp 0      TMA producer   cp.async.bulk.tensor (SWIZZLE_128B) into a multi-stage smem ring, mbarrier complete_tx
 //   warp 1      MMA issuer     one elected thread issues tcgen05.mma (M=128, N=BN<=256, K=16 per instruction),
 //                              tcgen05.commit releases smem stages / publishes the accumulator
-//   warps 2..5  epilogue       tcgen05.ld (32x32b) of the accumulator quarter they own, bias / accumulate / split-K atomics
+//   warps 2..9  epilogue       tcgen05.ld (32x32b) of the accumulator quarter they own (two warps per quarter, half of
+//                              the columns each), bias / accumulate / split-K atomics / fused decoder cells
 // Two accumulators (2 x BN TMEM columns) let the epilogue of tile i overlap the MMAs of tile i+1.
 //
 // Operand layouts (both served by TMA, no transposes in HBM):
@@ -23,7 +24,8 @@ using bf16 = __nv_bfloat16;
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
 constexpr int TC_MAX_STAGES = 8;
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;            // two warps per TMEM lane quarter, each takes half of the tile's columns
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 
 struct TcParams {
   int M, N, K;
@@ -43,12 +45,8 @@ struct TcParams {
   int Bt, Cc, Hh;
 };
 
-__device__ __forceinline__ float tanh_fast_(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float sigmoid_fast_(float x) { return fmaf(tanh_fast_(0.5f * x), 0.5f, 0.5f); }
+__device__ __forceinline__ float tanh_fast_(float x) { return tanh_approx_(x); }
+__device__ __forceinline__ float sigmoid_fast_(float x) { return sigmoid_approx_(x); }
 __device__ __forceinline__ void store16_bf16(bf16* dst, const float (&v)[16]) {
   uint32_t pk[8];
 #pragma unroll
@@ -116,7 +114,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; a++) {
       tc::mbar_init(&sh->tmem_full[a], 1);
-      tc::mbar_init(&sh->tmem_empty[a], 4);
+      tc::mbar_init(&sh->tmem_empty[a], TC_EPI_WARPS);
     }
     tc::fence_barrier_init();
   }
@@ -200,8 +198,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ===================================================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1)
+    // ===================================================== epilogue (warps 2..9 -> TMEM lane quarters 2,3,0,1,2,3,0,1)
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;          // which half of the tile's 16-column chunks this warp handles
+    const int nchunks = p.BN >> 4;
+    const int ch_lo = half == 0 ? 0 : (nchunks + 1) >> 1;
+    const int ch_hi = half == 0 ? (nchunks + 1) >> 1 : nchunks;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
       const int mi = tile % p.mt;
@@ -220,7 +222,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (p.epi == TC_EPI_DEC_CELL_FWD) {
         // accumulator columns of this 192-wide tile: [0,64) = i, [64,128) = g, [128,192) = o of units 64*ni .. 64*ni+63
         const int H = p.Hh;
-        for (int c0 = 0; c0 < 64; c0 += 16) {
+        for (int c0 = half * 32; c0 < half * 32 + 32; c0 += 16) {
           uint32_t ri[16], rg[16], ro[16];
           tc::tmem_ld16(taddr + c0, ri);
           tc::tmem_ld16(taddr + 64 + c0, rg);
@@ -251,7 +253,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tokv = p.tok[grow];
           crow = p.cond + (grow % p.Bt) * p.Cc;
         }
-        for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        for (int c0 = ch_lo * 16; c0 < ch_hi * 16; c0 += 16) {
           uint32_t r[16];
           tc::tmem_ld16(taddr + c0, r);
           tc::tmem_ld_wait();
@@ -271,18 +273,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               store16_bf16(p.dg_out + off + 128, dao);
             } else {
               const float* trow = p.table + (long)tokv * 3 * H + n;
+              float a3[3][16];
 #pragma unroll
-              for (int k = 0; k < 16; k++) {
-                float ai = __ldg(trow + k), ag = __ldg(trow + H + k), ao = __ldg(trow + 2 * H + k);
-                for (int c = 0; c < p.Cc; c++) {
-                  const float cv = crow[c];
-                  ai = fmaf(cv, __ldg(p.wc + (long)(n + k) * p.Cc + c), ai);
-                  ag = fmaf(cv, __ldg(p.wc + (long)(H + n + k) * p.Cc + c), ag);
-                  ao = fmaf(cv, __ldg(p.wc + (long)(2 * H + n + k) * p.Cc + c), ao);
+              for (int g = 0; g < 3; g++)
+#pragma unroll
+                for (int k4 = 0; k4 < 4; k4++) {
+                  const float4 v = __ldg(reinterpret_cast<const float4*>(trow + g * H) + k4);
+                  a3[g][4 * k4] = v.x; a3[g][4 * k4 + 1] = v.y; a3[g][4 * k4 + 2] = v.z; a3[g][4 * k4 + 3] = v.w;
                 }
-                dec_cell_grads_fast(sigmoid_fast_(ai), tanh_fast_(ag), sigmoid_fast_(ao), __uint_as_float(r[k]), dai[k],
-                                    dag[k], dao[k]);
+              if (p.Cc == 1) {
+                const float cv = __ldg(crow);
+#pragma unroll
+                for (int g = 0; g < 3; g++)
+#pragma unroll
+                  for (int k4 = 0; k4 < 4; k4++) {
+                    const float4 w = __ldg(reinterpret_cast<const float4*>(p.wc + g * H + n) + k4);
+                    a3[g][4 * k4] = fmaf(cv, w.x, a3[g][4 * k4]); a3[g][4 * k4 + 1] = fmaf(cv, w.y, a3[g][4 * k4 + 1]);
+                    a3[g][4 * k4 + 2] = fmaf(cv, w.z, a3[g][4 * k4 + 2]); a3[g][4 * k4 + 3] = fmaf(cv, w.w, a3[g][4 * k4 + 3]);
+                  }
+              } else {
+                for (int c = 0; c < p.Cc; c++) {
+                  const float cv = __ldg(crow + c);
+#pragma unroll
+                  for (int g = 0; g < 3; g++)
+#pragma unroll
+                    for (int k = 0; k < 16; k++)
+                      a3[g][k] = fmaf(cv, __ldg(p.wc + (long)(g * H + n + k) * p.Cc + c), a3[g][k]);
+                }
               }
+#pragma unroll
+              for (int k = 0; k < 16; k++)
+                dec_cell_grads_fast(sigmoid_fast_(a3[0][k]), tanh_fast_(a3[1][k]), sigmoid_fast_(a3[2][k]),
+                                    __uint_as_float(r[k]), dai[k], dag[k], dao[k]);
               bf16* dst = p.dg_out + grow * 3L * H + n;
               store16_bf16(dst, dai);
               store16_bf16(dst + H, dag);
@@ -291,7 +313,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       } else {
-      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+      for (int c0 = ch_lo * 16; c0 < ch_hi * 16; c0 += 16) {
         uint32_t r[16];
         tc::tmem_ld16(taddr + c0, r);
         tc::tmem_ld_wait();
@@ -509,7 +531,8 @@ int pick_splitk_tc(int M, int N, int K) {
   long tiles = (long)cdiv(M, TC_BM) * cdiv(N, pick_bn(N));
   long kblocks = cdiv(K, TC_BK);
   if (tiles >= 148 || kblocks < 16) return 1;
-  long want = (2 * 148 + tiles - 1) / tiles;
+  long want = (2 * 148) / tiles;              // floor: (tiles x splits) <= two full waves, no straggler wave
+  if (want < 1) want = 1;
   long maxs = kblocks / 8;
   if (maxs < 1) maxs = 1;
   return (int)(want < maxs ? want : maxs);

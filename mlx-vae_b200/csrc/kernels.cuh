@@ -110,6 +110,12 @@ int colsum_bf16(const __nv_bfloat16* X, long R, int N, int ldx, float* out, cuda
 int scatter_rows_by_token_bf16(const __nv_bfloat16* X, const int32_t* tok, long R, int N, int V, float* dtable,
                                cudaStream_t st);
 
+// the same scatter as a tcgen05 GEMM against a materialised one-hot operand (pointwise.cu): dtable_ext is
+// [SCATTER_NW, N] fp32 (rows [0,V) = dtable; rows V+2c, V+2c+1 = hi/lo parts of dwc[:,c]); onehot is bf16 [R, SCATTER_NW]
+constexpr int SCATTER_NW = 128;
+bool scatter_onehot_supported(int N, int V, int C);
+int scatter_rows_onehot_tc(const __nv_bfloat16* X, const int32_t* tok, long R, int N, int V, __nv_bfloat16* onehot,
+                           float* dtable_ext, const float* cond, int B, int C, float* dwc, cudaStream_t st);
 int scatter_rows_by_token_bf16_w(const __nv_bfloat16* X, const int32_t* tok, long R, int N, int V, float* dtable,
                                  const float* cond, int B, int C, float* dwc, cudaStream_t st);
 

@@ -116,12 +116,8 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 // MUFU.TANH based activations (abs error ~2^-11): used on the bf16 path only, where every gate is rounded to bf16
 // (2^-9) before it is stored or fed back through the tensor core anyway
-__device__ __forceinline__ float tanh_fast(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(tanh_fast(0.5f * x), 0.5f, 0.5f); }
+__device__ __forceinline__ float tanh_fast(float x) { return tanh_approx_(x); }
+__device__ __forceinline__ float sigmoid_fast(float x) { return sigmoid_approx_(x); }
 }  // namespace rc
 
 #define RC_STAMP(slot) do { if (p.dbg != nullptr && blockIdx.x < 4 && it < 64) { unsigned long long _gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_gt)); p.dbg[(blockIdx.x * 64 + it) * 16 + (slot)] = (long long)_gt; } } while (0)

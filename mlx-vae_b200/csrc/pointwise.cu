@@ -145,10 +145,65 @@ __global__ void k_dec_cell0_fwd(const float* __restrict__ table, const float* __
     if (hb != nullptr) hb[r * H + j] = __float2bfloat16(hv);
   }
 }
+// vectorised form: one thread = 8 consecutive hidden units of one row (H % 8 == 0).  FAST = MUFU.TANH activations
+// (bf16 path: h is rounded to bf16 anyway); otherwise full-precision expf / tanhf.
+template <bool FAST>
+__global__ void k_dec_cell0_fwd_v8(const float* __restrict__ table, const float* __restrict__ wc,
+                                   const int32_t* __restrict__ tok, const float* __restrict__ cond, int B, int C, int H,
+                                   int R, RowMap rm, float* __restrict__ h, __nv_bfloat16* __restrict__ hb) {
+  const int cpr = H >> 3;                               // 8-unit chunks per row
+  const long total = (long)R * cpr;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / cpr);
+    const int j = (int)(idx - (long)i * cpr) << 3;
+    const long r = rm(i);
+    const float* trow = table + (long)__ldg(tok + r) * 3 * H + j;
+    float a[3][8];
+#pragma unroll
+    for (int g = 0; g < 3; g++) {
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(trow + g * H));
+      const float4 v1 = __ldg(reinterpret_cast<const float4*>(trow + g * H + 4));
+      a[g][0] = v0.x; a[g][1] = v0.y; a[g][2] = v0.z; a[g][3] = v0.w;
+      a[g][4] = v1.x; a[g][5] = v1.y; a[g][6] = v1.z; a[g][7] = v1.w;
+    }
+    const float* crow = cond + (r % B) * C;
+    for (int c = 0; c < C; c++) {
+      const float cv = __ldg(crow + c);
+#pragma unroll
+      for (int g = 0; g < 3; g++)
+#pragma unroll
+        for (int k = 0; k < 8; k++) a[g][k] = fmaf(cv, __ldg(wc + (long)(g * H + j + k) * C + c), a[g][k]);
+    }
+    float hv[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      if (FAST) hv[k] = sigmoid_approx_(a[2][k]) * tanh_approx_(sigmoid_approx_(a[0][k]) * tanh_approx_(a[1][k]));
+      else hv[k] = sigmoidf_(a[2][k]) * tanhf_(sigmoidf_(a[0][k]) * tanhf_(a[1][k]));
+    }
+    if (h != nullptr) {
+      *reinterpret_cast<float4*>(h + r * H + j) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+      *reinterpret_cast<float4*>(h + r * H + j + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
+    }
+    if (hb != nullptr) {
+      uint4 o;
+      __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+      for (int k = 0; k < 4; k++) po[k] = __floats2bfloat162_rn(hv[2 * k], hv[2 * k + 1]);
+      *reinterpret_cast<uint4*>(hb + r * H + j) = o;
+    }
+  }
+}
 int dec_cell0_fwd(const float* table, const float* wc, const int32_t* tok, const float* cond, int B, int C, int H,
                   int R, RowMap rm, float* h, __nv_bfloat16* hb, cudaStream_t st) {
   if (R <= 0) return 0;
-  k_dec_cell0_fwd<<<grid_for((long)R * H, 256), 256, 0, st>>>(table, wc, tok, cond, B, C, H, R, rm, h, hb);
+  TimeScope ts(TIME_POINTWISE, st);
+  if ((H & 7) == 0) {
+    const long total = (long)R * (H >> 3);
+    if (h == nullptr) k_dec_cell0_fwd_v8<true><<<grid_for(total, 256, 16), 256, 0, st>>>(table, wc, tok, cond, B, C, H, R, rm, h, hb);
+    else k_dec_cell0_fwd_v8<false><<<grid_for(total, 256, 16), 256, 0, st>>>(table, wc, tok, cond, B, C, H, R, rm, h, hb);
+  } else {
+    k_dec_cell0_fwd<<<grid_for((long)R * H, 256), 256, 0, st>>>(table, wc, tok, cond, B, C, H, R, rm, h, hb);
+  }
   ARCVAE_LAUNCHED();
   return 0;
 }
@@ -412,6 +467,71 @@ int scatter_rows_by_token_bf16(const __nv_bfloat16* X, const int32_t* tok, long 
 int scatter_rows_by_token_bf16_w(const __nv_bfloat16* X, const int32_t* tok, long R, int N, int V, float* dtable,
                                  const float* cond, int B, int C, float* dwc, cudaStream_t st) {
   return scatter_t(X, tok, R, N, V, dtable, cond, B, C, dwc, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Token scatter on the tensor cores: dtable = onehot(tok)^T @ X is a GEMM with K = R.  The one-hot operand is
+// materialised as bf16 [R, NW] (NW = 128): columns [0,V) one-hot of the token (exact in bf16), columns V+2c, V+2c+1 the
+// bf16 hi / lo split of cond[r % B, c] (so that dwc = X^T cond comes out of the same GEMM with ~2^-17 relative error),
+// the rest zero.  Products with 0/1 are exact and accumulation is fp32, so the result equals the fp32 scatter of the
+// bf16 input up to summation order.
+__global__ void k_build_onehot(const int32_t* __restrict__ tok, long R, int V, int NW, const float* __restrict__ cond,
+                               int B, int C, __nv_bfloat16* __restrict__ out) {
+  const int cpr = NW >> 3;
+  const long total = R * cpr;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const long r = idx / cpr;
+    const int c0 = (int)(idx - r * cpr) << 3;
+    const int t = __ldg(tok + r);
+    __nv_bfloat16 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int col = c0 + k;
+      float x = (col == t) ? 1.f : 0.f;
+      if (cond != nullptr && col >= V && col < V + 2 * C) {
+        const int c = (col - V) >> 1;
+        const float cv = __ldg(cond + (r % B) * C + c);
+        const float hi = __bfloat162float(__float2bfloat16(cv));
+        x = ((col - V) & 1) ? (cv - hi) : hi;
+      }
+      v[k] = __float2bfloat16(x);
+    }
+    *reinterpret_cast<uint4*>(out + r * NW + c0) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+// dwc[n*C + c] += D[(V+2c)*N + n] + D[(V+2c+1)*N + n]
+__global__ void k_onehot_dwc(const float* __restrict__ D, int N, int V, int C, float* __restrict__ dwc) {
+  const int total = N * C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int n = i / C, c = i - n * C;
+    dwc[i] += D[(long)(V + 2 * c) * N + n] + D[(long)(V + 2 * c + 1) * N + n];
+  }
+}
+bool scatter_onehot_supported(int N, int V, int C) { return (N % 64) == 0 && V + 2 * C <= SCATTER_NW; }
+int scatter_rows_onehot_tc(const __nv_bfloat16* X, const int32_t* tok, long R, int N, int V, __nv_bfloat16* onehot,
+                           float* dtable_ext, const float* cond, int B, int C, float* dwc, cudaStream_t st) {
+  if (R <= 0) return 0;
+  ARCVAE_REQUIRE(scatter_onehot_supported(N, V, cond != nullptr ? C : 0), "one-hot scatter: N % 64 == 0, V + 2C <= 128");
+  const int NW = SCATTER_NW;
+  {
+    TimeScope ts(TIME_POINTWISE, st);
+    k_build_onehot<<<grid_for(R * (NW >> 3), 256, 16), 256, 0, st>>>(tok, R, V, NW, cond, B, C, onehot);
+    ARCVAE_LAUNCHED();
+  }
+  ARCVAE_CUDA(cudaMemsetAsync(dtable_ext, 0, (size_t)NW * N * sizeof(float), st));
+  TcGemm g{};
+  g.M = NW; g.N = N; g.K = (int)R;
+  g.A = onehot; g.lda = NW; g.a_mn = true;
+  g.B = X; g.ldb = N; g.b_mn = true;
+  g.C = dtable_ext; g.ldc = N; g.Cb = nullptr; g.ldcb = 0; g.bias = nullptr; g.accumulate = true;
+  g.splitk = pick_splitk_tc(NW, N, (int)R);
+  g.rm = RowMap{nullptr, 1}; g.a_rows_total = R;
+  ARCVAE_TRY(gemm_tc(g, st));
+  if (cond != nullptr && dwc != nullptr) {
+    k_onehot_dwc<<<cdiv((long)N * C, 256), 256, 0, st>>>(dtable_ext, N, V, C, dwc);
+    ARCVAE_LAUNCHED();
+  }
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
