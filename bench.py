@@ -16,9 +16,7 @@ global batch 4096*N, configs[2] at N=8 -> "scaling": "weak").
 import argparse
 import json
 import os
-import subprocess
 import sys
-import tempfile
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -44,47 +42,76 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region, sampled in-process through NVML every 50 ms
+    (B200_PROFILING.md recipe).  An `nvidia-smi -lms` child process was measurably perturbing the step (a query with
+    power and event-reason fields every 100 ms cost ~15 % of a 20 ms step), so the bench polls NVML from a thread."""
 
     def __init__(self, gpu_index):
+        import threading
         self.idx = gpu_index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        self.rows = []
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.err = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = gpu_index
+            if vis:
+                try:
+                    phys = int(vis.split(",")[gpu_index])
+                except Exception:
+                    phys = gpu_index
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # noqa: BLE001
+            self.nv = None
+            self.err = repr(e)
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((sm, reasons))
+            except Exception as e:  # noqa: BLE001
+                self.err = repr(e)
+                return
+            self.stop_flag.wait(0.05)
 
     def start(self):
-        try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
-        except Exception:
-            self.p = None
+        if self.nv is None:
+            return
+        import threading
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        rows = [r.strip().split(",") for r in open(self.f.name) if r.strip()]
-        os.unlink(self.f.name)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-                for n, v in zip(names, r[5:9]):
-                    if v.strip().lower().startswith("active"):
-                        reasons.add(n)
-            except Exception:
-                pass
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self.nv is None or self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + str(self.err)]}
+        time.sleep(0.06)
+        self.stop_flag.set()
+        self.thread.join(timeout=2)
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = set()
+        for _, mask in self.rows:
+            for n, bit in names.items():
+                if mask & bit:
+                    reasons.add(n)
+        return {"sm_mhz": float(sm[len(sm) // 2]) if sm else None, "sm_max_mhz": float(self.max_sm),
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvml"}
 
 
 def cpu_step_rate(steps, warmup, B=CPU_SAMPLE_B):
@@ -108,6 +135,61 @@ def cpu_step_rate(steps, warmup, B=CPU_SAMPLE_B):
             times.append(time.perf_counter() - t0)
     ms = 1e3 * sum(times) / len(times)
     return B / (ms / 1e3), ms, torch.get_num_threads()
+
+
+SAMPLE_B_PER_GPU, SAMPLE_T = 125_000, 128       # BASELINE configs[4]: 1M molecules over 8 GPUs, max length 128
+
+
+def bench_sampler(M, vae, steps=3, warmup=1, B=SAMPLE_B_PER_GPU, T=SAMPLE_T, cpu=True):
+    """Sampled molecules/s of generate_with_temperature (greedy = the reference's argmax path, multinomial = Philox
+    categorical) on B TPSA conditions swept over a z-scored grid; early stopping off so every row runs T steps.
+    resident: conditions already in HBM, tokens left in HBM; e2e: conditions from pinned host memory, tokens read back."""
+    import numpy as np
+    import torch
+    sampler = M.MLXAutoregressiveDecoderSampling(**DIMS, decoder=vae.decoder)
+    grid = np.linspace(-2.5, 2.5, B, dtype=np.float32).reshape(B, 1)
+    hc = torch.as_tensor(grid).pin_memory()
+    dc = hc.cuda()
+    out = {"workload": f"TPSA-conditioned sampling, B={B} molecules x max_length {T} per GPU (configs[4] shard), "
+                       "early stopping off", "unit": "molecules/s"}
+    for name, multi in (("greedy", False), ("multinomial", True)):
+        def run(c):
+            return sampler.generate_with_temperature(None, c, max_length=T, temperature=1.0, early_stopping=False,
+                                                     multinomial=multi, seed=67)
+        for _ in range(warmup):
+            run(dc)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = M._lib.launch_count()
+        e0.record()
+        for _ in range(steps):
+            toks = run(dc)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        launches = (M._lib.launch_count() - l0) // steps
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            host = run(hc.cuda(non_blocking=True)).cpu()
+        ms_e2e = 1e3 * (time.perf_counter() - t0) / steps
+        out[name] = {"value": B / (ms * 1e-3), "ms": ms, "e2e": B / (ms_e2e * 1e-3), "e2e_ms": ms_e2e,
+                     "gpu_launches": launches, "us_per_step_per_128_rows": 1e3 * ms / T / ((B + 127) // 128) * 148,
+                     "d2h_bytes": int(host.numel()) * 4, "h2d_bytes": B * 4}
+    if cpu:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import arcvae_oracle as O
+        torch.set_num_threads(os.cpu_count() or 1)
+        cfg = O.Config(**DIMS)
+        params = O.init_params(cfg, seed=67, dtype=torch.float32)
+        cb = 256
+        ct = torch.as_tensor(grid[:cb])
+        t0 = time.perf_counter()
+        O.generate_with_temperature(params["decoder"], torch.zeros(cb, cfg.latent_dim), ct, cfg.num_layers, max_length=T,
+                                    temperature=1.0, early_stopping=False)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": cb / dt, "unit": "molecules/s", "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": f"{cb} molecules x {T} steps, greedy, oracle torch-CPU fp32"}
+    return out
 
 
 def run_reference(args):
@@ -138,6 +220,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("ARCVAE_PRECISION", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-sampler", action="store_true", help="skip the sampled-molecules/s leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -267,6 +350,11 @@ def main():
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
             "gpu_launches": launches, "gpu_launches_per_step": launches // args.steps, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "final_loss": loss_val, **extra}
+    if not args.no_sampler:
+        try:
+            line["sampler"] = bench_sampler(M, vae, cpu=not args.no_cpu)
+        except Exception as e:  # noqa: BLE001 — the training line must still be printed
+            line["sampler"] = {"error": repr(e)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

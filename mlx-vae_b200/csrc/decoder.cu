@@ -388,6 +388,7 @@ struct SamplerWs {
   float* logits;     // [B,V]
   __nv_bfloat16* hdb[ARCVAE_MAX_LAYERS];  // bf16 [B,H]
   __nv_bfloat16* gates_b[ARCVAE_MAX_LAYERS];  // bf16 [B,3H] (fused path scratch)
+  void* sf_prep;                              // operands of the persistent sampler kernel (sampler_fused.cu)
 };
 static size_t sampler_layout(const arcvae_dims& d, int B, void* base, size_t cap, SamplerWs* w) {
   Arena a(base, cap);
@@ -403,6 +404,7 @@ static size_t sampler_layout(const arcvae_dims& d, int B, void* base, size_t cap
   ww.logits = a.take<float>((size_t)B * d.V);
   for (int l = 0; l < d.NL; l++) ww.hdb[l] = a.take<__nv_bfloat16>((size_t)B * d.H);
   for (int l = 0; l < d.NL; l++) ww.gates_b[l] = (l >= 1) ? a.take<__nv_bfloat16>((size_t)B * 3 * d.H) : nullptr;
+  ww.sf_prep = a.take<char>(sampler_fused_prep_bytes(d));
   if (w) *w = ww;
   return align_up(a.off, 256);
 }
@@ -427,6 +429,12 @@ extern "C" int arcvae_sample(const arcvae_dims* d, const arcvae_decoder_params* 
   size_t need = sampler_layout(*d, B, workspace, workspace_bytes, &ws);
   ARCVAE_REQUIRE(workspace != nullptr && need <= workspace_bytes, "sampler workspace too small");
   ARCVAE_TRY(dec_prepare(*d, p, ws.prep, precision, st));
+  if (sampler_fused_supported(*d, precision)) {
+    // one persistent kernel for the whole batch and all steps
+    return sampler_fused_run(*d, ws.prep.table, ws.prep.wc, ws.prep.Wxpb, ws.prep.bp, ws.prep.Woutb, p->fc_out_b, cond, B,
+                             max_length, temperature, early_stopping, multinomial, seed, tokens, t_stop, ws.ended_count,
+                             ws.sf_prep, st);
+  }
   ARCVAE_CUDA(cudaMemsetAsync(ws.cur, 0, (size_t)B * sizeof(int32_t), st));      // start token 0 (decoder_sampling.py:78)
   ARCVAE_CUDA(cudaMemsetAsync(ws.ended, 0, (size_t)B * sizeof(int32_t), st));
   ARCVAE_CUDA(cudaMemsetAsync(ws.ended_count, 0, 4 * sizeof(int32_t), st));

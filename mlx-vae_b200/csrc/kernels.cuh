@@ -119,6 +119,17 @@ int scatter_rows_onehot_tc(const __nv_bfloat16* X, const int32_t* tok, long R, i
 int scatter_rows_by_token_bf16_w(const __nv_bfloat16* X, const int32_t* tok, long R, int N, int V, float* dtable,
                                  const float* cond, int B, int C, float* dwc, cudaStream_t st);
 
+// fused persistent sampler (sampler_fused.cu): one kernel per batch, activations resident in shared memory
+constexpr int SF_MAX_LAYERS = 4;
+bool sampler_fused_supported(const arcvae_dims& d, int precision);
+size_t sampler_fused_prep_bytes(const arcvae_dims& d);
+// table [V,3H] fp32 (i|g|o), wc [3H,C]; Wxpb[l] / bp[l] tile-permuted compact weights / bias of layers >= 1;
+// ended_count: 4 ints of scratch; prep: sampler_fused_prep_bytes() of scratch
+int sampler_fused_run(const arcvae_dims& d, const float* table, const float* wc, __nv_bfloat16* const* Wxpb,
+                      float* const* bp, const __nv_bfloat16* Woutb, const float* bout, const float* cond, int B,
+                      int max_length, float temperature, int early_stopping, int multinomial, uint64_t seed,
+                      int32_t* tokens, int32_t* t_stop, int32_t* ended_count, void* prep, cudaStream_t st);
+
 // the same logical matrix in fp32 and (optionally) bf16; gemm_any picks the tensor-core kernel when precision is bf16
 // and the operands satisfy the TMA constraints, else the fp32 FFMA kernel on the fp32 copies
 struct Mat {
