@@ -40,8 +40,7 @@ struct SfParams {
   int B, H, V, VN, C, NL, max_length, end_token, multinomial;
   float temperature;
   uint64_t seed;
-  const float* wcp;                  // [3H, C] tile-permuted cond weights of layer 0
-  const float* bp[SF_MAX_LAYERS];    // [3H] tile-permuted bias, l >= 1
+  const bf16* bpb[SF_MAX_LAYERS];    // [3H] tile-permuted bias (bf16 copy), l >= 1
   const float* bout;                 // [V]
   const float* cond;                 // [B, C]
   int32_t* tokens;                   // [B, max_length]
@@ -75,7 +74,7 @@ sampler_fused_kernel(const __grid_constant__ SfMaps maps, const SfParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int KP = p.H >> 6;                      // 64-wide K panels of a hidden tile == 192-wide blocks per layer
-  const int VKS = (p.V + 15) >> 4;              // K16 steps of layer 0 (vocabulary)
+  const int VKS = (p.V + 2 * p.C + 15) >> 4;    // K16 steps of layer 0 (vocabulary + cond hi/lo columns)
   const int VP = (VKS + 3) >> 2;                // K panels of the one-hot tile
   uint8_t* hA = smem;                                             // outputs of even layers
   uint8_t* hB = hA + (size_t)KP * SF_PANEL;                       // outputs of odd layers; one-hot tile of layer 0
@@ -201,22 +200,63 @@ sampler_fused_kernel(const __grid_constant__ SfMaps maps, const SfParams p) {
     const int row = q * 32 + lane;
     const int ct = threadIdx.x - 64;           // 0..255
     uint32_t acc_it = 0, out_it = 0;
+    // byte offset of element (row, k) of the one-hot tile (K-major SWIZZLE_128B panels)
+    auto oh = [&](int k) -> uint8_t* {
+      return hB + (size_t)(k >> 6) * SF_PANEL + row * 128 + ((((k & 63) >> 3) ^ (row & 7)) << 4) + (k & 7) * 2;
+    };
+    auto cell16 = [&](uint32_t taddr, int c0, const uint4 (&a)[6], uint8_t* drow) {
+      uint32_t ri[16], rg[16], ro[16];
+      tc::tmem_ld16(taddr + c0, ri);
+      tc::tmem_ld16(taddr + 64 + c0, rg);
+      tc::tmem_ld16(taddr + 128 + c0, ro);
+      tc::tmem_ld_wait();
+      const __nv_bfloat162* ab = reinterpret_cast<const __nv_bfloat162*>(a);   // [g][8] pairs
+      float hv[16];
+#pragma unroll
+      for (int k2 = 0; k2 < 8; k2++) {
+        const float2 bi = __bfloat1622float2(ab[k2]), bg = __bfloat1622float2(ab[8 + k2]), bo = __bfloat1622float2(ab[16 + k2]);
+        const float ai0 = __uint_as_float(ri[2 * k2]) + bi.x, ai1 = __uint_as_float(ri[2 * k2 + 1]) + bi.y;
+        const float ag0 = __uint_as_float(rg[2 * k2]) + bg.x, ag1 = __uint_as_float(rg[2 * k2 + 1]) + bg.y;
+        const float ao0 = __uint_as_float(ro[2 * k2]) + bo.x, ao1 = __uint_as_float(ro[2 * k2 + 1]) + bo.y;
+        hv[2 * k2] = sigmoid_approx_(ao0) * tanh_approx_(sigmoid_approx_(ai0) * tanh_approx_(ag0));
+        hv[2 * k2 + 1] = sigmoid_approx_(ao1) * tanh_approx_(sigmoid_approx_(ai1) * tanh_approx_(ag1));
+      }
+      sf_store16(drow, c0 >> 3, row, hv);
+    };
+    auto load_bias = [&](const bf16* bl, int n, uint4 (&a)[6]) {     // 16 units x (i,g,o) starting at permuted row n
+#pragma unroll
+      for (int g = 0; g < 3; g++) {
+        a[2 * g] = __ldg(reinterpret_cast<const uint4*>(bl + n + g * 64));
+        a[2 * g + 1] = __ldg(reinterpret_cast<const uint4*>(bl + n + g * 64) + 1);
+      }
+    };
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int b = tile * SF_ROWS + row;
       const bool valid = b < p.B;
-      float cv0 = 0.f, cv1 = 0.f, cv2 = 0.f, cv3 = 0.f;
-      if (valid) {
-        const float* cr = p.cond + (long)b * p.C;
-        cv0 = __ldg(cr);
-        if (p.C > 1) cv1 = __ldg(cr + 1);
-        if (p.C > 2) cv2 = __ldg(cr + 2);
-        if (p.C > 3) cv3 = __ldg(cr + 3);
-      }
+      // cond enters layer 0 through the GEMM: columns V+2c, V+2c+1 of the one-hot tile hold the bf16 hi / lo split of
+      // cond[b, c] and the matching rows of Tt hold wc[:, c]
+      uint32_t cpk[4] = {0, 0, 0, 0};
+      if (valid)
+        for (int c = 0; c < p.C; c++) {
+          const float cvf = __ldg(p.cond + (long)b * p.C + c);
+          const __nv_bfloat16 hi = __float2bfloat16(cvf);
+          const __nv_bfloat16 lo = __float2bfloat16(cvf - __bfloat162float(hi));
+          const uint32_t pk = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+          if (c == 0) cpk[0] = pk; else if (c == 1) cpk[1] = pk; else if (c == 2) cpk[2] = pk; else cpk[3] = pk;
+        }
+      auto write_onehot = [&](int tokv) {
+        *reinterpret_cast<uint16_t*>(oh(tokv)) = 0x3F80;                 // bf16 1.0
+        for (int c = 0; c < p.C; c++) {
+          const uint32_t pk = (c == 0) ? cpk[0] : (c == 1) ? cpk[1] : (c == 2) ? cpk[2] : cpk[3];
+          *reinterpret_cast<uint16_t*>(oh(p.V + 2 * c)) = (uint16_t)(pk & 0xFFFF);
+          *reinterpret_cast<uint16_t*>(oh(p.V + 2 * c + 1)) = (uint16_t)(pk >> 16);
+        }
+      };
       bool ended = false;
-      // start token 0 (decoder_sampling.py:78): one-hot tile = e_0 for every row
+      // start token 0 (decoder_sampling.py:78)
       for (int i = ct; i < VP * (SF_PANEL / 16); i += 256) reinterpret_cast<uint4*>(hB)[i] = make_uint4(0, 0, 0, 0);
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (hs == 0) *reinterpret_cast<uint16_t*>(hB + row * 128 + ((0 ^ (row & 7)) << 4)) = 0x3F80;   // bf16 1.0 at k = 0
+      if (hs == 0) write_onehot(0);
       tc::fence_proxy_async();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&sh->a_ready);
@@ -224,57 +264,24 @@ sampler_fused_kernel(const __grid_constant__ SfMaps maps, const SfParams p) {
       for (int t = 0; t < T; t++) {
         for (int l = 0; l < NL; l++) {
           uint8_t* dst = (l & 1) ? hB : hA;
-          const float* bl = p.bp[l];
+          const bf16* bl = p.bpb[l];
+          // additive terms (bias of layers >= 1; layer 0 has none), software-pipelined one half-block ahead so the
+          // loads never sit between an accumulator becoming ready and its cell math
+          uint4 a0[6], a1[6];
+#pragma unroll
+          for (int i = 0; i < 6; i++) { a0[i] = make_uint4(0, 0, 0, 0); a1[i] = a0[i]; }
+          if (l > 0) load_bias(bl, hs * 32, a0);
           for (int j = 0; j < KP; j++) {
             const uint32_t acc = acc_it & 1;
             tc::mbar_wait(&sh->acc_full[acc], (acc_it >> 1) & 1);
             tc::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * SF_BN;
             uint8_t* drow = dst + (size_t)j * SF_PANEL + row * 128;
-            const int nb = j * SF_BN;
-#pragma unroll 1
-            for (int cc = 0; cc < 2; cc++) {
-              const int c0 = hs * 32 + cc * 16;
-              // additive term of the 16 units x (i,g,o): layer 0 = cond (x) wc (the bias is inside the table), else bias
-              float add[3][16];
-              if (l == 0) {
-#pragma unroll
-                for (int g = 0; g < 3; g++)
-#pragma unroll
-                  for (int k = 0; k < 16; k++) add[g][k] = 0.f;
-#pragma unroll 1
-                for (int c = 0; c < p.C; c++) {
-                  const float cvc = (c == 0) ? cv0 : (c == 1) ? cv1 : (c == 2) ? cv2 : cv3;
-                  const float* w = p.wcp + (long)(nb + c0) * p.C + c;
-#pragma unroll
-                  for (int g = 0; g < 3; g++)
-#pragma unroll
-                    for (int k = 0; k < 16; k++) add[g][k] = fmaf(cvc, __ldg(w + (long)(g * 64 + k) * p.C), add[g][k]);
-                }
-              } else {
-#pragma unroll
-                for (int g = 0; g < 3; g++)
-#pragma unroll
-                  for (int k4 = 0; k4 < 4; k4++) {
-                    const float4 v = __ldg(reinterpret_cast<const float4*>(bl + nb + g * 64 + c0) + k4);
-                    add[g][4 * k4] = v.x; add[g][4 * k4 + 1] = v.y; add[g][4 * k4 + 2] = v.z; add[g][4 * k4 + 3] = v.w;
-                  }
-              }
-              uint32_t ri[16], rg[16], ro[16];
-              tc::tmem_ld16(taddr + c0, ri);
-              tc::tmem_ld16(taddr + 64 + c0, rg);
-              tc::tmem_ld16(taddr + 128 + c0, ro);
-              tc::tmem_ld_wait();
-              float hv[16];
-#pragma unroll
-              for (int k = 0; k < 16; k++) {
-                const float ai = __uint_as_float(ri[k]) + add[0][k];
-                const float ag = __uint_as_float(rg[k]) + add[1][k];
-                const float ao = __uint_as_float(ro[k]) + add[2][k];
-                hv[k] = sigmoid_approx_(ao) * tanh_approx_(sigmoid_approx_(ai) * tanh_approx_(ag));
-              }
-              sf_store16(drow, c0 >> 3, row, hv);
-            }
+            const int nb = j * SF_BN + hs * 32;
+            if (l > 0) load_bias(bl, nb + 16, a1);
+            cell16(taddr, hs * 32, a0, drow);
+            if (l > 0 && j + 1 < KP) load_bias(bl, nb + SF_BN, a0);
+            cell16(taddr, hs * 32 + 16, a1, drow);
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&sh->acc_empty[acc]);
@@ -363,9 +370,7 @@ sampler_fused_kernel(const __grid_constant__ SfMaps maps, const SfParams p) {
           // next step's one-hot tile (it aliases the tile the odd layers write, so it is rebuilt every step)
           for (int i = ct; i < VP * (SF_PANEL / 16); i += 256) reinterpret_cast<uint4*>(hB)[i] = make_uint4(0, 0, 0, 0);
           asm volatile("bar.sync 1, 256;" ::: "memory");
-          if (hs == 0)
-            *reinterpret_cast<uint16_t*>(hB + (size_t)(choice >> 6) * SF_PANEL + row * 128 +
-                                         ((((choice & 63) >> 3) ^ (row & 7)) << 4) + (choice & 7) * 2) = 0x3F80;
+          if (hs == 0) write_onehot(choice);
           tc::fence_proxy_async();
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(&sh->a_ready);
@@ -389,17 +394,22 @@ __device__ __forceinline__ int sf_nat(int prow, int H) {
   const int j = prow / 192, rem = prow % 192;
   return (rem / 64) * H + j * 64 + (rem % 64);
 }
-// Tt[p, v] = table[v, nat(p)] (bf16, K = vocabulary padded to 128 with zeros);  wcp[p, c] = wc[nat(p), c]
-__global__ void k_sf_prepare(const float* __restrict__ table, const float* __restrict__ wc, int H, int V, int C,
-                             bf16* __restrict__ Tt, float* __restrict__ wcp) {
+// Tt[p, v] = table[v, nat(p)] for v < V, wc[nat(p), c] for v = V+2c, V+2c+1 (bf16, K padded to 128 with zeros);
+// biasb[l][p] = bf16(bp_l[p]) for layers >= 1
+struct SfBias { const float* b[SF_MAX_LAYERS]; };
+__global__ void k_sf_prepare(const float* __restrict__ table, const float* __restrict__ wc, SfBias bp, int H, int V, int C,
+                             int NL, bf16* __restrict__ Tt, bf16* __restrict__ biasb) {
   const int H3 = 3 * H;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H3 * 128; i += gridDim.x * blockDim.x) {
     const int prow = i >> 7, v = i & 127;
-    Tt[i] = __float2bfloat16(v < V ? table[(long)v * H3 + sf_nat(prow, H)] : 0.f);
+    float x = 0.f;
+    if (v < V) x = table[(long)v * H3 + sf_nat(prow, H)];
+    else if (v < V + 2 * C) x = wc[(long)sf_nat(prow, H) * C + ((v - V) >> 1)];
+    Tt[i] = __float2bfloat16(x);
   }
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H3 * C; i += gridDim.x * blockDim.x) {
-    const int prow = i / C, c = i - prow * C;
-    wcp[i] = wc[(long)sf_nat(prow, H) * C + c];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H3 * NL; i += gridDim.x * blockDim.x) {
+    const int l = i / H3;
+    if (l >= 1) biasb[i] = __float2bfloat16(bp.b[l][i - l * H3]);
   }
 }
 __global__ void k_sf_finalize(const int32_t* __restrict__ ended_count, int B, int max_length, int early_stopping,
@@ -412,11 +422,11 @@ int make_tmap_bf16(CUtensorMap* m, const bf16* ptr, long rows, long cols, long l
 
 bool sampler_fused_supported(const arcvae_dims& d, int precision) {
   if (precision != ARCVAE_PREC_BF16) return false;
-  if (d.H % 64 != 0 || d.H > 256 || d.V > 128 || d.C > 4 || d.NL > SF_MAX_LAYERS || d.NL < 1) return false;
+  if (d.H % 64 != 0 || d.H > 256 || d.V + 2 * d.C > 128 || d.C > 4 || d.NL > SF_MAX_LAYERS || d.NL < 1) return false;
   return std::getenv("ARCVAE_NO_FUSED_SAMPLER") == nullptr;
 }
 size_t sampler_fused_prep_bytes(const arcvae_dims& d) {
-  return align_up((size_t)3 * d.H * 128 * sizeof(bf16), 256) + align_up((size_t)3 * d.H * d.C * sizeof(float), 256);
+  return align_up((size_t)3 * d.H * 128 * sizeof(bf16), 256) + align_up((size_t)3 * d.H * SF_MAX_LAYERS * sizeof(bf16), 256);
 }
 
 int sampler_fused_run(const arcvae_dims& d, const float* table, const float* wc, __nv_bfloat16* const* Wxpb,
@@ -425,9 +435,11 @@ int sampler_fused_run(const arcvae_dims& d, const float* table, const float* wc,
                       int32_t* tokens, int32_t* t_stop, int32_t* ended_count, void* prep, cudaStream_t st) {
   const int H = d.H, H3 = 3 * d.H;
   bf16* Tt = reinterpret_cast<bf16*>(prep);
-  float* wcp = reinterpret_cast<float*>(reinterpret_cast<char*>(prep) + align_up((size_t)H3 * 128 * sizeof(bf16), 256));
+  bf16* biasb = reinterpret_cast<bf16*>(reinterpret_cast<char*>(prep) + align_up((size_t)H3 * 128 * sizeof(bf16), 256));
   TimeScope ts(TIME_SAMPLER, st);
-  k_sf_prepare<<<cdiv((long)H3 * 128, 256), 256, 0, st>>>(table, wc, H, d.V, d.C, Tt, wcp);
+  SfBias sb{};
+  for (int l = 1; l < d.NL && l < SF_MAX_LAYERS; l++) sb.b[l] = bp[l];
+  k_sf_prepare<<<cdiv((long)H3 * 128, 256), 256, 0, st>>>(table, wc, sb, H, d.V, d.C, d.NL, Tt, biasb);
   ARCVAE_LAUNCHED();
   ARCVAE_CUDA(cudaMemsetAsync(ended_count, 0, 4 * sizeof(int32_t), st));
   if (max_length > 0) {
@@ -435,16 +447,16 @@ int sampler_fused_run(const arcvae_dims& d, const float* table, const float* wc,
     SfParams p{};
     p.B = B; p.H = H; p.V = d.V; p.VN = ((d.V + 15) / 16) * 16; p.C = d.C; p.NL = d.NL; p.max_length = max_length;
     p.end_token = d.end_token; p.multinomial = multinomial; p.temperature = temperature; p.seed = seed;
-    p.wcp = wcp; p.bout = bout; p.cond = cond; p.tokens = tokens; p.ended_count = ended_count;
+    p.bout = bout; p.cond = cond; p.tokens = tokens; p.ended_count = ended_count;
     ARCVAE_TRY(make_tmap_bf16(&maps.w[0], Tt, H3, 128, 128, 64, SF_BN));
     for (int l = 1; l < SF_MAX_LAYERS; l++) {
-      p.bp[l] = l < d.NL ? bp[l] : nullptr;
+      p.bpb[l] = l < d.NL ? biasb + (size_t)l * H3 : nullptr;
       if (l < d.NL) ARCVAE_TRY(make_tmap_bf16(&maps.w[l], Wxpb[l], H3, H, H, 64, SF_BN));
       else maps.w[l] = maps.w[0];
     }
-    p.bp[0] = nullptr;
+    p.bpb[0] = nullptr;
     ARCVAE_TRY(make_tmap_bf16(&maps.wout, Woutb, d.V, H, H, 64, p.VN));
-    const int KP = H / 64, VP = (((d.V + 15) / 16) + 3) / 4;
+    const int KP = H / 64, VP = (((d.V + 2 * d.C + 15) / 16) + 3) / 4;
     const size_t smem = (size_t)(KP + (KP > VP ? KP : VP)) * SF_PANEL + (size_t)SF_STAGES * SF_STAGE_BYTES +
                         sizeof(SfShared) + 1024;
     ARCVAE_REQUIRE(smem <= 227 * 1024, "fused sampler shared-memory budget");
