@@ -103,6 +103,7 @@ struct EncScratch {
   float* dtable0;   // [max(V, SCATTER_NW),4H]  (rows >= V: scratch of the one-hot GEMM)
   bf16* dAb;        // [T*B,4H] bf16 pre-activation gradients (tensor-core operand / cluster exchange)
   bf16* onehot;     // [T*B,SCATTER_NW] one-hot tokens (tensor-core scatter)
+  void* xch;        // cluster backward: exchange buffers of the partial d h
 };
 
 static size_t enc_scratch_layout(const arcvae_dims& d, int B, int T, int path, void* base, size_t cap, EncScratch* s) {
@@ -119,6 +120,7 @@ static size_t enc_scratch_layout(const arcvae_dims& d, int B, int T, int path, v
   ss.dtable0 = a.take<float>((size_t)(d.V > SCATTER_NW ? d.V : SCATTER_NW) * 4 * d.H);
   ss.dAb = (path != PATH_STEP_F32) ? a.take<bf16>((size_t)T * B * 4 * d.H) : nullptr;
   ss.onehot = (path != PATH_STEP_F32) ? a.take<bf16>((size_t)T * B * SCATTER_NW) : nullptr;
+  ss.xch = (path != PATH_STEP_F32) ? a.take<char>(lstm_cluster_xch_bytes(B)) : nullptr;
   if (s) *s = ss;
   return align_up(a.off, 256);
 }
@@ -300,9 +302,14 @@ extern "C" int arcvae_encoder_backward(const arcvae_dims* d, const arcvae_encode
   if (path == PATH_CLUSTER) {
     for (int l = d->NL - 1; l >= 0; l--) {
       const bool top = (l == d->NL - 1);
-      ARCVAE_TRY(transpose_to_bf16(p->Wh[l], G4, H, tp.WhTb[l], st));          // WhT[h][gate] = Wh[gate][h]
-      ARCVAE_TRY(lstm_cluster_backward(B, T, H, tp.WhTb[l], tp.gates_b[l], tp.c[l], top ? nullptr : sc.dX,
-                                       top ? sc.du : nullptr, H2, sc.dAb, tp.err, st));
+      if (std::getenv("ARCVAE_BWD_ALLGATHER") == nullptr) {
+        ARCVAE_TRY(lstm_cluster_backward2(B, T, H, tp.Whb[l], tp.gates_b[l], tp.c[l], top ? nullptr : sc.dX,
+                                          top ? sc.du : nullptr, H2, sc.dAb, sc.xch, tp.err, st));
+      } else {
+        ARCVAE_TRY(transpose_to_bf16(p->Wh[l], G4, H, tp.WhTb[l], st));          // WhT[h][gate] = Wh[gate][h]
+        ARCVAE_TRY(lstm_cluster_backward(B, T, H, tp.WhTb[l], tp.gates_b[l], tp.c[l], top ? nullptr : sc.dX,
+                                         top ? sc.du : nullptr, H2, sc.dAb, tp.err, st));
+      }
       // dWh += dA[1:]^T @ h[:-1]
       if (T > 1) {
         long K = (long)(T - 1) * B;

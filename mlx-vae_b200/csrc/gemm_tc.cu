@@ -422,6 +422,26 @@ int make_tmap_bf16(CUtensorMap* m, const bf16* ptr, long rows, long cols, long l
   return 0;
 }
 
+// time-major bf16 tensor [T][rows_per_t][cols] with row pitch ld (elements); box {box_cols, box_rows, 1}.  Rows beyond
+// rows_per_t are clipped by the TMA unit, so a row tile never spills into the next timestep (ragged last tile).
+int make_tmap_bf16_3d(CUtensorMap* m, const bf16* ptr, long T, long rows_per_t, long cols, long ld, int box_cols, int box_rows) {
+  ARCVAE_TRY(get_encode());
+  ARCVAE_REQUIRE((ld % 8) == 0 && ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0),
+                 "TMA operands need 16-byte aligned base and pitch (ld multiple of 8 bf16)");
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows_per_t, (cuuint64_t)T};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * sizeof(bf16), (cuuint64_t)ld * rows_per_t * sizeof(bf16)};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (3-D) failed with code " + std::to_string((int)r));
+    return 3;
+  }
+  return 0;
+}
+
 static int pick_bn(int N) {
   if (N >= 256) return 256;
   return ((N + 15) / 16) * 16;

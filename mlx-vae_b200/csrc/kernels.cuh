@@ -106,6 +106,11 @@ int lstm_cluster_forward(int B, int T, int H, const __nv_bfloat16* Whb, const in
 int lstm_cluster_backward(int B, int T, int H, const __nv_bfloat16* WhTb, const __nv_bfloat16* gates_b, const float* c,
                           const float* dh_ext, const float* dh_last, int dh_last_ld, __nv_bfloat16* dAb, int* err_flag,
                           cudaStream_t st);
+// K-split backward: every CTA multiplies its own dA slice, partial d h reduce-scattered through `xch`
+size_t lstm_cluster_xch_bytes(int B);
+int lstm_cluster_backward2(int B, int T, int H, const __nv_bfloat16* Whb, const __nv_bfloat16* gates_b, const float* c,
+                           const float* dh_ext, const float* dh_last, int dh_last_ld, __nv_bfloat16* dAb, void* xch,
+                           int* err_flag, cudaStream_t st);
 int colsum_bf16(const __nv_bfloat16* X, long R, int N, int ldx, float* out, cudaStream_t st);
 int scatter_rows_by_token_bf16(const __nv_bfloat16* X, const int32_t* tok, long R, int N, int V, float* dtable,
                                cudaStream_t st);

@@ -55,6 +55,7 @@ struct RecParams {
   const float* dh_last;   // [B, dh_last_ld] gradient into h_{T-1} from the head (or null)
   int dh_last_ld;
   bf16* dAb;              // [T*B,4H] pre-activation gradients, bf16 (exchange + tape)
+  uint4* xch;             // backward, K-split design: exchange buffers of the partial d h (lstm_cluster_xch_bytes)
   int* err_flag;
   long long* dbg;        // optional: per-step clock64 stamps of CTA 0 (layout: [it][16])
 };
@@ -468,10 +469,356 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   }
 }
 
+long long* g_rc_dbg = nullptr;   // set by arcvae_debug_set_rc_stamps (tests only)
+
+// =====================================================================================================================
+// Backward, second design ("K-split").  d h_{t-1} = dA_t . Wh has K = 4H: four times the exchange of the forward if the
+// wide operand dA_t is all-gathered (the first design above: 16 chunks per step through a 4-slot ring = 4 serialized
+// round trips, and 64 issue-bound N=64 MMAs).  Here every CTA multiplies only ITS OWN slice of dA_t (4 gates x its 64
+// units, K = 256, written by its own epilogue straight into a shared-memory operand tile) with the matching rows of Wh
+// (the SAME resident 128 KB image the forward kernel holds, read as an MN-major operand) into a partial
+// d h_{t-1}[128 x 256] for ALL hidden units; the four partials are reduce-scattered: a CTA keeps the quarter of its own
+// units in TMEM and sends the other three quarters (bf16) to their owners through L2-resident exchange buffers,
+// signalled by cluster-scope mbarrier arrivals.  16 full-rate N=256 MMAs per step, one exchange round trip, and the dA
+// tape is written by TMA stores from the operand tile (no per-thread global stores on the critical path).
+struct __align__(8) Bwd2Shared {
+  uint64_t w_ready, a_ready, a_free, acc_full, part_full;
+  uint32_t tmem_base;
+  int failed;
+};
+
+namespace rc {
+__device__ __forceinline__ uint32_t mapa(uint32_t saddr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t raddr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\tselp.b32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(tc::smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void fence_acq_rel_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(tc::smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// bounded waits on a CTA-local failure flag (a protocol bug must not hang the GPU)
+__device__ __forceinline__ bool wait_flag(uint64_t* bar, uint32_t parity, volatile int* failed) {
+  for (long i = 0; i < RC_SPIN_LIMIT; i++) {
+    if (tc::mbar_try_wait(bar, parity)) return true;
+    if ((i & 1023) == 1023 && *failed) return false;
+  }
+  *failed = 1;
+  return false;
+}
+__device__ __forceinline__ bool wait_flag_cluster(uint64_t* bar, uint32_t parity, volatile int* failed) {
+  for (long i = 0; i < RC_SPIN_LIMIT; i++) {
+    if (mbar_try_wait_cluster(bar, parity)) return true;
+    if ((i & 1023) == 1023 && *failed) return false;
+  }
+  *failed = 1;
+  return false;
+}
+}  // namespace rc
+
+constexpr int RC_THREADS2 = 384;   // 3 full warpgroups: setmaxnreg is a warpgroup-wide operation (warps 10, 11 only donate registers)
+
+__global__ void __launch_bounds__(RC_THREADS2, 1)
+lstm_bwd2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmD, const RecParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* Wsm = smem;                         // 4 gate panels x [64 k-rows x 256 units] bf16, MN-major, 32 KB each
+  uint8_t* At = smem + RC_W_BYTES;             // 4 gate panels x [128 rows x 64 units] bf16, K-major, 16 KB each
+  Bwd2Shared* sh = reinterpret_cast<Bwd2Shared*>(At + 4 * RC_STAGE_BYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)rc::cluster_ctarank();
+  const int tile = blockIdx.x / RC_CL;
+  const int ntiles = gridDim.x / RC_CL;
+  const int row0 = tile * RC_ROWS;
+  const int B = p.B, T = p.T, H = p.H;
+  volatile int* failed = &sh->failed;
+
+  if (threadIdx.x == 0) {
+    tc::mbar_init(&sh->w_ready, 1);
+    tc::mbar_init(&sh->a_ready, 8);
+    tc::mbar_init(&sh->a_free, 2);
+    tc::mbar_init(&sh->acc_full, 1);
+    tc::mbar_init(&sh->part_full, 8 * (RC_CL - 1));
+    sh->failed = 0;
+    tc::fence_barrier_init();
+    tc::prefetch_tmap(&tmW);
+    tc::prefetch_tmap(&tmD);
+  }
+  if (warp == 9) tc::tmem_alloc(&sh->tmem_base, 256);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  rc::cluster_sync_all();                      // every CTA's barriers exist before any remote arrive
+  const uint32_t tmem_base = sh->tmem_base;
+
+  if (warp >= 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");   // control warpgroup releases registers (4 x 32 x 136) ...
+  if (warp == 8) {
+    // =========================================================== control: resident weights, then 16 MMAs per step
+    if (lane == 0) {
+      tc::mbar_expect_tx(&sh->w_ready, RC_W_BYTES);
+      for (int g = 0; g < 4; g++)
+        for (int j = 0; j < 4; j++)
+          tc::tma_load_2d(Wsm + g * 32768 + j * 8192, &tmW, &sh->w_ready, 64 * j, g * H + 64 * rank);
+      bool ok = rc::wait_flag(&sh->w_ready, 0, failed);
+      const uint32_t idesc = tc::make_idesc_bf16(RC_ROWS, 256, false, true);
+      for (int it = 0; it + 1 < T && ok; it++) {
+        ok = rc::wait_flag(&sh->a_ready, it & 1, failed);
+        if (!ok) break;
+        RC_STAMP(0);
+        tc::tc_fence_after();
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+          const uint32_t a_addr = tc::smem_u32(At + g * RC_STAGE_BYTES);
+          const uint32_t b_addr = tc::smem_u32(Wsm + g * 32768);
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            tc::mma_bf16(tmem_base, tc::make_smem_desc(a_addr + 32 * k, 16, 1024),
+                         tc::make_smem_desc(b_addr + 2048 * k, 8192, 1024), idesc, (g > 0 || k > 0) ? 1u : 0u);
+        }
+        tc::mma_commit(&sh->a_free);             // operand tile may be rewritten once these MMAs have read it
+        tc::mma_commit(&sh->acc_full);
+        RC_STAMP(2);
+      }
+    }
+  } else if (warp == 9) {
+    // =========================================================== tape: dA_t tile -> HBM by TMA (rows >= B are clipped)
+    if (lane == 0) {
+      bool ok = true;
+      for (int it = 0; it < T && ok; it++) {
+        ok = rc::wait_flag(&sh->a_ready, it & 1, failed);
+        if (!ok) break;
+        const int t = T - 1 - it;
+        RC_STAMP(8);
+#pragma unroll
+        for (int g = 0; g < 4; g++) rc::tma_store_3d(&tmD, At + g * RC_STAGE_BYTES, g * H + 64 * rank, row0, t);
+        rc::bulk_commit();
+        rc::bulk_wait_read0();
+        RC_STAMP(9);
+        tc::mbar_arrive(&sh->a_free);
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the last tile is in HBM before the kernel ends
+    }
+  } else if (warp < 8) {
+    // =========================================================== epilogue: cell backward, state in registers
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");                // ... which the eight epilogue warps take (8 x 32 x 64)
+    const int q = warp & 3;                  // TMEM lane quarter this warp may read
+    const int hs = warp >> 2;                // which 32 of the CTA's 64 hidden units
+    const int rl = q * 32 + lane;            // row inside the tile
+    const int row = row0 + rl;
+    const bool valid = row < B;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int ub = 64 * rank + hs * 32;      // first global hidden unit of this thread
+    const long warp_slot = ((((long)tile * RC_CL + rank) * 4 + q) * 2 + hs);
+    const long slots_per_t = (long)ntiles * RC_CL * 4 * 2;
+    auto gate_tape = [&](int tt, int g, int cu) -> const uint4* {
+      return reinterpret_cast<const uint4*>(p.gates_b) + (((long)tt * slots_per_t + warp_slot) * 16 + g * 4 + cu) * 32 + lane;
+    };
+    auto c_tape = [&](int tt, int i) -> const float4* {
+      return reinterpret_cast<const float4*>(p.c) + (((long)tt * slots_per_t + warp_slot) * 8 + i) * 32 + lane;
+    };
+    // exchange buffer [parity][tile][dst][src][warp][chunk][lane] x 16 B: reader and writer threads have the same
+    // (warp, lane), so every warp-wide access is 512 contiguous bytes
+    auto xch = [&](int par, int dst, int src, int ch) -> uint4* {
+      return p.xch + ((((((long)par * ntiles + tile) * RC_CL + dst) * RC_CL + src) * 8 + warp) * 4 + ch) * 32 + lane;
+    };
+    uint32_t peer_bar[RC_CL];
+#pragma unroll
+    for (int c = 0; c < RC_CL; c++) peer_bar[c] = rc::mapa(tc::smem_u32(&sh->part_full), (uint32_t)c);
+
+    float state[32];                         // dL/dc_t carried to t-1
+    float cnow[32];                          // c_t
+#pragma unroll
+    for (int i = 0; i < 32; i++) { state[i] = 0.f; cnow[i] = 0.f; }
+    uint4 pf[4][4];                          // [chunk][gate] activated gates of the step being prefetched
+    float4 cpf[8];                           // c_{t-1}
+    float4 epf[8];                           // d h from the layer above (dh_ext) for the step being prefetched
+#pragma unroll
+    for (int i = 0; i < 8; i++) epf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto prefetch = [&](int tt) {
+      if (!valid) return;
+      if (p.dh_ext != nullptr) {
+        const float4* e = reinterpret_cast<const float4*>(p.dh_ext + ((long)tt * B + row) * H + ub);
+#pragma unroll
+        for (int i = 0; i < 8; i++) epf[i] = __ldg(e + i);
+      }
+#pragma unroll
+      for (int cu = 0; cu < 4; cu++)
+#pragma unroll
+        for (int g = 0; g < 4; g++) pf[cu][g] = __ldg(gate_tape(tt, g, cu));
+      if (tt > 0) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) cpf[i] = __ldg(c_tape(tt - 1, i));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) cpf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    if (valid) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const float4 v = __ldg(c_tape(T - 1, i));
+        cnow[4 * i] = v.x; cnow[4 * i + 1] = v.y; cnow[4 * i + 2] = v.z; cnow[4 * i + 3] = v.w;
+      }
+    }
+    prefetch(T - 1);
+    bool ok = true;
+    for (int it = 0; it < T && ok; it++) {
+      const int t = T - 1 - it;
+      const long r = (long)t * B + row;
+      if (it > 0) {
+        ok = rc::wait_flag_cluster(&sh->part_full, (it - 1) & 1, failed);     // the three remote partials of d h_t
+        if (ok) ok = rc::wait_flag(&sh->a_free, (it - 1) & 1, failed);         // operand tile reusable
+        if (!ok) break;
+      }
+      if (threadIdx.x == 0) RC_STAMP(4);
+      // all twelve remote partial vectors at once: ONE L2 round trip on the critical path instead of one per chunk
+      uint4 xr[RC_CL - 1][4];
+      if (it > 0) {
+#pragma unroll
+        for (int c = 0, s3 = 0; c < RC_CL; c++) {
+          if (c == rank) continue;
+#pragma unroll
+          for (int cu = 0; cu < 4; cu++) xr[s3][cu] = __ldcg(xch((it - 1) & 1, rank, c, cu));
+          s3++;
+        }
+      }
+#pragma unroll
+      for (int cu = 0; cu < 4; cu++) {
+        const int ug = ub + cu * 8;                  // global hidden-unit index
+        float dh[8];
+        if (it > 0) {
+          // this CTA's own partial (its units) is still in TMEM: the next MMAs are issued only after this epilogue
+          uint32_t rr[8];
+          rc::tmem_ld8(taddr + (uint32_t)(64 * rank + hs * 32 + cu * 8), rr);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; j++) dh[j] = __uint_as_float(rr[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; j++) dh[j] = 0.f;
+        }
+        if (it > 0) {
+#pragma unroll
+          for (int s3 = 0; s3 < RC_CL - 1; s3++) {
+            float f[8];
+            rc::unpack8(xr[s3][cu], f);
+#pragma unroll
+            for (int j = 0; j < 8; j++) dh[j] += f[j];
+          }
+        }
+        if (valid) {
+          {
+            const float4 v0 = epf[2 * cu], v1 = epf[2 * cu + 1];
+            dh[0] += v0.x; dh[1] += v0.y; dh[2] += v0.z; dh[3] += v0.w;
+            dh[4] += v1.x; dh[5] += v1.y; dh[6] += v1.z; dh[7] += v1.w;
+          }
+          if (t == T - 1 && p.dh_last != nullptr) {
+            const float* e = p.dh_last + (long)row * p.dh_last_ld + ug;
+#pragma unroll
+            for (int j = 0; j < 8; j++) dh[j] += e[j];
+          }
+        }
+        float gi[8], gf[8], gg[8], go[8], cp[8];
+        rc::unpack8(pf[cu][0], gi);
+        rc::unpack8(pf[cu][1], gf);
+        rc::unpack8(pf[cu][2], gg);
+        rc::unpack8(pf[cu][3], go);
+        cp[0] = cpf[2 * cu].x; cp[1] = cpf[2 * cu].y; cp[2] = cpf[2 * cu].z; cp[3] = cpf[2 * cu].w;
+        cp[4] = cpf[2 * cu + 1].x; cp[5] = cpf[2 * cu + 1].y; cp[6] = cpf[2 * cu + 1].z; cp[7] = cpf[2 * cu + 1].w;
+        float ai[8], af[8], ag[8], ao[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const float tcv = rc::tanh_fast(cnow[cu * 8 + j]);
+          const float dct = state[cu * 8 + j] + dh[j] * go[j] * (1.f - tcv * tcv);
+          ao[j] = dh[j] * tcv * go[j] * (1.f - go[j]);
+          ai[j] = dct * gg[j] * gi[j] * (1.f - gi[j]);
+          ag[j] = dct * gi[j] * (1.f - gg[j] * gg[j]);
+          af[j] = dct * cp[j] * gf[j] * (1.f - gf[j]);
+          state[cu * 8 + j] = dct * gf[j];
+          cnow[cu * 8 + j] = cp[j];              // c_{t-1} is next iteration's c_t
+        }
+        // dA_t of these 8 units -> operand tile (gate panel g, row rl, 16-byte chunk hs*4+cu, SWIZZLE_128B)
+        uint8_t* arow = At + rl * 128 + (((hs * 4 + cu) ^ (rl & 7)) << 4);
+        *reinterpret_cast<uint4*>(arow) = rc::pack8(ai);
+        *reinterpret_cast<uint4*>(arow + RC_STAGE_BYTES) = rc::pack8(af);
+        *reinterpret_cast<uint4*>(arow + 2 * RC_STAGE_BYTES) = rc::pack8(ag);
+        *reinterpret_cast<uint4*>(arow + 3 * RC_STAGE_BYTES) = rc::pack8(ao);
+      }
+      if (threadIdx.x == 0) RC_STAMP(5);
+      tc::fence_proxy_async();               // generic-proxy smem writes -> visible to tcgen05.mma / TMA store
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&sh->a_ready);
+      if (threadIdx.x == 0) RC_STAMP(7);
+      if (it + 1 < T) {
+        prefetch(t - 1);                     // tape of the next step: latency hides behind the MMAs
+        if (threadIdx.x == 0) RC_STAMP(10);
+        ok = rc::wait_flag(&sh->acc_full, it & 1, failed);
+        if (!ok) break;
+        if (threadIdx.x == 0) RC_STAMP(11);
+        tc::tc_fence_after();
+        // partial d h_{t-1}[128 x 256]: the quarter of this CTA's units stays in TMEM (read by the next epilogue), the
+        // other three go to their owners
+#pragma unroll
+        for (int c = 0; c < RC_CL; c++) {
+          if (c == rank) continue;
+#pragma unroll
+          for (int hf = 0; hf < 2; hf++) {
+            uint32_t v[16];
+            tc::tmem_ld16(taddr + (uint32_t)(64 * c + hs * 32 + hf * 16), v);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int ch = 0; ch < 2; ch++) {
+              float f[8];
+#pragma unroll
+              for (int j = 0; j < 8; j++) f[j] = __uint_as_float(v[ch * 8 + j]);
+              __stcg(xch(it & 1, c, rank, hf * 2 + ch), rc::pack8(f));
+            }
+          }
+        }
+        if (threadIdx.x == 0) RC_STAMP(12);
+        tc::tc_fence_before();
+        rc::fence_acq_rel_cluster();         // this lane's exchange stores are ordered before the arrivals below
+        if (threadIdx.x == 0) RC_STAMP(13);
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+          for (int c = 0; c < RC_CL; c++)
+            if (c != rank) rc::mbar_arrive_remote(peer_bar[c]);
+        }
+      }
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0 && sh->failed && p.err_flag != nullptr) atomicExch(p.err_flag, 1);
+  rc::cluster_sync_all();                    // nobody exits while a peer may still arrive on its barriers
+  if (warp == 9) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_base, 256);
+  }
+}
+
 // ---- host ---------------------------------------------------------------------------------------------------------
 int make_tmap_bf16(CUtensorMap* m, const bf16* ptr, long rows, long cols, long ld, int box_cols, int box_rows);
 
-long long* g_rc_dbg = nullptr;   // set by arcvae_debug_set_rc_stamps (tests only)
 
 static int launch_rec(bool bwd, const CUtensorMap& tmW, const CUtensorMap& tmX, const RecParams& p_in, cudaStream_t st) {
   RecParams p = p_in;
@@ -516,6 +863,47 @@ int lstm_cluster_forward(int B, int T, int H, const bf16* Whb, const int32_t* xT
   p.xT = xT; p.table0b = table0b; p.Pb = Pb; p.hb = hb; p.gates_b = gates_b; p.c = c; p.h_last = h_last;
   p.err_flag = err_flag;
   return launch_rec(false, tmW, tmX, p, st);
+}
+
+int make_tmap_bf16_3d(CUtensorMap* m, const bf16* ptr, long T, long rows_per_t, long cols, long ld, int box_cols, int box_rows);
+
+size_t lstm_cluster_xch_bytes(int B) { return (size_t)2 * cdiv(B, RC_ROWS) * RC_CL * RC_CL * 8 * 4 * 32 * sizeof(uint4); }
+
+// K-split backward (lstm_bwd2_kernel): Whb is the SAME [4H,H] bf16 matrix the forward kernel uses
+int lstm_cluster_backward2(int B, int T, int H, const bf16* Whb, const bf16* gates_b, const float* c, const float* dh_ext,
+                           const float* dh_last, int dh_last_ld, bf16* dAb, void* xch, int* err_flag, cudaStream_t st) {
+  ARCVAE_REQUIRE(lstm_cluster_supported(H), "cluster recurrence kernel is built for hidden_dim 256");
+  CUtensorMap tmW, tmD;
+  ARCVAE_TRY(make_tmap_bf16(&tmW, Whb, 4L * H, H, H, 64, 64));
+  ARCVAE_TRY(make_tmap_bf16_3d(&tmD, dAb, T, B, 4L * H, 4L * H, 64, RC_ROWS));
+  RecParams p{};
+  p.B = B; p.T = T; p.H = H;
+  p.gates_b = const_cast<bf16*>(gates_b); p.c = const_cast<float*>(c);
+  p.dh_ext = dh_ext; p.dh_last = dh_last; p.dh_last_ld = dh_last_ld; p.dAb = dAb; p.err_flag = err_flag;
+  p.xch = reinterpret_cast<uint4*>(xch);
+  p.dbg = g_rc_dbg;
+  const size_t smem = RC_W_BYTES + 4 * RC_STAGE_BYTES + sizeof(Bwd2Shared) + 1024;
+  static bool attr = false;
+  if (!attr) {
+    ARCVAE_CUDA(cudaFuncSetAttribute(lstm_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(cdiv(B, RC_ROWS) * RC_CL);
+  cfg.blockDim = dim3(RC_THREADS2);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = RC_CL;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  TimeScope ts(TIME_RECURRENCE, st);
+  ARCVAE_CUDA(cudaLaunchKernelEx(&cfg, lstm_bwd2_kernel, tmW, tmD, p));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
 }
 
 int lstm_cluster_backward(int B, int T, int H, const bf16* WhTb, const bf16* gates_b, const float* c,
