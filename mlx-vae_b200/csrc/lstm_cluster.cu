@@ -16,6 +16,7 @@
 // (thread = batch row; two warps per TMEM lane quarter, 32 hidden units each; c_t / dc_t live in registers across
 // the whole sequence).
 #include <cooperative_groups.h>
+#include <cstdlib>
 
 #include "kernels.cuh"
 #include "tc_common.cuh"
@@ -816,6 +817,282 @@ lstm_bwd2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
   }
 }
 
+// =====================================================================================================================
+// Forward, second design: h_t is exchanged through DISTRIBUTED SHARED MEMORY.  The first design publishes h_t to HBM,
+// pays a generic->async proxy fence over global memory (~0.8 us) and an L2 round trip for the TMA multicast (~1 us) on
+// every step.  Here the epilogue writes h_t (bf16, SWIZZLE_128B operand layout) into the CTA's OWN ring slot and a
+// sender thread forwards that 16 KB slot to the same slot of the three peer CTAs with DSMEM bulk copies
+// (cp.async.bulk.shared::cluster.shared::cta) whose bytes complete the peers' `full` mbarriers; the MMA warp of every
+// CTA starts as soon as its four slots are complete.  (Per-thread st.shared::cluster stores were measured at ~4 us per
+// step for the same 48 KB and rejected.)  The bf16 h tape for the next layer / the weight gradients leaves the SM by a
+// TMA store from the own slot, off the critical path.  Three full warpgroups so that setmaxnreg can hand the control warps' registers to
+// the epilogue (no spills).
+struct __align__(8) Fwd2Shared {
+  uint64_t full[RC_CL];      // slot s holds h_t of source CTA s: one arrival (+ 16 KB of DSMEM copy bytes for s != rank)
+  uint64_t empty[RC_CL];     // slot s consumed by the MMAs of all CTAs: RC_CL arrivals (tcgen05.commit multicast)
+  uint64_t own_ready;        // this CTA's epilogue has written h_t into its own slot: 8 arrivals
+  uint64_t slot_free;        // own slot read by the TMA store
+  uint64_t w_ready, acc_full;
+  uint32_t tmem_base;
+  int failed;
+};
+
+namespace rc {
+__device__ __forceinline__ void tma_load_3d_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(tc::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+        "h"(mask)
+      : "memory");
+}
+// bulk copy local shared memory -> a peer CTA's shared memory; completion (bytes) is signalled on the PEER's mbarrier
+__device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_caddr, const void* src, uint32_t bytes, uint32_t bar_caddr) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_caddr), "r"(tc::smem_u32(src)), "r"(bytes), "r"(bar_caddr)
+               : "memory");
+}
+}  // namespace rc
+
+__global__ void __launch_bounds__(RC_THREADS2, 1)
+lstm_fwd2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH, const RecParams p) {
+  constexpr int BN = 256;
+  constexpr int WPANEL = BN * 128;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* Wsm = smem;
+  uint8_t* ring = smem + RC_W_BYTES;
+  Fwd2Shared* sh = reinterpret_cast<Fwd2Shared*>(ring + RC_CL * RC_STAGE_BYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)rc::cluster_ctarank();
+  const int tile = blockIdx.x / RC_CL;
+  const int row0 = tile * RC_ROWS;
+  const int B = p.B, T = p.T, H = p.H;
+  const uint16_t ALL = (uint16_t)((1u << RC_CL) - 1);
+  volatile int* failed = &sh->failed;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < RC_CL; s++) {
+      tc::mbar_init(&sh->full[s], 1);
+      tc::mbar_init(&sh->empty[s], RC_CL);
+    }
+    tc::mbar_init(&sh->own_ready, 8);
+    tc::mbar_init(&sh->slot_free, 1);
+    tc::mbar_init(&sh->w_ready, 1);
+    tc::mbar_init(&sh->acc_full, 1);
+    sh->failed = 0;
+    tc::fence_barrier_init();
+    tc::prefetch_tmap(&tmW);
+    tc::prefetch_tmap(&tmH);
+  }
+  if (warp == 9) tc::tmem_alloc(&sh->tmem_base, BN);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  rc::cluster_sync_all();                      // every CTA's barriers exist before any remote store / arrive
+  const uint32_t tmem_base = sh->tmem_base;
+
+  if (warp >= 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+  if (warp == 8) {
+    // =========================================================== control: weights once, then the MMAs of every step
+    if (lane == 0) {
+      tc::mbar_expect_tx(&sh->w_ready, RC_W_BYTES);
+      for (int kp = 0; kp < 4; kp++)
+        for (int g = 0; g < 4; g++)
+          tc::tma_load_2d(Wsm + kp * WPANEL + g * 8192, &tmW, &sh->w_ready, 64 * kp, g * H + 64 * rank);
+      bool ok = rc::wait_flag(&sh->w_ready, 0, failed);
+      const uint32_t idesc = tc::make_idesc_bf16(RC_ROWS, BN, false, false);
+      for (int it = 1; it < T && ok; it++) {
+        // arm the three slots the peers fill by DSMEM bulk copies (the bytes may already have landed)
+#pragma unroll
+        for (int s = 0; s < RC_CL; s++)
+          if (s != rank) tc::mbar_expect_tx(&sh->full[s], RC_STAGE_BYTES);
+#pragma unroll
+        for (int s = 0; s < RC_CL; s++) {
+          ok = ok && rc::wait_flag_cluster(&sh->full[s], (it - 1) & 1, failed);
+          if (s == 0) RC_STAMP(0);
+        }
+        RC_STAMP(1);
+        if (!ok) break;
+        tc::tc_fence_after();
+#pragma unroll
+        for (int kq = 0; kq < RC_CL; kq++) {
+          const uint32_t a_addr = tc::smem_u32(ring + kq * RC_STAGE_BYTES);
+          const uint32_t b_addr = tc::smem_u32(Wsm + kq * WPANEL);
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+            tc::mma_bf16(tmem_base, tc::make_smem_desc(a_addr + 32 * j, 16, 1024),
+                         tc::make_smem_desc(b_addr + 32 * j, 16, 1024), idesc, (kq > 0 || j > 0) ? 1u : 0u);
+        }
+#pragma unroll
+        for (int s = 0; s < RC_CL; s++) rc::mma_commit_mc(&sh->empty[s], ALL);   // slot s free in ALL CTAs once read
+        tc::mma_commit(&sh->acc_full);
+        RC_STAMP(2);
+      }
+    }
+  } else if (warp == 9) {
+    // =========================================================== sender: own slot -> the three peers (DSMEM bulk copies)
+    //                                                              and -> HBM (TMA store of the bf16 h tape, rows >= B clipped)
+    if (lane == 0) {
+      uint32_t slot_at[RC_CL], full_at[RC_CL];
+#pragma unroll
+      for (int c = 0; c < RC_CL; c++) {
+        slot_at[c] = rc::mapa(tc::smem_u32(ring + rank * RC_STAGE_BYTES), (uint32_t)c);
+        full_at[c] = rc::mapa(tc::smem_u32(&sh->full[rank]), (uint32_t)c);
+      }
+      bool ok = true;
+      for (int it = 0; it < T && ok; it++) {
+        ok = rc::wait_flag(&sh->own_ready, it & 1, failed);
+        if (!ok) break;
+        RC_STAMP(8);
+        // tape first (the next layer and the weight gradients need h_t in HBM anyway) ...
+        rc::tma_store_3d(&tmH, ring + rank * RC_STAGE_BYTES, 64 * rank, row0, it);
+        rc::bulk_commit();
+        if (it + 1 < T) {
+          // ... and once the store has completed, ONE multicast load brings the tile from L2 into slot `rank` of the
+          // three peers (own slot already holds it): measured faster than 3 x 16 KB DSMEM bulk copies (~8 B/clk)
+          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+          rc::tma_load_3d_mc(ring + rank * RC_STAGE_BYTES, &tmH, &sh->full[rank], 64 * rank, row0, it,
+                             (uint16_t)(ALL & ~(1u << rank)));
+          tc::mbar_arrive(&sh->full[rank]);
+        } else {
+          rc::bulk_wait_read0();
+        }
+        RC_STAMP(9);
+        tc::mbar_arrive(&sh->slot_free);
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+  } else if (warp < 8) {
+    // =========================================================== epilogue: gate math, cell state in registers
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int q = warp & 3;
+    const int hs = warp >> 2;
+    const int rl = q * 32 + lane;
+    const int row = row0 + rl;
+    const bool valid = row < B;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int ub = 64 * rank + hs * 32;
+    const int ntiles = gridDim.x / RC_CL;
+    const long warp_slot = ((((long)tile * RC_CL + rank) * 4 + q) * 2 + hs);
+    const long slots_per_t = (long)ntiles * RC_CL * 4 * 2;
+    auto gate_tape = [&](int tt, int g, int cu) -> uint4* {
+      return reinterpret_cast<uint4*>(p.gates_b) + (((long)tt * slots_per_t + warp_slot) * 16 + g * 4 + cu) * 32 + lane;
+    };
+    auto c_tape = [&](int tt, int i) -> float4* {
+      return reinterpret_cast<float4*>(p.c) + (((long)tt * slots_per_t + warp_slot) * 8 + i) * 32 + lane;
+    };
+    uint8_t* own_row = ring + rank * RC_STAGE_BYTES + rl * 128;      // this thread's row of the CTA's own slot
+    float state[32];                         // c_{t-1}
+#pragma unroll
+    for (int i = 0; i < 32; i++) state[i] = 0.f;
+    uint4 pf[4][4];                          // [chunk][gate] 8 x bf16 of P_t, prefetched one step ahead
+    auto prefetch = [&](int tt) {
+      if (!valid) return;
+      const long rr = (long)tt * B + row;
+      const bf16* prow = (p.table0b != nullptr ? p.table0b + (long)__ldg(p.xT + rr) * 4 * H : p.Pb + rr * 4 * H) + ub;
+#pragma unroll
+      for (int cu = 0; cu < 4; cu++)
+#pragma unroll
+        for (int g = 0; g < 4; g++) pf[cu][g] = __ldg(reinterpret_cast<const uint4*>(prow + g * H + cu * 8));
+    };
+    prefetch(0);
+    bool ok = true;
+    for (int it = 0; it < T && ok; it++) {
+      const int t = it;
+      if (it > 0) {
+        ok = rc::wait_flag(&sh->acc_full, (it - 1) & 1, failed);
+        if (!ok) break;
+        tc::tc_fence_after();
+      }
+      if (threadIdx.x == 0) RC_STAMP(4);
+      uint4 outq[4][4];                      // activated gates [gate][chunk]
+      uint4 hq[4];                           // h_t
+#pragma unroll
+      for (int cu = 0; cu < 4; cu++) {
+        const int u0 = hs * 32 + cu * 8;             // unit offset inside the CTA's 64
+        float a[4][8];
+        if (it > 0) {
+#pragma unroll
+          for (int g = 0; g < 4; g++) {
+            uint32_t rr[8];
+            rc::tmem_ld8(taddr + (uint32_t)(g * 64 + u0), rr);
+#pragma unroll
+            for (int j = 0; j < 8; j++) a[g][j] = __uint_as_float(rr[j]);
+          }
+          tc::tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int g = 0; g < 4; g++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) a[g][j] = 0.f;
+        }
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+          float f[8];
+          rc::unpack8(pf[cu][g], f);
+#pragma unroll
+          for (int j = 0; j < 8; j++) a[g][j] += f[j];
+        }
+        float hv[8], gi[8], gf[8], gg[8], go[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          gi[j] = rc::sigmoid_fast(a[0][j]);
+          gf[j] = rc::sigmoid_fast(a[1][j]);
+          gg[j] = rc::tanh_fast(a[2][j]);
+          go[j] = rc::sigmoid_fast(a[3][j]);
+          const float cn = fmaf(gf[j], state[cu * 8 + j], gi[j] * gg[j]);   // t = 0: state = 0 -> c = i*g
+          state[cu * 8 + j] = cn;
+          hv[j] = go[j] * rc::tanh_fast(cn);
+        }
+        hq[cu] = rc::pack8(hv);
+        outq[0][cu] = rc::pack8(gi); outq[1][cu] = rc::pack8(gf); outq[2][cu] = rc::pack8(gg); outq[3][cu] = rc::pack8(go);
+        if (valid && t == T - 1 && p.h_last != nullptr) {
+          float* hl = p.h_last + (long)row * H + ub + cu * 8;
+          *reinterpret_cast<float4*>(hl) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+          *reinterpret_cast<float4*>(hl + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
+        }
+      }
+      if (threadIdx.x == 0) RC_STAMP(5);
+      // ---- exchange: this thread's 64 bytes of h_t into the CTA's own slot; the sender thread forwards the slot
+      if (it > 0) {
+        ok = rc::wait_flag_cluster(&sh->empty[rank], (it - 1) & 1, failed);   // every CTA's MMAs have read h_{t-1}
+        if (ok) ok = rc::wait_flag(&sh->slot_free, (it - 1) & 1, failed);      // and the tape store has read it
+        if (!ok) break;
+      }
+      if (threadIdx.x == 0) RC_STAMP(6);
+#pragma unroll
+      for (int cu = 0; cu < 4; cu++) *reinterpret_cast<uint4*>(own_row + (((hs * 4 + cu) ^ (rl & 7)) << 4)) = hq[cu];
+      tc::fence_proxy_async();               // generic-proxy smem writes -> visible to the bulk copies / tcgen05.mma / TMA
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&sh->own_ready);
+      if (threadIdx.x == 0) RC_STAMP(7);
+      // ---- off the critical path: the tape, then the operands of the next step
+      if (valid) {
+#pragma unroll
+        for (int g = 0; g < 4; g++)
+#pragma unroll
+          for (int cu = 0; cu < 4; cu++) *gate_tape(t, g, cu) = outq[g][cu];
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+          *c_tape(t, i) = make_float4(state[4 * i], state[4 * i + 1], state[4 * i + 2], state[4 * i + 3]);
+      }
+      if (it + 1 < T) prefetch(t + 1);
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0 && sh->failed && p.err_flag != nullptr) atomicExch(p.err_flag, 1);
+  rc::cluster_sync_all();                    // nobody exits while a peer may still store into / arrive on its smem
+  if (warp == 9) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_base, BN);
+  }
+}
+
 // ---- host ---------------------------------------------------------------------------------------------------------
 int make_tmap_bf16(CUtensorMap* m, const bf16* ptr, long rows, long cols, long ld, int box_cols, int box_rows);
 
@@ -852,9 +1129,54 @@ static int launch_rec(bool bwd, const CUtensorMap& tmW, const CUtensorMap& tmX, 
 
 bool lstm_cluster_supported(int H) { return H == 256; }
 
+int make_tmap_bf16_3d(CUtensorMap* m, const bf16* ptr, long T, long rows_per_t, long cols, long ld, int box_cols, int box_rows);
+
+static int launch_cluster384(const void* fn, size_t smem, int B, const CUtensorMap& a, const CUtensorMap& b, const RecParams& p,
+                             cudaStream_t st) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(cdiv(B, RC_ROWS) * RC_CL);
+  cfg.blockDim = dim3(RC_THREADS2);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = RC_CL;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  void* args[3] = {(void*)&a, (void*)&b, (void*)&p};
+  TimeScope ts(TIME_RECURRENCE, st);
+  ARCVAE_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+// DSMEM-exchange forward (lstm_fwd2_kernel)
+static int lstm_cluster_forward2(int B, int T, int H, const bf16* Whb, const int32_t* xT, const bf16* table0b, const bf16* Pb,
+                                 bf16* hb, bf16* gates_b, float* c, float* h_last, int* err_flag, cudaStream_t st) {
+  CUtensorMap tmW, tmH;
+  ARCVAE_TRY(make_tmap_bf16(&tmW, Whb, 4L * H, H, H, 64, 64));
+  ARCVAE_TRY(make_tmap_bf16_3d(&tmH, hb, T, B, H, H, 64, RC_ROWS));
+  RecParams p{};
+  p.B = B; p.T = T; p.H = H;
+  p.xT = xT; p.table0b = table0b; p.Pb = Pb; p.hb = hb; p.gates_b = gates_b; p.c = c; p.h_last = h_last;
+  p.err_flag = err_flag;
+  p.dbg = g_rc_dbg;
+  const size_t smem = RC_W_BYTES + RC_CL * RC_STAGE_BYTES + sizeof(Fwd2Shared) + 1024;
+  static bool attr = false;
+  if (!attr) {
+    ARCVAE_CUDA(cudaFuncSetAttribute(lstm_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  return launch_cluster384((const void*)lstm_fwd2_kernel, smem, B, tmW, tmH, p, st);
+}
+
 int lstm_cluster_forward(int B, int T, int H, const bf16* Whb, const int32_t* xT, const bf16* table0b, const bf16* Pb,
                          bf16* hb, bf16* gates_b, float* c, float* h_last, int* err_flag, cudaStream_t st) {
   ARCVAE_REQUIRE(lstm_cluster_supported(H), "cluster recurrence kernel is built for hidden_dim 256");
+  if (std::getenv("ARCVAE_FWD_MULTICAST") == nullptr)
+    return lstm_cluster_forward2(B, T, H, Whb, xT, table0b, Pb, hb, gates_b, c, h_last, err_flag, st);
   CUtensorMap tmW, tmX;
   ARCVAE_TRY(make_tmap_bf16(&tmW, Whb, 4L * H, H, H, 64, 64));
   ARCVAE_TRY(make_tmap_bf16(&tmX, hb, (long)T * B, H, H, 64, RC_ROWS));
@@ -864,8 +1186,6 @@ int lstm_cluster_forward(int B, int T, int H, const bf16* Whb, const int32_t* xT
   p.err_flag = err_flag;
   return launch_rec(false, tmW, tmX, p, st);
 }
-
-int make_tmap_bf16_3d(CUtensorMap* m, const bf16* ptr, long T, long rows_per_t, long cols, long ld, int box_cols, int box_rows);
 
 size_t lstm_cluster_xch_bytes(int B) { return (size_t)2 * cdiv(B, RC_ROWS) * RC_CL * RC_CL * 8 * 4 * 32 * sizeof(uint4); }
 
