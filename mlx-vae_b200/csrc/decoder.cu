@@ -34,7 +34,7 @@ struct DecPrep {
 };
 
 static bool dec_fused_ok(const arcvae_dims& d, int precision, int B, bool row_mapped) {
-  if (precision != ARCVAE_PREC_BF16 || d.H % 64 != 0 || d.NL < 1) return false;
+  if (precision != ARCVAE_PREC_BF16 || d.H % 64 != 0 || d.NL < 1 || d.V + 2 * d.C > SCATTER_NW) return false;
   if (row_mapped && (B % 128) != 0) return false;
   return std::getenv("ARCVAE_NO_FUSED_DEC") == nullptr;
 }
@@ -92,7 +92,7 @@ struct DecTape {
   int* tlists;                       // [2T] level lists + feedback lists
   uint8_t* mask;                     // [T]
   __nv_bfloat16* hdb[ARCVAE_MAX_LAYERS];   // bf16 [R,H] copies (tensor-core operands)
-  __nv_bfloat16* gates_b[ARCVAE_MAX_LAYERS];   // fused path: bf16 [R,3H] activated gates, tile-permuted, l >= 1
+  __nv_bfloat16* gates_b[ARCVAE_MAX_LAYERS];   // fused path: bf16 [R,3H] activated gates, tile-permuted
 };
 
 static size_t dec_tape_layout(const arcvae_dims& d, int B, int T, void* base, size_t cap, DecTape* t) {
@@ -108,7 +108,7 @@ static size_t dec_tape_layout(const arcvae_dims& d, int B, int T, void* base, si
   tt.tlists = a.take<int>((size_t)2 * T + 2);
   tt.mask = a.take<uint8_t>((size_t)T + 16);
   for (int l = 0; l < d.NL; l++) tt.hdb[l] = a.take<__nv_bfloat16>(R * d.H);
-  for (int l = 0; l < d.NL; l++) tt.gates_b[l] = (l >= 1) ? a.take<__nv_bfloat16>(R * 3 * d.H) : nullptr;
+  for (int l = 0; l < d.NL; l++) tt.gates_b[l] = a.take<__nv_bfloat16>(R * 3 * d.H);   // layer 0 too: no recompute in backward
   if (t) *t = tt;
   return align_up(a.off, 256);
 }
@@ -124,6 +124,7 @@ struct DecScratch {
   __nv_bfloat16* dGb;                 // bf16 [R,3H] copy of the pre-activation gradients
   __nv_bfloat16* dGb2;                // fused path: second [R,3H] buffer (ping-pong between layers, layer-0 dG)
   __nv_bfloat16* onehot;              // fused path: [R,SCATTER_NW] one-hot of the fed tokens + cond hi/lo columns
+  float* dtable_tmp;                  // fused path: [SCATTER_NW,3H] table gradient in tile-permuted column order
 };
 
 static size_t dec_scratch_layout(const arcvae_dims& d, int B, int T, void* base, size_t cap, DecScratch* s) {
@@ -144,6 +145,7 @@ static size_t dec_scratch_layout(const arcvae_dims& d, int B, int T, void* base,
   ss.dGb = a.take<__nv_bfloat16>(R * 3 * d.H);
   ss.dGb2 = a.take<__nv_bfloat16>(R * 3 * d.H);
   ss.onehot = a.take<__nv_bfloat16>(R * SCATTER_NW);
+  ss.dtable_tmp = a.take<float>((size_t)SCATTER_NW * 3 * d.H);
   if (s) *s = ss;
   return align_up(a.off, 256);
 }
@@ -168,7 +170,7 @@ static int dec_stack_forward(const arcvae_dims& d, const arcvae_decoder_params* 
   const int H = d.H, H3 = 3 * d.H;
   const bool bf = precision == ARCVAE_PREC_BF16;
   ARCVAE_TRY(dec_cell0_fwd(pr.table, pr.wc, in_tok, cond, B, d.C, H, nrows, rm, fused ? nullptr : hd[0],
-                           bf ? hdb[0] : nullptr, st));
+                           bf ? hdb[0] : nullptr, fused ? gates_b[0] : nullptr, st));
   for (int l = 1; l < d.NL; l++) {
     if (fused) {
       // GEMM + zero-state cell in the epilogue: h_{l-1} @ Wxp_l^T + bp_l -> (i,g,o) -> h_l ; gates saved as bf16
@@ -307,12 +309,7 @@ extern "C" int arcvae_decoder_backward(const arcvae_dims* d, const arcvae_decode
       q.A = A; q.lda = K; q.a_mn = false;
       q.B = Bw; q.ldb = H; q.b_mn = true;                       // B[k*H + n]: row-major [K,H]
       q.accumulate = false; q.splitk = 1; q.rm = id; q.a_rows_total = R; q.Hh = H; q.dg_out = out;
-      if (layer_below >= 1) {
-        q.epi = TC_EPI_DEC_CELL_BWD; q.gates_b = tp.gates_b[layer_below];
-      } else {
-        q.epi = TC_EPI_DEC_CELL0_BWD; q.table = tp.prep.table; q.wc = tp.prep.wc; q.tok = tp.in_tok; q.cond = cond;
-        q.Bt = B; q.Cc = C;
-      }
+      q.epi = TC_EPI_DEC_CELL_BWD; q.gates_b = tp.gates_b[layer_below];      // layer 0 keeps its gate tape as well
       return gemm_tc(q, st);
     };
     __nv_bfloat16* cur = sc.dGb;
@@ -330,16 +327,12 @@ extern "C" int arcvae_decoder_backward(const arcvae_dims* d, const arcvae_decode
       ARCVAE_TRY(expand_perm_gates_add(sc.dbc[l], H, 1, g->bias[l], st));
       __nv_bfloat16* tmp = cur; cur = nxt; nxt = tmp;
     }
-    // cur = dG_0 in the natural compact (i|g|o) layout
+    // cur = dG_0 in the tile-permuted compact layout; the table gradient is un-permuted after the scatter
     ARCVAE_CUDA(cudaMemsetAsync(sc.dwc, 0, (size_t)H3 * C * sizeof(float), st));
     ARCVAE_CUDA(cudaMemsetAsync(sc.dWxc[0], 0, (size_t)H3 * (E + C) * sizeof(float), st));
     ARCVAE_CUDA(cudaMemsetAsync(sc.dbc[0], 0, (size_t)H3 * sizeof(float), st));
-    if (scatter_onehot_supported(H3, V, C)) {
-      ARCVAE_TRY(scatter_rows_onehot_tc(cur, tp.in_tok, R, H3, V, sc.onehot, sc.dtable, cond, B, C, sc.dwc, st));
-    } else {
-      ARCVAE_CUDA(cudaMemsetAsync(sc.dtable, 0, (size_t)V * H3 * sizeof(float), st));
-      ARCVAE_TRY(scatter_rows_by_token_bf16_w(cur, tp.in_tok, R, H3, V, sc.dtable, cond, B, C, sc.dwc, st));
-    }
+    ARCVAE_REQUIRE(scatter_onehot_supported(H3, V, C), "fused decoder backward: V + 2C <= 128");
+    ARCVAE_TRY(scatter_rows_onehot_tc(cur, tp.in_tok, R, H3, V, sc.onehot, sc.dtable, cond, B, C, sc.dwc, H, sc.dtable_tmp, st));
   } else {
   ARCVAE_TRY(gemm_any(precision, 0, 0, (int)R, H, V, Mat{dlogits_tm, bf ? sc.dlb : nullptr, V},
                       Mat{p->fc_out_w, tp.prep.Woutb, H}, dh, H, nullptr, false, id, R, st));

@@ -324,7 +324,7 @@ extern "C" int arcvae_encoder_backward(const arcvae_dims* d, const arcvae_encode
                             nullptr, false, id, R, st));
       } else {
         if (scatter_onehot_supported(G4, d->V, 0)) {
-          ARCVAE_TRY(scatter_rows_onehot_tc(sc.dAb, tp.xT, R, G4, d->V, sc.onehot, sc.dtable0, nullptr, B, 0, nullptr, st));
+          ARCVAE_TRY(scatter_rows_onehot_tc(sc.dAb, tp.xT, R, G4, d->V, sc.onehot, sc.dtable0, nullptr, B, 0, nullptr, 0, nullptr, st));
         } else {
           ARCVAE_CUDA(cudaMemsetAsync(sc.dtable0, 0, (size_t)d->V * G4 * sizeof(float), st));
           ARCVAE_TRY(scatter_rows_by_token_bf16(sc.dAb, tp.xT, R, G4, d->V, sc.dtable0, st));

@@ -43,6 +43,7 @@ struct TcParams {
   bf16* gates_b; bf16* hb_out; bf16* dg_out;
   const float* table; const float* wc; const int32_t* tok; const float* cond;
   int Bt, Cc, Hh;
+  int use_scratch;   // per-warp transposition scratch present after the TcShared block
 };
 
 __device__ __forceinline__ float tanh_fast_(float x) { return tanh_approx_(x); }
@@ -80,6 +81,65 @@ __device__ __forceinline__ void dec_cell_grads_fast(float i_, float g_, float o_
   dag = dcc * i_ * (1.f - g_ * g_);
 }
 
+// ---- per-warp transposition scratch: the epilogue thread owns a ROW (tcgen05.ld 32x32b), but a warp-wide 16-byte
+// access to 32 different rows costs 32 L1 wavefronts instead of 4.  Row segments are therefore staged in shared
+// memory (pitch 400 B: conflict-free for the thread=row side) and moved to / from HBM with lanes running along the row.
+constexpr int TC_SCR_PITCH = 400;
+constexpr int TC_SCR_BYTES = 32 * TC_SCR_PITCH;   // per epilogue warp
+__device__ __forceinline__ void scr_store_rows(const uint8_t* scr, uint8_t* gbase, long gstride, int nb, int nrows, int lane) {
+  const int cpr = nb >> 4, total = nrows * cpr;
+  for (int idx = lane; idx < total; idx += 32) {
+    const int r = idx / cpr, c = idx - r * cpr;
+    *reinterpret_cast<uint4*>(gbase + r * gstride + c * 16) = *reinterpret_cast<const uint4*>(scr + r * TC_SCR_PITCH + c * 16);
+  }
+}
+__device__ __forceinline__ void scr_load_rows(uint8_t* scr, const uint8_t* gbase, long gstride, int nb, int nrows, int lane) {
+  // batches of 8 independent 16-byte loads per lane, so one HBM/L2 latency covers 4 KB per warp instead of 512 B
+  const int cpr = nb >> 4, total = nrows * cpr;
+  for (int base = 0; base < total; base += 8 * 32) {
+    uint4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int idx = base + u * 32 + lane;
+      if (idx < total) {
+        const int r = idx / cpr, c = idx - r * cpr;
+        v[u] = __ldg(reinterpret_cast<const uint4*>(gbase + r * gstride + c * 16));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int idx = base + u * 32 + lane;
+      if (idx < total) {
+        const int r = idx / cpr, c = idx - r * cpr;
+        *reinterpret_cast<uint4*>(scr + r * TC_SCR_PITCH + c * 16) = v[u];
+      }
+    }
+  }
+}
+__device__ __forceinline__ void scr_put16(uint8_t* dst, const float (&v)[16]) {
+  uint32_t pk[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    pk[j] = *reinterpret_cast<uint32_t*>(&t);
+  }
+  *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  *reinterpret_cast<uint4*>(dst + 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+}
+__device__ __forceinline__ void scr_get16(const uint8_t* src, float (&v)[16]) {
+  const uint4 a = *reinterpret_cast<const uint4*>(src);
+  const uint4 b = *reinterpret_cast<const uint4*>(src + 16);
+  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    float2 t = __bfloat1622float2(pa[j]);
+    v[2 * j] = t.x; v[2 * j + 1] = t.y;
+    float2 w = __bfloat1622float2(pb[j]);
+    v[8 + 2 * j] = w.x; v[8 + 2 * j + 1] = w.y;
+  }
+}
+
 struct __align__(8) TcShared {
   uint64_t full[TC_MAX_STAGES];
   uint64_t empty[TC_MAX_STAGES];
@@ -97,6 +157,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t b_bytes = (uint32_t)p.BN * TC_BK * 2;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   TcShared* sh = reinterpret_cast<TcShared*>(smem + (size_t)p.stages * stage_bytes);
+  uint8_t* scratch = reinterpret_cast<uint8_t*>(sh) + 256;      // TC_EPI_WARPS x TC_SCR_BYTES when p.use_scratch
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -130,8 +191,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mi = tile % p.mt;
-        const int ni = (tile / p.mt) % p.nt;
+        // N-fastest tile order: the nt column tiles of one row tile run on neighbouring CTAs at the same time, so the
+        // A tile is fetched from HBM once and re-read from L2 (M-fastest streamed A nt times: ncu, r01a)
+        const int ni = tile % p.nt;
+        const int mi = (tile / p.nt) % p.mt;
         const int ks = tile / (p.mt * p.nt);
         const int m0 = mi * TC_BM, n0 = ni * p.BN;
         const int gm0 = (int)p.rm(m0);
@@ -206,8 +269,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int ch_hi = half == 0 ? (nchunks + 1) >> 1 : nchunks;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
-      const int mi = tile % p.mt;
-      const int ni = (tile / p.mt) % p.nt;
+      const int ni = tile % p.nt;
+      const int mi = (tile / p.nt) % p.mt;
       const int m0 = mi * TC_BM, n0 = ni * p.BN;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -219,37 +282,85 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
       const bool atomic = p.splitk > 1;
       const bool add_bias = p.bias != nullptr && (tile / (p.mt * p.nt)) == 0;
+      uint8_t* scr = scratch + (warp - 2) * TC_SCR_BYTES;
+      uint8_t* srow = scr + lane * TC_SCR_PITCH;
+      const int rows_here = min(32, p.M - (m0 + q * 32));          // rows of this warp's quarter inside the matrix
+      const long grow0 = rows_here > 0 ? p.rm(m0 + q * 32) : 0;     // first global row (a row tile never straddles timesteps)
       if (p.epi == TC_EPI_DEC_CELL_FWD) {
-        // accumulator columns of this 192-wide tile: [0,64) = i, [64,128) = g, [128,192) = o of units 64*ni .. 64*ni+63
+        // accumulator columns of this 192-wide tile: [0,64) = i, [64,128) = g, [128,192) = o of units 64*ni .. 64*ni+63;
+        // this warp: units half*32 .. +32.  scratch row = [h 64 B | i 64 B | g 64 B | o 64 B]
         const int H = p.Hh;
-        for (int c0 = half * 32; c0 < half * 32 + 32; c0 += 16) {
+#pragma unroll 1
+        for (int cc = 0; cc < 2; cc++) {
+          const int c0 = half * 32 + cc * 16;
           uint32_t ri[16], rg[16], ro[16];
           tc::tmem_ld16(taddr + c0, ri);
           tc::tmem_ld16(taddr + 64 + c0, rg);
           tc::tmem_ld16(taddr + 128 + c0, ro);
           tc::tmem_ld_wait();
-          if (row_ok) {
-            float gi[16], gg[16], go[16], hv[16];
+          float gi[16], gg[16], go[16], hv[16];
 #pragma unroll
-            for (int k = 0; k < 16; k++) {
-              gi[k] = sigmoid_fast_(__uint_as_float(ri[k]) + p.bias[n0 + c0 + k]);
-              gg[k] = tanh_fast_(__uint_as_float(rg[k]) + p.bias[n0 + 64 + c0 + k]);
-              go[k] = sigmoid_fast_(__uint_as_float(ro[k]) + p.bias[n0 + 128 + c0 + k]);
-              hv[k] = go[k] * tanh_fast_(gi[k] * gg[k]);
-            }
-            store16_bf16(p.hb_out + grow * H + ni * 64 + c0, hv);
-            bf16* gb = p.gates_b + grow * 3L * H + n0 + c0;
-            store16_bf16(gb, gi);
-            store16_bf16(gb + 64, gg);
-            store16_bf16(gb + 128, go);
+          for (int k = 0; k < 16; k++) {
+            gi[k] = sigmoid_fast_(__uint_as_float(ri[k]) + __ldg(p.bias + n0 + c0 + k));
+            gg[k] = tanh_fast_(__uint_as_float(rg[k]) + __ldg(p.bias + n0 + 64 + c0 + k));
+            go[k] = sigmoid_fast_(__uint_as_float(ro[k]) + __ldg(p.bias + n0 + 128 + c0 + k));
+            hv[k] = go[k] * tanh_fast_(gi[k] * gg[k]);
           }
+          scr_put16(srow + cc * 32, hv);
+          scr_put16(srow + 64 + cc * 32, gi);
+          scr_put16(srow + 128 + cc * 32, gg);
+          scr_put16(srow + 192 + cc * 32, go);
         }
-      } else if (p.epi == TC_EPI_DEC_CELL_BWD || p.epi == TC_EPI_DEC_CELL0_BWD) {
-        // accumulator = d h for units n0 + c; emit the pre-activation gradients of the zero-state cell
+        __syncwarp();
+        if (rows_here > 0) {
+          scr_store_rows(scr, reinterpret_cast<uint8_t*>(p.hb_out + grow0 * H + ni * 64 + half * 32), (long)H * 2, 64, rows_here, lane);
+          bf16* gb = p.gates_b + grow0 * 3L * H + n0 + half * 32;
+          scr_store_rows(scr + 64, reinterpret_cast<uint8_t*>(gb), 3L * H * 2, 64, rows_here, lane);
+          scr_store_rows(scr + 128, reinterpret_cast<uint8_t*>(gb + 64), 3L * H * 2, 64, rows_here, lane);
+          scr_store_rows(scr + 192, reinterpret_cast<uint8_t*>(gb + 128), 3L * H * 2, 64, rows_here, lane);
+        }
+        __syncwarp();
+      } else if (p.epi == TC_EPI_DEC_CELL_BWD) {
+        // accumulator = d h of units n0 + c; per 64-unit block the saved gates of a row are 384 contiguous bytes
+        // [i 64 | g 64 | o 64] and the pre-activation gradients go out in the same layout
+        const int H = p.Hh;
+        const int nblocks = p.BN >> 6;                          // whole 64-unit blocks are split between the two warps of a quarter
+        const int blk_lo = half == 0 ? 0 : (nblocks + 1) >> 1;
+        const int blk_hi = half == 0 ? (nblocks + 1) >> 1 : nblocks;
+#pragma unroll 1
+        for (int blk = blk_lo; blk < blk_hi; blk++) {
+          const int nblk = n0 + blk * 64;                       // first unit of the block
+          const long goff = grow0 * 3L * H + (long)(nblk / 64) * 192;
+          if (rows_here > 0)
+            scr_load_rows(scr, reinterpret_cast<const uint8_t*>(p.gates_b + goff), 3L * H * 2, 384, rows_here, lane);
+          __syncwarp();
+#pragma unroll 1
+          for (int cc = 0; cc < 4; cc++) {
+            const int ch = blk * 4 + cc;
+            uint32_t r[16];
+            tc::tmem_ld16(taddr + ch * 16, r);
+            tc::tmem_ld_wait();
+            float gi[16], gg[16], go[16], dai[16], dag[16], dao[16];
+            scr_get16(srow + cc * 32, gi);
+            scr_get16(srow + 128 + cc * 32, gg);
+            scr_get16(srow + 256 + cc * 32, go);
+#pragma unroll
+            for (int k = 0; k < 16; k++) dec_cell_grads_fast(gi[k], gg[k], go[k], __uint_as_float(r[k]), dai[k], dag[k], dao[k]);
+            scr_put16(srow + cc * 32, dai);
+            scr_put16(srow + 128 + cc * 32, dag);
+            scr_put16(srow + 256 + cc * 32, dao);
+          }
+          __syncwarp();
+          if (rows_here > 0)
+            scr_store_rows(scr, reinterpret_cast<uint8_t*>(p.dg_out + goff), 3L * H * 2, 384, rows_here, lane);
+          __syncwarp();
+        }
+      } else if (p.epi == TC_EPI_DEC_CELL0_BWD) {
+        // layer-0 gates recomputed from the table (used when the layer-0 gate tape is not kept)
         const int H = p.Hh;
         int tokv = 0;
         const float* crow = nullptr;
-        if (p.epi == TC_EPI_DEC_CELL0_BWD && row_ok) {
+        if (row_ok) {
           tokv = p.tok[grow];
           crow = p.cond + (grow % p.Bt) * p.Cc;
         }
@@ -257,61 +368,68 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint32_t r[16];
           tc::tmem_ld16(taddr + c0, r);
           tc::tmem_ld_wait();
-          const int n = n0 + c0;                       // first unit of this chunk (16 units, same 64-block)
+          const int n = n0 + c0;
           if (row_ok && n < H) {
             float dai[16], dag[16], dao[16];
-            if (p.epi == TC_EPI_DEC_CELL_BWD) {
-              const long off = grow * 3L * H + (n / 64) * 192 + (n % 64);
-              float gi[16], gg[16], go[16];
-              load16_bf16(p.gates_b + off, gi);
-              load16_bf16(p.gates_b + off + 64, gg);
-              load16_bf16(p.gates_b + off + 128, go);
+            const float* trow = p.table + (long)tokv * 3 * H + n;
+            float a3[3][16];
 #pragma unroll
-              for (int k = 0; k < 16; k++) dec_cell_grads_fast(gi[k], gg[k], go[k], __uint_as_float(r[k]), dai[k], dag[k], dao[k]);
-              store16_bf16(p.dg_out + off, dai);
-              store16_bf16(p.dg_out + off + 64, dag);
-              store16_bf16(p.dg_out + off + 128, dao);
-            } else {
-              const float* trow = p.table + (long)tokv * 3 * H + n;
-              float a3[3][16];
+            for (int g = 0; g < 3; g++)
+#pragma unroll
+              for (int k4 = 0; k4 < 4; k4++) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(trow + g * H) + k4);
+                a3[g][4 * k4] = v.x; a3[g][4 * k4 + 1] = v.y; a3[g][4 * k4 + 2] = v.z; a3[g][4 * k4 + 3] = v.w;
+              }
+            if (p.Cc == 1) {
+              const float cv = __ldg(crow);
 #pragma unroll
               for (int g = 0; g < 3; g++)
 #pragma unroll
                 for (int k4 = 0; k4 < 4; k4++) {
-                  const float4 v = __ldg(reinterpret_cast<const float4*>(trow + g * H) + k4);
-                  a3[g][4 * k4] = v.x; a3[g][4 * k4 + 1] = v.y; a3[g][4 * k4 + 2] = v.z; a3[g][4 * k4 + 3] = v.w;
+                  const float4 w = __ldg(reinterpret_cast<const float4*>(p.wc + g * H + n) + k4);
+                  a3[g][4 * k4] = fmaf(cv, w.x, a3[g][4 * k4]); a3[g][4 * k4 + 1] = fmaf(cv, w.y, a3[g][4 * k4 + 1]);
+                  a3[g][4 * k4 + 2] = fmaf(cv, w.z, a3[g][4 * k4 + 2]); a3[g][4 * k4 + 3] = fmaf(cv, w.w, a3[g][4 * k4 + 3]);
                 }
-              if (p.Cc == 1) {
-                const float cv = __ldg(crow);
+            } else {
+              for (int c = 0; c < p.Cc; c++) {
+                const float cv = __ldg(crow + c);
 #pragma unroll
                 for (int g = 0; g < 3; g++)
 #pragma unroll
-                  for (int k4 = 0; k4 < 4; k4++) {
-                    const float4 w = __ldg(reinterpret_cast<const float4*>(p.wc + g * H + n) + k4);
-                    a3[g][4 * k4] = fmaf(cv, w.x, a3[g][4 * k4]); a3[g][4 * k4 + 1] = fmaf(cv, w.y, a3[g][4 * k4 + 1]);
-                    a3[g][4 * k4 + 2] = fmaf(cv, w.z, a3[g][4 * k4 + 2]); a3[g][4 * k4 + 3] = fmaf(cv, w.w, a3[g][4 * k4 + 3]);
-                  }
-              } else {
-                for (int c = 0; c < p.Cc; c++) {
-                  const float cv = __ldg(crow + c);
-#pragma unroll
-                  for (int g = 0; g < 3; g++)
-#pragma unroll
-                    for (int k = 0; k < 16; k++)
-                      a3[g][k] = fmaf(cv, __ldg(p.wc + (long)(g * H + n + k) * p.Cc + c), a3[g][k]);
-                }
+                  for (int k = 0; k < 16; k++)
+                    a3[g][k] = fmaf(cv, __ldg(p.wc + (long)(g * H + n + k) * p.Cc + c), a3[g][k]);
               }
-#pragma unroll
-              for (int k = 0; k < 16; k++)
-                dec_cell_grads_fast(sigmoid_fast_(a3[0][k]), tanh_fast_(a3[1][k]), sigmoid_fast_(a3[2][k]),
-                                    __uint_as_float(r[k]), dai[k], dag[k], dao[k]);
-              bf16* dst = p.dg_out + grow * 3L * H + n;
-              store16_bf16(dst, dai);
-              store16_bf16(dst + H, dag);
-              store16_bf16(dst + 2 * H, dao);
             }
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+              dec_cell_grads_fast(sigmoid_fast_(a3[0][k]), tanh_fast_(a3[1][k]), sigmoid_fast_(a3[2][k]),
+                                  __uint_as_float(r[k]), dai[k], dag[k], dao[k]);
+            bf16* dst = p.dg_out + grow * 3L * H + n;
+            store16_bf16(dst, dai);
+            store16_bf16(dst + H, dag);
+            store16_bf16(dst + 2 * H, dao);
           }
         }
+      } else if (p.use_scratch) {
+        // plain bf16 output, full tiles: this warp's half of the tile's columns, staged and written along the rows
+        const int nb = (ch_hi - ch_lo) * 32;                    // bytes per row
+#pragma unroll 1
+        for (int ch = ch_lo; ch < ch_hi; ch++) {
+          uint32_t r[16];
+          tc::tmem_ld16(taddr + ch * 16, r);
+          tc::tmem_ld_wait();
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; j++) {
+            v[j] = __uint_as_float(r[j]);
+            if (add_bias) v[j] += __ldg(p.bias + n0 + ch * 16 + j);
+          }
+          scr_put16(srow + (ch - ch_lo) * 32, v);
+        }
+        __syncwarp();
+        if (rows_here > 0)
+          scr_store_rows(scr, reinterpret_cast<uint8_t*>(p.Cb + grow0 * p.ldcb + n0 + ch_lo * 16), (long)p.ldcb * 2, nb, rows_here, lane);
+        __syncwarp();
       } else {
       for (int c0 = ch_lo * 16; c0 < ch_hi * 16; c0 += 16) {
         uint32_t r[16];
@@ -484,12 +602,20 @@ int gemm_tc(const TcGemm& g, cudaStream_t st) {
     ARCVAE_REQUIRE(g.epi != TC_EPI_DEC_CELL0_BWD || (g.table && g.wc && g.tok && g.cond), "layer-0 recompute inputs");
   }
   const size_t stage_bytes = (size_t)TC_BM * TC_BK * 2 + (size_t)p.BN * TC_BK * 2;
-  int stages = (int)((200 * 1024) / stage_bytes);
+  // transposition scratch for the fused cells and for plain bf16-only outputs of full, aligned tiles
+  const bool plain_fast = g.epi == TC_EPI_PLAIN && g.Cb != nullptr && g.C == nullptr && p.splitk == 1 && (g.N % p.BN) == 0 &&
+                          (p.BN % 32) == 0 && p.BN * 2 / 2 <= 384 && (g.ldcb % 8) == 0 &&
+                          ((reinterpret_cast<uintptr_t>(g.Cb) & 15) == 0);
+  p.use_scratch = (g.epi == TC_EPI_DEC_CELL_FWD || g.epi == TC_EPI_DEC_CELL_BWD || plain_fast) ? 1 : 0;
+  const size_t scratch_bytes = p.use_scratch ? (size_t)TC_EPI_WARPS * TC_SCR_BYTES : 0;
+  int stages = (int)((225 * 1024 - 2048 - scratch_bytes) / stage_bytes);
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   if (stages > p.kb_per + 1 && p.kb_per + 1 >= 2) stages = p.kb_per + 1 > 2 ? p.kb_per + 1 : 2;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + sizeof(TcShared) + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + 256 + scratch_bytes + 1024;
+  ARCVAE_REQUIRE(stages >= 2, "gemm_tc: pipeline needs two stages");
+  static_assert(sizeof(TcShared) <= 256, "TcShared must fit the 256-byte slot in front of the scratch");
 
   CUtensorMap tmA, tmB;
   if (!g.a_mn) {

@@ -22,8 +22,9 @@ int lstm_cell_bwd(float* gates, const float* c, const float* c_prev, const float
 
 // decoder cells (zero state: c = i*g, h = o*tanh(c); forget gate unused) on COMPACT gate layout [.., 3H] = (i,g,o)
 // layer 0: a = table[tok[r]] + cond[r % B] @ wc^T   (table [V,3H], wc [3H,C]); rows r = rm(i), i < R
+// gates_b (optional, fused bf16 path): activated (i,g,o) in the tile-permuted layout of the fused GEMM epilogues
 int dec_cell0_fwd(const float* table, const float* wc, const int32_t* tok, const float* cond, int B, int C, int H,
-                  int R, RowMap rm, float* h, __nv_bfloat16* hb, cudaStream_t st);
+                  int R, RowMap rm, float* h, __nv_bfloat16* hb, __nv_bfloat16* gates_b, cudaStream_t st);
 // layers >= 1: G [.,3H] pre-activation -> activated in place; h out
 int dec_cell_fwd(float* G, float* h, __nv_bfloat16* hb, int H, int R, RowMap rm, cudaStream_t st);
 // backward: G activated (in) -> dG (out, in place) given dh [.,H]
@@ -120,7 +121,8 @@ int scatter_rows_by_token_bf16(const __nv_bfloat16* X, const int32_t* tok, long 
 constexpr int SCATTER_NW = 128;
 bool scatter_onehot_supported(int N, int V, int C);
 int scatter_rows_onehot_tc(const __nv_bfloat16* X, const int32_t* tok, long R, int N, int V, __nv_bfloat16* onehot,
-                           float* dtable_ext, const float* cond, int B, int C, float* dwc, cudaStream_t st);
+                           float* dtable_ext, const float* cond, int B, int C, float* dwc, int perm_H, float* tmp,
+                           cudaStream_t st);
 int scatter_rows_by_token_bf16_w(const __nv_bfloat16* X, const int32_t* tok, long R, int N, int V, float* dtable,
                                  const float* cond, int B, int C, float* dwc, cudaStream_t st);
 

@@ -150,7 +150,8 @@ __global__ void k_dec_cell0_fwd(const float* __restrict__ table, const float* __
 template <bool FAST>
 __global__ void k_dec_cell0_fwd_v8(const float* __restrict__ table, const float* __restrict__ wc,
                                    const int32_t* __restrict__ tok, const float* __restrict__ cond, int B, int C, int H,
-                                   int R, RowMap rm, float* __restrict__ h, __nv_bfloat16* __restrict__ hb) {
+                                   int R, RowMap rm, float* __restrict__ h, __nv_bfloat16* __restrict__ hb,
+                                   __nv_bfloat16* __restrict__ gates_b) {
   const int cpr = H >> 3;                               // 8-unit chunks per row
   const long total = (long)R * cpr;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -177,8 +178,24 @@ __global__ void k_dec_cell0_fwd_v8(const float* __restrict__ table, const float*
     float hv[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-      if (FAST) hv[k] = sigmoid_approx_(a[2][k]) * tanh_approx_(sigmoid_approx_(a[0][k]) * tanh_approx_(a[1][k]));
-      else hv[k] = sigmoidf_(a[2][k]) * tanhf_(sigmoidf_(a[0][k]) * tanhf_(a[1][k]));
+      if (FAST) {
+        a[0][k] = sigmoid_approx_(a[0][k]); a[1][k] = tanh_approx_(a[1][k]); a[2][k] = sigmoid_approx_(a[2][k]);
+        hv[k] = a[2][k] * tanh_approx_(a[0][k] * a[1][k]);
+      } else {
+        hv[k] = sigmoidf_(a[2][k]) * tanhf_(sigmoidf_(a[0][k]) * tanhf_(a[1][k]));
+      }
+    }
+    if (FAST && gates_b != nullptr) {
+      // activated gates for the fused backward, tile-permuted layout [row][64-unit block][i|g|o][64] (needs H % 64 == 0)
+      __nv_bfloat16* gb = gates_b + r * 3L * H + (j >> 6) * 192 + (j & 63);
+#pragma unroll
+      for (int g = 0; g < 3; g++) {
+        uint4 o;
+        __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int k = 0; k < 4; k++) po[k] = __floats2bfloat162_rn(a[g][2 * k], a[g][2 * k + 1]);
+        *reinterpret_cast<uint4*>(gb + g * 64) = o;
+      }
     }
     if (h != nullptr) {
       *reinterpret_cast<float4*>(h + r * H + j) = make_float4(hv[0], hv[1], hv[2], hv[3]);
@@ -194,13 +211,14 @@ __global__ void k_dec_cell0_fwd_v8(const float* __restrict__ table, const float*
   }
 }
 int dec_cell0_fwd(const float* table, const float* wc, const int32_t* tok, const float* cond, int B, int C, int H,
-                  int R, RowMap rm, float* h, __nv_bfloat16* hb, cudaStream_t st) {
+                  int R, RowMap rm, float* h, __nv_bfloat16* hb, __nv_bfloat16* gates_b, cudaStream_t st) {
   if (R <= 0) return 0;
   TimeScope ts(TIME_POINTWISE, st);
+  ARCVAE_REQUIRE(gates_b == nullptr || (h == nullptr && (H % 64) == 0), "layer-0 gate tape: fused bf16 path, H % 64 == 0");
   if ((H & 7) == 0) {
     const long total = (long)R * (H >> 3);
-    if (h == nullptr) k_dec_cell0_fwd_v8<true><<<grid_for(total, 256, 16), 256, 0, st>>>(table, wc, tok, cond, B, C, H, R, rm, h, hb);
-    else k_dec_cell0_fwd_v8<false><<<grid_for(total, 256, 16), 256, 0, st>>>(table, wc, tok, cond, B, C, H, R, rm, h, hb);
+    if (h == nullptr) k_dec_cell0_fwd_v8<true><<<grid_for(total, 256, 16), 256, 0, st>>>(table, wc, tok, cond, B, C, H, R, rm, h, hb, gates_b);
+    else k_dec_cell0_fwd_v8<false><<<grid_for(total, 256, 16), 256, 0, st>>>(table, wc, tok, cond, B, C, H, R, rm, h, hb, nullptr);
   } else {
     k_dec_cell0_fwd<<<grid_for((long)R * H, 256), 256, 0, st>>>(table, wc, tok, cond, B, C, H, R, rm, h, hb);
   }
@@ -507,9 +525,28 @@ __global__ void k_onehot_dwc(const float* __restrict__ D, int N, int V, int C, f
     dwc[i] += D[(long)(V + 2 * c) * N + n] + D[(long)(V + 2 * c + 1) * N + n];
   }
 }
+// dst[r, nat(p)] = src[r, p]: columns in tile-permuted compact order (p = j*192 + gi*64 + u) -> natural (gi*H + j*64 + u)
+__global__ void k_unpermute_cols(const float* __restrict__ src, int rows, int H, float* __restrict__ dst) {
+  const int H3 = 3 * H;
+  const long total = (long)rows * H3;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / H3;
+    const int pc = (int)(i - r * H3);
+    const int j = pc / 192, rem = pc % 192;
+    dst[r * H3 + (rem / 64) * H + j * 64 + (rem % 64)] = src[i];
+  }
+}
 bool scatter_onehot_supported(int N, int V, int C) { return (N % 64) == 0 && V + 2 * C <= SCATTER_NW; }
+// perm_H > 0: X's columns are in tile-permuted compact order (N = 3*perm_H); dtable_ext comes out in natural order and
+// `tmp` ([SCATTER_NW, N] floats) receives the permuted product first
 int scatter_rows_onehot_tc(const __nv_bfloat16* X, const int32_t* tok, long R, int N, int V, __nv_bfloat16* onehot,
-                           float* dtable_ext, const float* cond, int B, int C, float* dwc, cudaStream_t st) {
+                           float* dtable_ext, const float* cond, int B, int C, float* dwc, int perm_H, float* tmp,
+                           cudaStream_t st) {
+  float* natural = dtable_ext;
+  if (perm_H > 0) {
+    ARCVAE_REQUIRE(tmp != nullptr && N == 3 * perm_H && (perm_H % 64) == 0, "permuted scatter needs a scratch table, N = 3H");
+    dtable_ext = tmp;
+  }
   if (R <= 0) return 0;
   ARCVAE_REQUIRE(scatter_onehot_supported(N, V, cond != nullptr ? C : 0), "one-hot scatter: N % 64 == 0, V + 2C <= 128");
   const int NW = SCATTER_NW;
@@ -527,6 +564,11 @@ int scatter_rows_onehot_tc(const __nv_bfloat16* X, const int32_t* tok, long R, i
   g.splitk = pick_splitk_tc(NW, N, (int)R);
   g.rm = RowMap{nullptr, 1}; g.a_rows_total = R;
   ARCVAE_TRY(gemm_tc(g, st));
+  if (perm_H > 0) {
+    k_unpermute_cols<<<grid_for((long)NW * N, 256), 256, 0, st>>>(dtable_ext, NW, perm_H, natural);
+    ARCVAE_LAUNCHED();
+    dtable_ext = natural;
+  }
   if (cond != nullptr && dwc != nullptr) {
     k_onehot_dwc<<<cdiv((long)N * C, 256), 256, 0, st>>>(dtable_ext, N, V, C, dwc);
     ARCVAE_LAUNCHED();
