@@ -49,6 +49,12 @@ struct EncTape {
   // cluster path
   bf16* gates_b[ARCVAE_MAX_LAYERS]; // [T*B,4H] activated gates
   bf16* WhTb[ARCVAE_MAX_LAYERS];    // [H,4H]
+  // bf16 operands of the tensor-core head products (bf16 paths)
+  bf16* ub;          // [B,2H]
+  bf16* lvhb;        // [B,2H]
+  bf16* Wmub;        // [L,2H]
+  bf16* Wlhb;        // [2H,2H]
+  bf16* Wlvb;        // [L,2H]
   bf16* Pb;                         // [T*B,4H] input projection of the layer being run (reused)
   bf16* table0b;                    // [V,4H] bf16 copy of table0
 };
@@ -67,6 +73,13 @@ static size_t enc_tape_layout(const arcvae_dims& d, int B, int T, int path, void
   tt.logvar = a.take<float>((size_t)B * d.L);
   tt.h_last = a.take<float>((size_t)B * H);
   tt.err = a.take<int>(4);
+  if (path != PATH_STEP_F32) {
+    tt.ub = a.take<bf16>((size_t)B * 2 * H);
+    tt.lvhb = a.take<bf16>((size_t)B * 2 * H);
+    tt.Wmub = a.take<bf16>((size_t)d.L * 2 * H);
+    tt.Wlhb = a.take<bf16>((size_t)4 * H * H);
+    tt.Wlvb = a.take<bf16>((size_t)d.L * 2 * H);
+  }
   const size_t Rpad = (size_t)T * (((size_t)B + 127) / 128 * 128);   // cluster path: tile-padded, thread-friendly tape
   for (int l = 0; l < d.NL; l++) {
     tt.c[l] = a.take<float>((path == PATH_CLUSTER ? Rpad : R) * H);
@@ -102,6 +115,9 @@ struct EncScratch {
   float* dc;        // [B,H]
   float* dtable0;   // [max(V, SCATTER_NW),4H]  (rows >= V: scratch of the one-hot GEMM)
   bf16* dAb;        // [T*B,4H] bf16 pre-activation gradients (tensor-core operand / cluster exchange)
+  bf16* dmub;       // [B,L]   bf16 copies for the tensor-core head products
+  bf16* dlvb;       // [B,L]
+  bf16* dlvhb;      // [B,2H]
   bf16* onehot;     // [T*B,SCATTER_NW] one-hot tokens (tensor-core scatter)
   void* xch;        // cluster backward: exchange buffers of the partial d h
 };
@@ -119,6 +135,11 @@ static size_t enc_scratch_layout(const arcvae_dims& d, int B, int T, int path, v
   ss.dc = a.take<float>((size_t)B * d.H);
   ss.dtable0 = a.take<float>((size_t)(d.V > SCATTER_NW ? d.V : SCATTER_NW) * 4 * d.H);
   ss.dAb = (path != PATH_STEP_F32) ? a.take<bf16>((size_t)T * B * 4 * d.H) : nullptr;
+  if (path != PATH_STEP_F32) {
+    ss.dmub = a.take<bf16>((size_t)B * d.L);
+    ss.dlvb = a.take<bf16>((size_t)B * d.L);
+    ss.dlvhb = a.take<bf16>((size_t)B * 2 * d.H);
+  }
   ss.onehot = (path != PATH_STEP_F32) ? a.take<bf16>((size_t)T * B * SCATTER_NW) : nullptr;
   ss.xch = (path != PATH_STEP_F32) ? a.take<char>(lstm_cluster_xch_bytes(B)) : nullptr;
   if (s) *s = ss;
@@ -134,14 +155,23 @@ static int check_dims(const arcvae_dims* d) {
 
 // ---- head: encoder.py:106-130 and its reverse ----------------------------------------------------------------------
 static int head_forward(const arcvae_dims& d, const arcvae_encoder_params* p, const EncTape& tp, const float* h_last,
-                        const float* cond, int B, float* mu, float* logvar, cudaStream_t st) {
-  const int H = d.H;
+                        const float* cond, int B, float* mu, float* logvar, int precision, cudaStream_t st) {
+  const int H = d.H, H2 = 2 * d.H;
   RowMap id{nullptr, 1};
-  ARCVAE_TRY(head_build_u(h_last, cond, p->condition_fc_w, p->condition_fc_b, B, H, d.C, tp.u, st));
-  ARCVAE_TRY(gemm_f32(0, 1, B, d.L, 2 * H, tp.u, 2 * H, p->fc_mu_w, 2 * H, tp.mu_raw, d.L, p->fc_mu_b, false, id, 1, st));
-  ARCVAE_TRY(gemm_f32(0, 1, B, 2 * H, 2 * H, tp.u, 2 * H, p->fc_logvar_hidden_w, 2 * H, tp.lvh, 2 * H, p->fc_logvar_hidden_b, false, id, 1, st));
-  ARCVAE_TRY(tanh_inplace(tp.lvh, (long)B * 2 * H, st));
-  ARCVAE_TRY(gemm_f32(0, 1, B, d.L, 2 * H, tp.lvh, 2 * H, p->fc_logvar_w, 2 * H, tp.lv_raw, d.L, p->fc_logvar_b, false, id, 1, st));
+  const bool bf = precision == ARCVAE_PREC_BF16;      // bf16 mode: the head products run on the tensor cores as well
+  if (bf) {
+    ARCVAE_TRY(f32_to_bf16(p->fc_mu_w, tp.Wmub, (long)d.L * H2, st));
+    ARCVAE_TRY(f32_to_bf16(p->fc_logvar_hidden_w, tp.Wlhb, (long)H2 * H2, st));
+    ARCVAE_TRY(f32_to_bf16(p->fc_logvar_w, tp.Wlvb, (long)d.L * H2, st));
+  }
+  ARCVAE_TRY(head_build_u(h_last, cond, p->condition_fc_w, p->condition_fc_b, B, H, d.C, tp.u, bf ? tp.ub : nullptr, st));
+  ARCVAE_TRY(gemm_any(precision, 0, 1, B, d.L, H2, Mat{tp.u, bf ? tp.ub : nullptr, H2}, Mat{p->fc_mu_w, bf ? tp.Wmub : nullptr, H2},
+                      tp.mu_raw, d.L, p->fc_mu_b, false, id, B, st));
+  ARCVAE_TRY(gemm_any(precision, 0, 1, B, H2, H2, Mat{tp.u, bf ? tp.ub : nullptr, H2},
+                      Mat{p->fc_logvar_hidden_w, bf ? tp.Wlhb : nullptr, H2}, tp.lvh, H2, p->fc_logvar_hidden_b, false, id, B, st));
+  ARCVAE_TRY(tanh_inplace(tp.lvh, (long)B * H2, bf ? tp.lvhb : nullptr, st));
+  ARCVAE_TRY(gemm_any(precision, 0, 1, B, d.L, H2, Mat{tp.lvh, bf ? tp.lvhb : nullptr, H2},
+                      Mat{p->fc_logvar_w, bf ? tp.Wlvb : nullptr, H2}, tp.lv_raw, d.L, p->fc_logvar_b, false, id, B, st));
   ARCVAE_TRY(head_bound(tp.mu_raw, tp.lv_raw, (long)B * d.L, tp.mu, tp.logvar, st));
   if (mu) ARCVAE_CUDA(cudaMemcpyAsync(mu, tp.mu, (size_t)B * d.L * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (logvar) ARCVAE_CUDA(cudaMemcpyAsync(logvar, tp.logvar, (size_t)B * d.L * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -151,24 +181,33 @@ static int head_forward(const arcvae_dims& d, const arcvae_encoder_params* p, co
 // leaves d h_T in sc.du[:, 0:H] (row pitch 2H)
 static int head_backward(const arcvae_dims& d, const arcvae_encoder_params* p, const arcvae_encoder_params* g,
                          const EncTape& tp, const EncScratch& sc, const float* cond, int B, const float* dmu,
-                         const float* dlogvar, cudaStream_t st) {
+                         const float* dlogvar, int precision, cudaStream_t st) {
   const int H = d.H, L = d.L, H2 = 2 * d.H;
   RowMap id{nullptr, 1};
-  ARCVAE_TRY(head_bound_bwd(tp.mu, tp.logvar, dmu, dlogvar, (long)B * L, sc.dmu_raw, sc.dlv_raw, st));
+  const bool bf = precision == ARCVAE_PREC_BF16;
+  auto M2 = [&](const float* f, const bf16* b, int ld) { return Mat{f, bf ? b : nullptr, ld}; };
+  ARCVAE_TRY(head_bound_bwd(tp.mu, tp.logvar, dmu, dlogvar, (long)B * L, sc.dmu_raw, sc.dlv_raw, bf ? sc.dmub : nullptr,
+                            bf ? sc.dlvb : nullptr, st));
   // fc_logvar: lv_raw = lvh @ Wlv^T + b
-  ARCVAE_TRY(gemm_f32(1, 0, L, H2, B, sc.dlv_raw, L, tp.lvh, H2, g->fc_logvar_w, H2, nullptr, true, id, pick_splitk(L, H2, B), st));
+  ARCVAE_TRY(gemm_any(precision, 1, 0, L, H2, B, M2(sc.dlv_raw, sc.dlvb, L), M2(tp.lvh, tp.lvhb, H2), g->fc_logvar_w, H2, nullptr,
+                      true, id, B, st));
   ARCVAE_TRY(colsum(sc.dlv_raw, B, L, L, g->fc_logvar_b, st));
-  ARCVAE_TRY(gemm_f32(0, 0, B, H2, L, sc.dlv_raw, L, p->fc_logvar_w, H2, sc.dlvh, H2, nullptr, false, id, 1, st));
-  ARCVAE_TRY(tanh_bwd_inplace(sc.dlvh, tp.lvh, (long)B * H2, st));
+  ARCVAE_TRY(gemm_any(precision, 0, 0, B, H2, L, M2(sc.dlv_raw, sc.dlvb, L), M2(p->fc_logvar_w, tp.Wlvb, H2), sc.dlvh, H2, nullptr,
+                      false, id, B, st));
+  ARCVAE_TRY(tanh_bwd_inplace(sc.dlvh, tp.lvh, (long)B * H2, bf ? sc.dlvhb : nullptr, st));
   // fc_logvar_hidden: pre = u @ Wlh^T + b
-  ARCVAE_TRY(gemm_f32(1, 0, H2, H2, B, sc.dlvh, H2, tp.u, H2, g->fc_logvar_hidden_w, H2, nullptr, true, id, pick_splitk(H2, H2, B), st));
+  ARCVAE_TRY(gemm_any(precision, 1, 0, H2, H2, B, M2(sc.dlvh, sc.dlvhb, H2), M2(tp.u, tp.ub, H2), g->fc_logvar_hidden_w, H2, nullptr,
+                      true, id, B, st));
   ARCVAE_TRY(colsum(sc.dlvh, B, H2, H2, g->fc_logvar_hidden_b, st));
-  ARCVAE_TRY(gemm_f32(0, 0, B, H2, H2, sc.dlvh, H2, p->fc_logvar_hidden_w, H2, sc.du, H2, nullptr, false, id, 1, st));
+  ARCVAE_TRY(gemm_any(precision, 0, 0, B, H2, H2, M2(sc.dlvh, sc.dlvhb, H2), M2(p->fc_logvar_hidden_w, tp.Wlhb, H2), sc.du, H2,
+                      nullptr, false, id, B, st));
   // fc_mu
-  ARCVAE_TRY(gemm_f32(1, 0, L, H2, B, sc.dmu_raw, L, tp.u, H2, g->fc_mu_w, H2, nullptr, true, id, pick_splitk(L, H2, B), st));
+  ARCVAE_TRY(gemm_any(precision, 1, 0, L, H2, B, M2(sc.dmu_raw, sc.dmub, L), M2(tp.u, tp.ub, H2), g->fc_mu_w, H2, nullptr, true, id,
+                      B, st));
   ARCVAE_TRY(colsum(sc.dmu_raw, B, L, L, g->fc_mu_b, st));
-  ARCVAE_TRY(gemm_f32(0, 0, B, H2, L, sc.dmu_raw, L, p->fc_mu_w, H2, sc.du, H2, nullptr, true, id, 1, st));
-  // condition_fc: cproj = cond @ Wc^T + bc ; d cproj = du[:, H:2H]
+  ARCVAE_TRY(gemm_any(precision, 0, 0, B, H2, L, M2(sc.dmu_raw, sc.dmub, L), M2(p->fc_mu_w, tp.Wmub, H2), sc.du, H2, nullptr, true,
+                      id, B, st));
+  // condition_fc: cproj = cond @ Wc^T + bc ; d cproj = du[:, H:2H]   (N = num_conditions: not tensor-core shaped)
   ARCVAE_TRY(gemm_f32(1, 0, H, d.C, B, sc.du + H, H2, cond, d.C, g->condition_fc_w, d.C, nullptr, true, id, pick_splitk(H, d.C, B), st));
   ARCVAE_TRY(colsum(sc.du + H, B, H, H2, g->condition_fc_b, st));
   return 0;
@@ -248,7 +287,7 @@ extern "C" int arcvae_encoder_forward(const arcvae_dims* d, const arcvae_encoder
       ARCVAE_TRY(lstm_cluster_forward(B, T, H, tp.Whb[l], tp.xT, l == 0 ? tp.table0b : nullptr, l == 0 ? nullptr : tp.Pb,
                                       tp.hb[l], tp.gates_b[l], tp.c[l], l == d->NL - 1 ? tp.h_last : nullptr, tp.err, st));
     }
-    return head_forward(*d, p, tp, tp.h_last, cond, B, mu, logvar, st);
+    return head_forward(*d, p, tp, tp.h_last, cond, B, mu, logvar, precision, st);
   }
 
   for (int l = 0; l < d->NL; l++) {
@@ -274,7 +313,7 @@ extern "C" int arcvae_encoder_forward(const arcvae_dims* d, const arcvae_encoder
     }
   }
   const float* h_last = tp.h[d->NL - 1] + (long)(T - 1) * B * H;
-  return head_forward(*d, p, tp, h_last, cond, B, mu, logvar, st);
+  return head_forward(*d, p, tp, h_last, cond, B, mu, logvar, precision, st);
 }
 
 extern "C" int arcvae_encoder_backward(const arcvae_dims* d, const arcvae_encoder_params* p, const float* cond, int B,
@@ -297,7 +336,7 @@ extern "C" int arcvae_encoder_backward(const arcvae_dims* d, const arcvae_encode
   RowMap id{nullptr, 1};
   const bool bf = path != PATH_STEP_F32;
 
-  ARCVAE_TRY(head_backward(*d, p, g, tp, sc, cond, B, dmu, dlogvar, st));
+  ARCVAE_TRY(head_backward(*d, p, g, tp, sc, cond, B, dmu, dlogvar, precision, st));
 
   if (path == PATH_CLUSTER) {
     for (int l = d->NL - 1; l >= 0; l--) {

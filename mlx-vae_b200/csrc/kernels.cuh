@@ -34,16 +34,17 @@ int dec_cell0_bwd(const float* table, const float* wc, const int32_t* tok, const
                   long R, const float* dh, float* dG, cudaStream_t st);
 
 // head: u[b,0:H] = h_last[b,:]; u[b,H:2H] = cond[b,:] @ Wc^T + bc
+// the bf16 pointers (nullable) receive a rounded copy of the fp32 result: operands of the tensor-core head products
 int head_build_u(const float* h_last, const float* cond, const float* Wc, const float* bc, int B, int H, int C,
-                 float* u, cudaStream_t st);
-int tanh_inplace(float* x, long n, cudaStream_t st);
+                 float* u, __nv_bfloat16* ub, cudaStream_t st);
+int tanh_inplace(float* x, long n, __nv_bfloat16* xb, cudaStream_t st);
 // d <- d * (1 - y*y)
-int tanh_bwd_inplace(float* d, const float* y, long n, cudaStream_t st);
+int tanh_bwd_inplace(float* d, const float* y, long n, __nv_bfloat16* db, cudaStream_t st);
 // mu = 2*tanh(mu_raw/2); logvar = tanh(lv_raw/2) - 1   (encoder.py:126,:130)
 int head_bound(const float* mu_raw, const float* lv_raw, long n, float* mu, float* logvar, cudaStream_t st);
 // dmu_raw = dmu*(1-(mu/2)^2); dlv_raw = dlogvar*0.5*(1-(logvar+1)^2)
 int head_bound_bwd(const float* mu, const float* logvar, const float* dmu, const float* dlogvar, long n,
-                   float* dmu_raw, float* dlv_raw, cudaStream_t st);
+                   float* dmu_raw, float* dlv_raw, __nv_bfloat16* dmu_b, __nv_bfloat16* dlv_b, cudaStream_t st);
 
 // out[n] += sum_r X[r*ldx + n]
 int colsum(const float* X, long R, int N, int ldx, float* out, cudaStream_t st);

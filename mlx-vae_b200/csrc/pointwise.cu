@@ -306,7 +306,7 @@ int dec_cell0_bwd(const float* table, const float* wc, const int32_t* tok, const
 // ------------------------------------------------------------------------------------------------
 __global__ void k_head_build_u(const float* __restrict__ h_last, const float* __restrict__ cond,
                                const float* __restrict__ Wc, const float* __restrict__ bc, int B, int H, int C,
-                               float* __restrict__ u) {
+                               float* __restrict__ u, __nv_bfloat16* __restrict__ ub) {
   long total = (long)B * 2 * H;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
     long b = idx / (2 * H);
@@ -320,32 +320,38 @@ __global__ void k_head_build_u(const float* __restrict__ h_last, const float* __
       for (int c = 0; c < C; c++) v = fmaf(cond[b * C + c], Wc[(long)jj * C + c], v);
     }
     u[idx] = v;
+    if (ub != nullptr) ub[idx] = __float2bfloat16(v);
   }
 }
 int head_build_u(const float* h_last, const float* cond, const float* Wc, const float* bc, int B, int H, int C,
-                 float* u, cudaStream_t st) {
-  k_head_build_u<<<grid_for((long)B * 2 * H, 256), 256, 0, st>>>(h_last, cond, Wc, bc, B, H, C, u);
+                 float* u, __nv_bfloat16* ub, cudaStream_t st) {
+  k_head_build_u<<<grid_for((long)B * 2 * H, 256), 256, 0, st>>>(h_last, cond, Wc, bc, B, H, C, u, ub);
   ARCVAE_LAUNCHED();
   return 0;
 }
 
-__global__ void k_tanh_inplace(float* x, long n) {
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
-    x[i] = tanhf_(x[i]);
+__global__ void k_tanh_inplace(float* x, long n, __nv_bfloat16* __restrict__ xb) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float y = tanhf_(x[i]);
+    x[i] = y;
+    if (xb != nullptr) xb[i] = __float2bfloat16(y);
+  }
 }
-int tanh_inplace(float* x, long n, cudaStream_t st) {
-  k_tanh_inplace<<<grid_for(n, 256), 256, 0, st>>>(x, n);
+int tanh_inplace(float* x, long n, __nv_bfloat16* xb, cudaStream_t st) {
+  k_tanh_inplace<<<grid_for(n, 256), 256, 0, st>>>(x, n, xb);
   ARCVAE_LAUNCHED();
   return 0;
 }
-__global__ void k_tanh_bwd_inplace(float* d, const float* __restrict__ y, long n) {
+__global__ void k_tanh_bwd_inplace(float* d, const float* __restrict__ y, long n, __nv_bfloat16* __restrict__ db) {
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     float yy = y[i];
-    d[i] = d[i] * (1.f - yy * yy);
+    const float v = d[i] * (1.f - yy * yy);
+    d[i] = v;
+    if (db != nullptr) db[i] = __float2bfloat16(v);
   }
 }
-int tanh_bwd_inplace(float* d, const float* y, long n, cudaStream_t st) {
-  k_tanh_bwd_inplace<<<grid_for(n, 256), 256, 0, st>>>(d, y, n);
+int tanh_bwd_inplace(float* d, const float* y, long n, __nv_bfloat16* db, cudaStream_t st) {
+  k_tanh_bwd_inplace<<<grid_for(n, 256), 256, 0, st>>>(d, y, n, db);
   ARCVAE_LAUNCHED();
   return 0;
 }
@@ -364,17 +370,21 @@ int head_bound(const float* mu_raw, const float* lv_raw, long n, float* mu, floa
 }
 __global__ void k_head_bound_bwd(const float* __restrict__ mu, const float* __restrict__ logvar,
                                  const float* __restrict__ dmu, const float* __restrict__ dlogvar, long n,
-                                 float* __restrict__ dmu_raw, float* __restrict__ dlv_raw) {
+                                 float* __restrict__ dmu_raw, float* __restrict__ dlv_raw,
+                                 __nv_bfloat16* __restrict__ dmu_b, __nv_bfloat16* __restrict__ dlv_b) {
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     float tm = mu[i] * 0.5f;          // tanh(mu_raw/2)
     float tl = logvar[i] + 1.0f;      // tanh(lv_raw/2)
-    dmu_raw[i] = dmu[i] * (1.f - tm * tm);            // d/dx 2*tanh(x/2) = 1 - tanh^2
-    dlv_raw[i] = dlogvar[i] * 0.5f * (1.f - tl * tl);  // d/dx tanh(x/2) = (1 - tanh^2)/2
+    const float a = dmu[i] * (1.f - tm * tm);            // d/dx 2*tanh(x/2) = 1 - tanh^2
+    const float b = dlogvar[i] * 0.5f * (1.f - tl * tl);  // d/dx tanh(x/2) = (1 - tanh^2)/2
+    dmu_raw[i] = a;
+    dlv_raw[i] = b;
+    if (dmu_b != nullptr) { dmu_b[i] = __float2bfloat16(a); dlv_b[i] = __float2bfloat16(b); }
   }
 }
 int head_bound_bwd(const float* mu, const float* logvar, const float* dmu, const float* dlogvar, long n,
-                   float* dmu_raw, float* dlv_raw, cudaStream_t st) {
-  k_head_bound_bwd<<<grid_for(n, 256), 256, 0, st>>>(mu, logvar, dmu, dlogvar, n, dmu_raw, dlv_raw);
+                   float* dmu_raw, float* dlv_raw, __nv_bfloat16* dmu_b, __nv_bfloat16* dlv_b, cudaStream_t st) {
+  k_head_bound_bwd<<<grid_for(n, 256), 256, 0, st>>>(mu, logvar, dmu, dlogvar, n, dmu_raw, dlv_raw, dmu_b, dlv_b);
   ARCVAE_LAUNCHED();
   return 0;
 }
@@ -416,8 +426,52 @@ static int colsum_t(const TIn* X, long R, int N, int ldx, float* out, cudaStream
   ARCVAE_LAUNCHED();
   return 0;
 }
+// bf16, 8 columns (16 bytes) per thread: a warp reads 512 contiguous bytes of a row; block = 32 x 8 covers 256 columns
+__global__ void k_colsum_bf16_v8(const __nv_bfloat16* __restrict__ X, long R, int N, int ldx, float* __restrict__ out,
+                                 long rows_per_block) {
+  __shared__ float red[8][32][9];
+  const int n = (blockIdx.x * 32 + threadIdx.x) * 8;
+  const long r0 = blockIdx.y * rows_per_block;
+  long r1 = r0 + rows_per_block;
+  if (r1 > R) r1 = R;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (n < N) {
+    for (long r = r0 + threadIdx.y; r < r1; r += 8) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(X + r * ldx + n));
+      const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const float2 t = __bfloat1622float2(pv[k]);
+        acc[2 * k] += t.x; acc[2 * k + 1] += t.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; k++) red[threadIdx.y][threadIdx.x][k] = acc[k];
+  __syncthreads();
+  if (threadIdx.y == 0 && n < N) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; i++) s += red[i][threadIdx.x][k];
+      atomicAdd(out + n + k, s);
+    }
+  }
+}
 int colsum(const float* X, long R, int N, int ldx, float* out, cudaStream_t st) { return colsum_t(X, R, N, ldx, out, st); }
 int colsum_bf16(const __nv_bfloat16* X, long R, int N, int ldx, float* out, cudaStream_t st) {
+  if (R <= 0 || N <= 0) return 0;
+  if ((N % 8) == 0 && (ldx % 8) == 0 && ((reinterpret_cast<uintptr_t>(X) & 15) == 0)) {
+    const int gx = cdiv(N, 256);
+    long want = (148L * 8 + gx - 1) / gx;
+    long rpb = (R + want - 1) / want;
+    if (rpb < 64) rpb = 64;
+    TimeScope ts(TIME_POINTWISE, st);
+    k_colsum_bf16_v8<<<dim3(gx, cdiv(R, rpb)), dim3(32, 8), 0, st>>>(X, R, N, ldx, out, rpb);
+    ARCVAE_LAUNCHED();
+    return 0;
+  }
   return colsum_t(X, R, N, ldx, out, st);
 }
 
