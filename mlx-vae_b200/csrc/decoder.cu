@@ -169,7 +169,7 @@ static int dec_stack_forward(const arcvae_dims& d, const arcvae_decoder_params* 
                              int precision, bool fused, cudaStream_t st) {
   const int H = d.H, H3 = 3 * d.H;
   const bool bf = precision == ARCVAE_PREC_BF16;
-  ARCVAE_TRY(dec_cell0_fwd(pr.table, pr.wc, in_tok, cond, B, d.C, H, nrows, rm, fused ? nullptr : hd[0],
+  ARCVAE_TRY(dec_cell0_fwd(pr.table, pr.wc, in_tok, cond, B, d.C, H, d.V, nrows, rm, fused ? nullptr : hd[0],
                            bf ? hdb[0] : nullptr, fused ? gates_b[0] : nullptr, st));
   for (int l = 1; l < d.NL; l++) {
     if (fused) {

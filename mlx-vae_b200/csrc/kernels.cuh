@@ -23,7 +23,8 @@ int lstm_cell_bwd(float* gates, const float* c, const float* c_prev, const float
 // decoder cells (zero state: c = i*g, h = o*tanh(c); forget gate unused) on COMPACT gate layout [.., 3H] = (i,g,o)
 // layer 0: a = table[tok[r]] + cond[r % B] @ wc^T   (table [V,3H], wc [3H,C]); rows r = rm(i), i < R
 // gates_b (optional, fused bf16 path): activated (i,g,o) in the tile-permuted layout of the fused GEMM epilogues
-int dec_cell0_fwd(const float* table, const float* wc, const int32_t* tok, const float* cond, int B, int C, int H,
+// V = rows of the table (sizes the shared-memory copy of the large-batch bf16 kernel)
+int dec_cell0_fwd(const float* table, const float* wc, const int32_t* tok, const float* cond, int B, int C, int H, int V,
                   int R, RowMap rm, float* h, __nv_bfloat16* hb, __nv_bfloat16* gates_b, cudaStream_t st);
 // layers >= 1: G [.,3H] pre-activation -> activated in place; h out
 int dec_cell_fwd(float* G, float* h, __nv_bfloat16* hb, int H, int R, RowMap rm, cudaStream_t st);

@@ -210,11 +210,113 @@ __global__ void k_dec_cell0_fwd_v8(const float* __restrict__ table, const float*
     }
   }
 }
-int dec_cell0_fwd(const float* table, const float* wc, const int32_t* tok, const float* cond, int B, int C, int H,
+// bf16 path, large row counts: the [V,3H] table is staged ONCE per CTA in shared memory as bf16 (V=80, H=256: 120 KB), so
+// the gather never leaves the SM (the global-memory version pulls 1.5-3 KB per row through L2: 1.6 GB at B*T = 524288)
+// and the kernel is bound by its h / gate-tape writes.  One persistent CTA per SM, 1024 threads, thread = 8 hidden units.
+__global__ void __launch_bounds__(1024, 1)
+k_dec_cell0_fwd_smem(const float* __restrict__ table, const float* __restrict__ wc, const int32_t* __restrict__ tok,
+                     const float* __restrict__ cond, int B, int C, int H, int V, int R, RowMap rm,
+                     __nv_bfloat16* __restrict__ hb, __nv_bfloat16* __restrict__ gates_b) {
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  __nv_bfloat16* tb = reinterpret_cast<__nv_bfloat16*>(sm_raw);                       // [V,3H]
+  float* wcs = reinterpret_cast<float*>(sm_raw + (size_t)V * 3 * H * sizeof(__nv_bfloat16));   // [3H,C]
+  const int H3 = 3 * H;
+  for (int i = threadIdx.x; i < V * H3 / 2; i += blockDim.x) {
+    const float2 v = reinterpret_cast<const float2*>(table)[i];
+    reinterpret_cast<__nv_bfloat162*>(tb)[i] = __floats2bfloat162_rn(v.x, v.y);
+  }
+  for (int i = threadIdx.x; i < H3 * C; i += blockDim.x) wcs[i] = wc[i];
+  __syncthreads();
+  const int cpr = H >> 3;
+  const long total = (long)R * cpr;
+  const long stride = (long)gridDim.x * blockDim.x;
+  // the token (and through it the table row) is a dependent load: fetch the NEXT item's token and condition while this
+  // item's cell math runs, otherwise every item pays a full L2 round trip with nothing to overlap it
+  long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  long r_n = 0;
+  int tok_n = 0, j_n = 0;
+  float c0_n = 0.f;
+  if (idx < total) {
+    const int i = (int)(idx / cpr);
+    j_n = (int)(idx - (long)i * cpr) << 3;
+    r_n = rm(i);
+    tok_n = __ldg(tok + r_n);
+    c0_n = __ldg(cond + (r_n % B) * C);
+  }
+  for (; idx < total; idx += stride) {
+    const long r = r_n;
+    const int j = j_n;
+    const int tokv = tok_n;
+    const float cond0 = c0_n;
+    if (idx + stride < total) {
+      const long nidx = idx + stride;
+      const int i = (int)(nidx / cpr);
+      j_n = (int)(nidx - (long)i * cpr) << 3;
+      r_n = rm(i);
+      tok_n = __ldg(tok + r_n);
+      c0_n = __ldg(cond + (r_n % B) * C);
+    }
+    const __nv_bfloat16* trow = tb + (long)tokv * H3 + j;
+    float a[3][8];
+#pragma unroll
+    for (int g = 0; g < 3; g++) {
+      const uint4 v = *reinterpret_cast<const uint4*>(trow + g * H);
+      const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const float2 t = __bfloat1622float2(pv[k]);
+        a[g][2 * k] = t.x; a[g][2 * k + 1] = t.y;
+      }
+    }
+    const float* crow = cond + (r % B) * C;
+    for (int c = 0; c < C; c++) {
+      const float cv = (c == 0) ? cond0 : __ldg(crow + c);
+#pragma unroll
+      for (int g = 0; g < 3; g++)
+#pragma unroll
+        for (int k = 0; k < 8; k++) a[g][k] = fmaf(cv, wcs[(g * H + j + k) * C + c], a[g][k]);
+    }
+    float hv[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      a[0][k] = sigmoid_approx_(a[0][k]); a[1][k] = tanh_approx_(a[1][k]); a[2][k] = sigmoid_approx_(a[2][k]);
+      hv[k] = a[2][k] * tanh_approx_(a[0][k] * a[1][k]);
+    }
+    if (gates_b != nullptr) {
+      __nv_bfloat16* gb = gates_b + r * 3L * H + (j >> 6) * 192 + (j & 63);
+#pragma unroll
+      for (int g = 0; g < 3; g++) {
+        uint4 o;
+        __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int k = 0; k < 4; k++) po[k] = __floats2bfloat162_rn(a[g][2 * k], a[g][2 * k + 1]);
+        *reinterpret_cast<uint4*>(gb + g * 64) = o;
+      }
+    }
+    uint4 o;
+    __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int k = 0; k < 4; k++) po[k] = __floats2bfloat162_rn(hv[2 * k], hv[2 * k + 1]);
+    *reinterpret_cast<uint4*>(hb + r * H + j) = o;
+  }
+}
+
+int dec_cell0_fwd(const float* table, const float* wc, const int32_t* tok, const float* cond, int B, int C, int H, int V,
                   int R, RowMap rm, float* h, __nv_bfloat16* hb, __nv_bfloat16* gates_b, cudaStream_t st) {
   if (R <= 0) return 0;
   TimeScope ts(TIME_POINTWISE, st);
   ARCVAE_REQUIRE(gates_b == nullptr || (h == nullptr && (H % 64) == 0), "layer-0 gate tape: fused bf16 path, H % 64 == 0");
+  const size_t smem_tab = (size_t)V * 3 * H * sizeof(__nv_bfloat16) + (size_t)3 * H * C * sizeof(float);
+  if (h == nullptr && hb != nullptr && (H & 7) == 0 && V > 0 && smem_tab <= 200 * 1024 && (long)R * H >= (1L << 24)) {
+    static bool attr = false;
+    if (!attr) {
+      ARCVAE_CUDA(cudaFuncSetAttribute(k_dec_cell0_fwd_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr = true;
+    }
+    k_dec_cell0_fwd_smem<<<148, 1024, smem_tab, st>>>(table, wc, tok, cond, B, C, H, V, R, rm, hb, gates_b);
+    ARCVAE_LAUNCHED();
+    return 0;
+  }
   if ((H & 7) == 0) {
     const long total = (long)R * (H >> 3);
     if (h == nullptr) k_dec_cell0_fwd_v8<true><<<grid_for(total, 256, 16), 256, 0, st>>>(table, wc, tok, cond, B, C, H, R, rm, h, hb, gates_b);
