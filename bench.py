@@ -304,30 +304,57 @@ def main():
         return
     pk = peaks()
     per_step = {k: v[0] / nprof for k, v in cats.items() if v[1] > 0}
-    dom = max(per_step, key=per_step.get) if per_step else None
-    roof = None
-    if dom in ("gemm_f32", "gemm_tc", "recurrence"):
-        # GEMM-shaped work of the step: algorithmic FLOP of the reference formulation over the device
-        # time of every launch of the GEMM-shaped categories
-        t_ms = sum(per_step.get(k, 0.0) for k in ("gemm_f32", "gemm_tc", "recurrence"))
-        flop = FLOP_STEP_PER_MOLECULE * B
+    launches_cat = {k: v[1] / nprof for k, v in cats.items() if v[1] > 0}
+    H, NL = DIMS["hidden_dim"], DIMS["num_layers"]
+    R = B * T
+    # ncu --set full DRAM bytes per launch of the same command (profiles/ncu_traffic.json, written from the committed
+    # capture by profiles/scripts/summarize_ncu.py --traffic); only valid for the default B x T
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath) and B == B_PER_GPU:
+        traffic = json.load(open(tpath))
+    roofs = {}
+    if "recurrence" in per_step:
+        # encoder LSTM recurrence: per layer T steps of [B,H]x[H,4H] forward and [B,4H]x[4H,H] backward
+        flop = NL * 2 * (2.0 * 4 * H * H) * R
+        t_ms = per_step["recurrence"]
+        n = max(1.0, launches_cat["recurrence"])
         ach = flop / (t_ms * 1e-3) / 1e12
-        roof = {"kernel": "+".join(k for k in ("gemm_f32", "gemm_tc", "recurrence") if k in per_step),
-                "bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": ach / pk["bf16_sustained"], "traffic": None, "peak_source": pk["src"] + " (sustained bf16)",
-                "ms_per_step": t_ms, "share_of_step": t_ms / ms,
-                "note": "algorithmic FLOP = 3 x 341,836,288 per molecule (SURVEY 8d); timed in a separate instrumented pass"}
-    elif dom == "loss":
+        tape = NL * R * (4 * H * 2 * 2 + H * 4 * 2 + H * 2 + 4 * H * 2 + H * 4)   # gates w+r, c w+r, h w, dA w, P/dX r (bf16/fp32 mix)
+        roofs["recurrence"] = {"kernel": "lstm_fwd2_kernel+lstm_bwd2_kernel", "bound": "tensor", "achieved": ach,
+                               "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"],
+                               "traffic": traffic.get("recurrence"), "peak_source": pk["src"] + " (sustained bf16)",
+                               "launches_per_step": n, "avg_launch_ms": t_ms / n, "ms_per_step": t_ms,
+                               "share_of_step": t_ms / ms, "algorithmic_flop_per_launch": flop / n,
+                               "hbm_tape_gbs": tape / (t_ms * 1e-3) / 1e9, "hbm_tape_frac": tape / (t_ms * 1e-3) / 1e9 / pk["hbm"],
+                               "note": "latency-bound by construction (T sequential cluster exchanges); algorithmic FLOP = "
+                                       "2*4H*H per row-step, forward + d h backward, both layers"}
+    if "gemm_tc" in per_step:
+        # time-parallel contractions: everything of SURVEY 8d's 3 x 341.8 MFLOP/molecule that is not the recurrence
+        flop = FLOP_STEP_PER_MOLECULE * B - NL * 2 * (2.0 * 4 * H * H) * R
+        t_ms = per_step["gemm_tc"] + per_step.get("gemm_f32", 0.0)
+        n = max(1.0, launches_cat.get("gemm_tc", 0) + launches_cat.get("gemm_f32", 0))
+        ach = flop / (t_ms * 1e-3) / 1e12
+        roofs["gemm"] = {"kernel": "gemm_tc_kernel(+gemm_f32_kernel)", "bound": "tensor", "achieved": ach,
+                         "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"],
+                         "traffic": traffic.get("gemm_tc"), "peak_source": pk["src"] + " (sustained bf16)",
+                         "launches_per_step": n, "avg_launch_ms": t_ms / n, "ms_per_step": t_ms, "share_of_step": t_ms / ms,
+                         "note": "K <= 768 projections are HBM-bound on B200 (2K FLOP per 2-byte output element, machine "
+                                 "balance ~210 FLOP/B); algorithmic FLOP of the reference formulation"}
+    if "loss" in per_step:
         t_ms = per_step["loss"]
         by = LOSS_BYTES_PER_MOLECULE * B
         ach = by / (t_ms * 1e-3) / 1e9
-        roof = {"kernel": "k_loss_fused", "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
-                "frac": ach / pk["hbm"], "traffic": None, "peak_source": pk["src"]}
-    loss_ms = per_step.get("loss")
-    extra = {"per_category_ms": per_step}
-    if loss_ms:
-        extra["loss_kernel_gbs"] = LOSS_BYTES_PER_MOLECULE * B / (loss_ms * 1e-3) / 1e9
-        extra["loss_kernel_frac_of_hbm_peak"] = extra["loss_kernel_gbs"] / pk["hbm"]
+        roofs["loss"] = {"kernel": "k_loss_fused", "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
+                         "frac": ach / pk["hbm"], "traffic": traffic.get("loss"), "peak_source": pk["src"],
+                         "avg_launch_ms": t_ms, "share_of_step": t_ms / ms,
+                         "note": "algorithmic bytes = logits read + dlogits write + tokens (SURVEY 8d: 82.4 KB/molecule)"}
+    dom = max(("recurrence", "gemm"), key=lambda k: roofs[k]["ms_per_step"] if k in roofs else -1.0) if roofs else None
+    roof = roofs.get(dom)
+    extra = {"per_category_ms": per_step, "rooflines": roofs}
+    if "loss" in roofs:
+        extra["loss_kernel_gbs"] = roofs["loss"]["achieved"]
+        extra["loss_kernel_frac_of_hbm_peak"] = roofs["loss"]["frac"]
 
     cpu = None
     if not args.no_cpu:

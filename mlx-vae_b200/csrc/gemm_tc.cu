@@ -44,6 +44,7 @@ struct TcParams {
   const float* table; const float* wc; const int32_t* tok; const float* cond;
   int Bt, Cc, Hh;
   int use_scratch;   // per-warp transposition scratch present after the TcShared block
+  int scr_pitch;     // bytes per scratch row
 };
 
 __device__ __forceinline__ float tanh_fast_(float x) { return tanh_approx_(x); }
@@ -84,16 +85,16 @@ __device__ __forceinline__ void dec_cell_grads_fast(float i_, float g_, float o_
 // ---- per-warp transposition scratch: the epilogue thread owns a ROW (tcgen05.ld 32x32b), but a warp-wide 16-byte
 // access to 32 different rows costs 32 L1 wavefronts instead of 4.  Row segments are therefore staged in shared
 // memory (pitch 400 B: conflict-free for the thread=row side) and moved to / from HBM with lanes running along the row.
-constexpr int TC_SCR_PITCH = 400;
-constexpr int TC_SCR_BYTES = 32 * TC_SCR_PITCH;   // per epilogue warp
-__device__ __forceinline__ void scr_store_rows(const uint8_t* scr, uint8_t* gbase, long gstride, int nb, int nrows, int lane) {
+constexpr int TC_SCR_PITCH_BWD = 400;             // 384-byte rows (a 64-unit block of i|g|o) + 16
+constexpr int TC_SCR_PITCH_FWD = 272;             // 256-byte rows + 16
+__device__ __forceinline__ void scr_store_rows(const uint8_t* scr, int TC_SCR_PITCH, uint8_t* gbase, long gstride, int nb, int nrows, int lane) {
   const int cpr = nb >> 4, total = nrows * cpr;
   for (int idx = lane; idx < total; idx += 32) {
     const int r = idx / cpr, c = idx - r * cpr;
     *reinterpret_cast<uint4*>(gbase + r * gstride + c * 16) = *reinterpret_cast<const uint4*>(scr + r * TC_SCR_PITCH + c * 16);
   }
 }
-__device__ __forceinline__ void scr_load_rows(uint8_t* scr, const uint8_t* gbase, long gstride, int nb, int nrows, int lane) {
+__device__ __forceinline__ void scr_load_rows(uint8_t* scr, int TC_SCR_PITCH, const uint8_t* gbase, long gstride, int nb, int nrows, int lane) {
   // batches of 8 independent 16-byte loads per lane, so one HBM/L2 latency covers 4 KB per warp instead of 512 B
   const int cpr = nb >> 4, total = nrows * cpr;
   for (int base = 0; base < total; base += 8 * 32) {
@@ -157,7 +158,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t b_bytes = (uint32_t)p.BN * TC_BK * 2;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   TcShared* sh = reinterpret_cast<TcShared*>(smem + (size_t)p.stages * stage_bytes);
-  uint8_t* scratch = reinterpret_cast<uint8_t*>(sh) + 256;      // TC_EPI_WARPS x TC_SCR_BYTES when p.use_scratch
+  uint8_t* scratch = reinterpret_cast<uint8_t*>(sh) + 256;      // TC_EPI_WARPS x 32 rows x p.scr_pitch when p.use_scratch
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -282,7 +283,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
       const bool atomic = p.splitk > 1;
       const bool add_bias = p.bias != nullptr && (tile / (p.mt * p.nt)) == 0;
-      uint8_t* scr = scratch + (warp - 2) * TC_SCR_BYTES;
+      const int TC_SCR_PITCH = p.scr_pitch;
+      uint8_t* scr = scratch + (warp - 2) * 32 * TC_SCR_PITCH;
       uint8_t* srow = scr + lane * TC_SCR_PITCH;
       const int rows_here = min(32, p.M - (m0 + q * 32));          // rows of this warp's quarter inside the matrix
       const long grow0 = rows_here > 0 ? p.rm(m0 + q * 32) : 0;     // first global row (a row tile never straddles timesteps)
@@ -313,11 +315,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         __syncwarp();
         if (rows_here > 0) {
-          scr_store_rows(scr, reinterpret_cast<uint8_t*>(p.hb_out + grow0 * H + ni * 64 + half * 32), (long)H * 2, 64, rows_here, lane);
+          scr_store_rows(scr, TC_SCR_PITCH, reinterpret_cast<uint8_t*>(p.hb_out + grow0 * H + ni * 64 + half * 32), (long)H * 2, 64, rows_here, lane);
           bf16* gb = p.gates_b + grow0 * 3L * H + n0 + half * 32;
-          scr_store_rows(scr + 64, reinterpret_cast<uint8_t*>(gb), 3L * H * 2, 64, rows_here, lane);
-          scr_store_rows(scr + 128, reinterpret_cast<uint8_t*>(gb + 64), 3L * H * 2, 64, rows_here, lane);
-          scr_store_rows(scr + 192, reinterpret_cast<uint8_t*>(gb + 128), 3L * H * 2, 64, rows_here, lane);
+          scr_store_rows(scr + 64, TC_SCR_PITCH, reinterpret_cast<uint8_t*>(gb), 3L * H * 2, 64, rows_here, lane);
+          scr_store_rows(scr + 128, TC_SCR_PITCH, reinterpret_cast<uint8_t*>(gb + 64), 3L * H * 2, 64, rows_here, lane);
+          scr_store_rows(scr + 192, TC_SCR_PITCH, reinterpret_cast<uint8_t*>(gb + 128), 3L * H * 2, 64, rows_here, lane);
         }
         __syncwarp();
       } else if (p.epi == TC_EPI_DEC_CELL_BWD) {
@@ -332,7 +334,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int nblk = n0 + blk * 64;                       // first unit of the block
           const long goff = grow0 * 3L * H + (long)(nblk / 64) * 192;
           if (rows_here > 0)
-            scr_load_rows(scr, reinterpret_cast<const uint8_t*>(p.gates_b + goff), 3L * H * 2, 384, rows_here, lane);
+            scr_load_rows(scr, TC_SCR_PITCH, reinterpret_cast<const uint8_t*>(p.gates_b + goff), 3L * H * 2, 384, rows_here, lane);
           __syncwarp();
 #pragma unroll 1
           for (int cc = 0; cc < 4; cc++) {
@@ -352,7 +354,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           __syncwarp();
           if (rows_here > 0)
-            scr_store_rows(scr, reinterpret_cast<uint8_t*>(p.dg_out + goff), 3L * H * 2, 384, rows_here, lane);
+            scr_store_rows(scr, TC_SCR_PITCH, reinterpret_cast<uint8_t*>(p.dg_out + goff), 3L * H * 2, 384, rows_here, lane);
           __syncwarp();
         }
       } else if (p.epi == TC_EPI_DEC_CELL0_BWD) {
@@ -428,7 +430,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         __syncwarp();
         if (rows_here > 0)
-          scr_store_rows(scr, reinterpret_cast<uint8_t*>(p.Cb + grow0 * p.ldcb + n0 + ch_lo * 16), (long)p.ldcb * 2, nb, rows_here, lane);
+          scr_store_rows(scr, TC_SCR_PITCH, reinterpret_cast<uint8_t*>(p.Cb + grow0 * p.ldcb + n0 + ch_lo * 16), (long)p.ldcb * 2, nb, rows_here, lane);
         __syncwarp();
       } else {
       for (int c0 = ch_lo * 16; c0 < ch_hi * 16; c0 += 16) {
@@ -607,7 +609,8 @@ int gemm_tc(const TcGemm& g, cudaStream_t st) {
                           (p.BN % 32) == 0 && p.BN * 2 / 2 <= 384 && (g.ldcb % 8) == 0 &&
                           ((reinterpret_cast<uintptr_t>(g.Cb) & 15) == 0);
   p.use_scratch = (g.epi == TC_EPI_DEC_CELL_FWD || g.epi == TC_EPI_DEC_CELL_BWD || plain_fast) ? 1 : 0;
-  const size_t scratch_bytes = p.use_scratch ? (size_t)TC_EPI_WARPS * TC_SCR_BYTES : 0;
+  p.scr_pitch = g.epi == TC_EPI_DEC_CELL_BWD ? TC_SCR_PITCH_BWD : TC_SCR_PITCH_FWD;
+  const size_t scratch_bytes = p.use_scratch ? (size_t)TC_EPI_WARPS * 32 * p.scr_pitch : 0;
   int stages = (int)((225 * 1024 - 2048 - scratch_bytes) / stage_bytes);
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   if (stages > p.kb_per + 1 && p.kb_per + 1 >= 2) stages = p.kb_per + 1 > 2 ? p.kb_per + 1 : 2;

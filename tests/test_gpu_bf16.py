@@ -115,3 +115,41 @@ def test_bf16_full_size_step_runs_and_is_sane(M):
     for i in (1, 2, 3):
         a, b = res["fp32"][i], res["bf16"][i]
         assert float((a - b).abs().max()) / float(a.abs().max()) < TOL_GRAD, i
+
+
+def test_scaled_config_bf16_matches_fp32(M):
+    """BASELINE configs[3] dims (hidden 1024, latent 256, 3 layers): hidden_dim != 256 takes the per-step tensor-core
+    recurrence (the cluster kernel is specialised for 256) and the multi-launch sampler; same tolerances."""
+    cfg = O.Config(80, 128, 1024, 256, 1, 3)
+    B, T = 128, 6
+    x, cond, eps, tf_mask = O.synthetic_batch(B, T, cfg, seed=3, tf_ratio=0.7)
+    p = O.init_params(cfg, seed=4, dtype=torch.float32)
+    p["decoder"] = O.tree_map(lambda t: t * 2.0, p["decoder"])
+    kw = model_kwargs(cfg)
+    hyper = dict(beta=0.05, lambda_prop=0.1, lambda_collapse=0.001, free_bits=1.0, lambda_mi=0.01, target_mi=4.85)
+    mask = np.ones(T, dtype=bool)
+    out = {}
+    for prec in ("fp32", "bf16"):
+        enc = M.MLXEncoder(**kw, precision=prec).load_parameters(p["encoder"])
+        dec = M.MLXAutoregressiveDecoder(**kw, precision=prec).load_parameters(p["decoder"])
+        d, (ge, gd) = M.loss_and_grad(enc, dec, None, cuda(x), cuda(cond), eps=cuda(eps), tf_mask=mask, **hyper)
+        out[prec] = (d, {k: v.clone() for k, v in O.tree_flatten({"e": ge, "d": gd}).items()})
+        if prec == "bf16":
+            s = M.MLXAutoregressiveDecoderSampling(**kw, decoder=dec)
+            toks = s.generate_with_temperature(None, cuda(cond), max_length=5, early_stopping=False)
+            assert tuple(toks.shape) == (B, 5)
+    d32, g32 = out["fp32"]; d16, g16 = out["bf16"]
+    for k in ("total_loss", "recon_loss", "kl_loss"):
+        assert abs(float(d32[k]) - float(d16[k])) / abs(float(d32[k])) < TOL_FWD, k
+    assert rel_err(d16["mu"].cpu(), d32["mu"].cpu()) < TOL_FWD
+    worst, name = 0.0, None
+    for n in g32:
+        s = float(g32[n].abs().max())
+        if s == 0.0:
+            assert float(g16[n].abs().max()) == 0.0
+            continue
+        e = float((g32[n] - g16[n]).abs().max()) / s
+        if e > worst:
+            worst, name = e, n
+    print("scaled config: worst gradient rel err", worst, name)
+    assert worst < TOL_GRAD, (worst, name)
