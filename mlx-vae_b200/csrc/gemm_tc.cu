@@ -87,15 +87,33 @@ __device__ __forceinline__ void dec_cell_grads_fast(float i_, float g_, float o_
 // memory (pitch 400 B: conflict-free for the thread=row side) and moved to / from HBM with lanes running along the row.
 constexpr int TC_SCR_PITCH_BWD = 400;             // 384-byte rows (a 64-unit block of i|g|o) + 16
 constexpr int TC_SCR_PITCH_FWD = 272;             // 256-byte rows + 16
-__device__ __forceinline__ void scr_store_rows(const uint8_t* scr, int TC_SCR_PITCH, uint8_t* gbase, long gstride, int nb, int nrows, int lane) {
-  const int cpr = nb >> 4, total = nrows * cpr;
+template <int CPR>   // 16-byte chunks per row segment (compile-time: the index split is a shift / constant division)
+__device__ __forceinline__ void scr_store_rows_t(const uint8_t* scr, int pitch, uint8_t* gbase, long gstride, int nrows, int lane) {
+  const int total = nrows * CPR;
+#pragma unroll 4
   for (int idx = lane; idx < total; idx += 32) {
-    const int r = idx / cpr, c = idx - r * cpr;
-    *reinterpret_cast<uint4*>(gbase + r * gstride + c * 16) = *reinterpret_cast<const uint4*>(scr + r * TC_SCR_PITCH + c * 16);
+    const int r = idx / CPR, c = idx - r * CPR;
+    *reinterpret_cast<uint4*>(gbase + r * gstride + c * 16) = *reinterpret_cast<const uint4*>(scr + r * pitch + c * 16);
   }
 }
-__device__ __forceinline__ void scr_load_rows(uint8_t* scr, int TC_SCR_PITCH, const uint8_t* gbase, long gstride, int nb, int nrows, int lane) {
-  // batches of 8 independent 16-byte loads per lane, so one HBM/L2 latency covers 4 KB per warp instead of 512 B
+__device__ __forceinline__ void scr_store_rows(const uint8_t* scr, int pitch, uint8_t* gbase, long gstride, int nb, int nrows, int lane) {
+  switch (nb >> 4) {
+    case 4: scr_store_rows_t<4>(scr, pitch, gbase, gstride, nrows, lane); break;
+    case 8: scr_store_rows_t<8>(scr, pitch, gbase, gstride, nrows, lane); break;
+    case 16: scr_store_rows_t<16>(scr, pitch, gbase, gstride, nrows, lane); break;
+    case 24: scr_store_rows_t<24>(scr, pitch, gbase, gstride, nrows, lane); break;
+    default: {
+      const int cpr = nb >> 4, total = nrows * cpr;
+      for (int idx = lane; idx < total; idx += 32) {
+        const int r = idx / cpr, c = idx - r * cpr;
+        *reinterpret_cast<uint4*>(gbase + r * gstride + c * 16) = *reinterpret_cast<const uint4*>(scr + r * pitch + c * 16);
+      }
+    }
+  }
+}
+// 384-byte row segments (24 chunks): batches of 8 independent 16-byte loads per lane, so one HBM/L2 latency covers 4 KB
+// per warp instead of 512 B
+__device__ __forceinline__ void scr_load_rows(uint8_t* scr, int pitch, const uint8_t* gbase, long gstride, int nb, int nrows, int lane) {
   const int cpr = nb >> 4, total = nrows * cpr;
   for (int base = 0; base < total; base += 8 * 32) {
     uint4 v[8];
@@ -103,7 +121,7 @@ __device__ __forceinline__ void scr_load_rows(uint8_t* scr, int TC_SCR_PITCH, co
     for (int u = 0; u < 8; u++) {
       const int idx = base + u * 32 + lane;
       if (idx < total) {
-        const int r = idx / cpr, c = idx - r * cpr;
+        const int r = (cpr == 24) ? idx / 24 : idx / cpr, c = idx - r * cpr;
         v[u] = __ldg(reinterpret_cast<const uint4*>(gbase + r * gstride + c * 16));
       }
     }
@@ -111,8 +129,8 @@ __device__ __forceinline__ void scr_load_rows(uint8_t* scr, int TC_SCR_PITCH, co
     for (int u = 0; u < 8; u++) {
       const int idx = base + u * 32 + lane;
       if (idx < total) {
-        const int r = idx / cpr, c = idx - r * cpr;
-        *reinterpret_cast<uint4*>(scr + r * TC_SCR_PITCH + c * 16) = v[u];
+        const int r = (cpr == 24) ? idx / 24 : idx / cpr, c = idx - r * cpr;
+        *reinterpret_cast<uint4*>(scr + r * pitch + c * 16) = v[u];
       }
     }
   }
@@ -299,13 +317,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc::tmem_ld16(taddr + c0, ri);
           tc::tmem_ld16(taddr + 64 + c0, rg);
           tc::tmem_ld16(taddr + 128 + c0, ro);
+          float4 bv[3][4];                                      // bias of the 16 units x (i,g,o), in flight with the TMEM loads
+#pragma unroll
+          for (int g3 = 0; g3 < 3; g3++)
+#pragma unroll
+            for (int k4 = 0; k4 < 4; k4++) bv[g3][k4] = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + g3 * 64 + c0) + k4);
           tc::tmem_ld_wait();
+          const float* bfi = reinterpret_cast<const float*>(bv[0]);
+          const float* bfg = reinterpret_cast<const float*>(bv[1]);
+          const float* bfo = reinterpret_cast<const float*>(bv[2]);
           float gi[16], gg[16], go[16], hv[16];
 #pragma unroll
           for (int k = 0; k < 16; k++) {
-            gi[k] = sigmoid_fast_(__uint_as_float(ri[k]) + __ldg(p.bias + n0 + c0 + k));
-            gg[k] = tanh_fast_(__uint_as_float(rg[k]) + __ldg(p.bias + n0 + 64 + c0 + k));
-            go[k] = sigmoid_fast_(__uint_as_float(ro[k]) + __ldg(p.bias + n0 + 128 + c0 + k));
+            gi[k] = sigmoid_fast_(__uint_as_float(ri[k]) + bfi[k]);
+            gg[k] = tanh_fast_(__uint_as_float(rg[k]) + bfg[k]);
+            go[k] = sigmoid_fast_(__uint_as_float(ro[k]) + bfo[k]);
             hv[k] = go[k] * tanh_fast_(gi[k] * gg[k]);
           }
           scr_put16(srow + cc * 32, hv);
@@ -419,13 +445,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int ch = ch_lo; ch < ch_hi; ch++) {
           uint32_t r[16];
           tc::tmem_ld16(taddr + ch * 16, r);
+          float4 bv[4];                                         // bias vector of the chunk, in flight with the TMEM load
+#pragma unroll
+          for (int k4 = 0; k4 < 4; k4++)
+            bv[k4] = add_bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + ch * 16) + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
           tc::tmem_ld_wait();
+          const float* bf = reinterpret_cast<const float*>(bv);
           float v[16];
 #pragma unroll
-          for (int j = 0; j < 16; j++) {
-            v[j] = __uint_as_float(r[j]);
-            if (add_bias) v[j] += __ldg(p.bias + n0 + ch * 16 + j);
-          }
+          for (int j = 0; j < 16; j++) v[j] = __uint_as_float(r[j]) + bf[j];
           scr_put16(srow + (ch - ch_lo) * 32, v);
         }
         __syncwarp();
@@ -607,7 +635,8 @@ int gemm_tc(const TcGemm& g, cudaStream_t st) {
   // transposition scratch for the fused cells and for plain bf16-only outputs of full, aligned tiles
   const bool plain_fast = g.epi == TC_EPI_PLAIN && g.Cb != nullptr && g.C == nullptr && p.splitk == 1 && (g.N % p.BN) == 0 &&
                           (p.BN % 32) == 0 && p.BN * 2 / 2 <= 384 && (g.ldcb % 8) == 0 &&
-                          ((reinterpret_cast<uintptr_t>(g.Cb) & 15) == 0);
+                          ((reinterpret_cast<uintptr_t>(g.Cb) & 15) == 0) &&
+                          (g.bias == nullptr || (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0);
   p.use_scratch = (g.epi == TC_EPI_DEC_CELL_FWD || g.epi == TC_EPI_DEC_CELL_BWD || plain_fast) ? 1 : 0;
   p.scr_pitch = g.epi == TC_EPI_DEC_CELL_BWD ? TC_SCR_PITCH_BWD : TC_SCR_PITCH_FWD;
   const size_t scratch_bytes = p.use_scratch ? (size_t)TC_EPI_WARPS * 32 * p.scr_pitch : 0;
