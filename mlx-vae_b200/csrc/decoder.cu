@@ -125,6 +125,7 @@ struct DecScratch {
   __nv_bfloat16* dGb2;                // fused path: second [R,3H] buffer (ping-pong between layers, layer-0 dG)
   __nv_bfloat16* onehot;              // fused path: [R,SCATTER_NW] one-hot of the fed tokens + cond hi/lo columns
   float* dtable_tmp;                  // fused path: [SCATTER_NW,3H] table gradient in tile-permuted column order
+  float* segtmp;                      // fused path: [3H,SCATTER_NW] one-hot segment of the weight-gradient GEMM (bias row sums)
 };
 
 static size_t dec_scratch_layout(const arcvae_dims& d, int B, int T, void* base, size_t cap, DecScratch* s) {
@@ -146,6 +147,7 @@ static size_t dec_scratch_layout(const arcvae_dims& d, int B, int T, void* base,
   ss.dGb2 = a.take<__nv_bfloat16>(R * 3 * d.H);
   ss.onehot = a.take<__nv_bfloat16>(R * SCATTER_NW);
   ss.dtable_tmp = a.take<float>((size_t)SCATTER_NW * 3 * d.H);
+  ss.segtmp = a.take<float>((size_t)3 * d.H * SCATTER_NW);
   if (s) *s = ss;
   return align_up(a.off, 256);
 }
@@ -312,6 +314,10 @@ extern "C" int arcvae_decoder_backward(const arcvae_dims* d, const arcvae_decode
       q.epi = TC_EPI_DEC_CELL_BWD; q.gates_b = tp.gates_b[layer_below];      // layer 0 keeps its gate tape as well
       return gemm_tc(q, st);
     };
+    // one-hot of the fed tokens (+ cond hi/lo columns): operand of the layer-0 table scatter and, through its row sums,
+    // of the bias gradients of the upper layers
+    ARCVAE_TRY(build_onehot(tp.in_tok, R, V, cond, B, C, sc.onehot, st));
+    const bool fuse_dw = H <= 256;
     __nv_bfloat16* cur = sc.dGb;
     __nv_bfloat16* nxt = sc.dGb2;
     ARCVAE_TRY(fused_gemm(sc.dlb, V, tp.prep.Woutb, top, cur));   // d h_top = dlogits @ Wout, then cell backward of `top`
@@ -319,9 +325,28 @@ extern "C" int arcvae_decoder_backward(const arcvae_dims* d, const arcvae_decode
       // cur = dG_l (tile-permuted compact layout)
       ARCVAE_CUDA(cudaMemsetAsync(sc.dWxc[l], 0, (size_t)H3 * H * sizeof(float), st));
       ARCVAE_CUDA(cudaMemsetAsync(sc.dbc[l], 0, (size_t)H3 * sizeof(float), st));
-      ARCVAE_TRY(gemm_any(precision, 1, 0, H3, H, (int)R, Mat{nullptr, cur, H3}, Mat{nullptr, tp.hdb[l - 1], H}, sc.dWxc[l], H,
-                          nullptr, true, id, R, st));
-      ARCVAE_TRY(colsum_bf16(cur, R, H3, H3, sc.dbc[l], st));
+      if (fuse_dw) {
+        // dWx_l = dG^T h_{l-1} and the bias gradient (row sums of dG^T onehot) in ONE pass over dG
+        ARCVAE_CUDA(cudaMemsetAsync(sc.segtmp, 0, (size_t)H3 * SCATTER_NW * sizeof(float), st));
+        TcGemm q{};
+        q.M = H3; q.N = H; q.K = (int)R;
+        q.A = cur; q.lda = H3; q.a_mn = true; q.b_mn = true;
+        q.accumulate = true; q.rm = id; q.a_rows_total = R;
+        q.nseg = 2;
+        q.seg[0] = {tp.hdb[l - 1], H, H, 0, sc.dWxc[l], H};
+        q.seg[1] = {sc.onehot, SCATTER_NW, SCATTER_NW, 0, sc.segtmp, SCATTER_NW};
+        const long tiles = (long)cdiv(H3, 128) * 2;
+        long sk = (2 * 148) / tiles;
+        const long maxs = cdiv(R, 64) / 8;
+        if (sk > maxs) sk = maxs;
+        q.splitk = sk < 1 ? 1 : (int)sk;
+        ARCVAE_TRY(gemm_tc(q, st));
+        ARCVAE_TRY(rowsum_add(sc.segtmp, H3, SCATTER_NW, V, sc.dbc[l], st));
+      } else {
+        ARCVAE_TRY(gemm_any(precision, 1, 0, H3, H, (int)R, Mat{nullptr, cur, H3}, Mat{nullptr, tp.hdb[l - 1], H}, sc.dWxc[l], H,
+                            nullptr, true, id, R, st));
+        ARCVAE_TRY(colsum_bf16(cur, R, H3, H3, sc.dbc[l], st));
+      }
       ARCVAE_TRY(fused_gemm(cur, H3, tp.prep.Wxpb[l], l - 1, nxt));
       ARCVAE_TRY(expand_perm_gates_add(sc.dWxc[l], H, H, g->Wx[l], st));
       ARCVAE_TRY(expand_perm_gates_add(sc.dbc[l], H, 1, g->bias[l], st));
@@ -332,7 +357,7 @@ extern "C" int arcvae_decoder_backward(const arcvae_dims* d, const arcvae_decode
     ARCVAE_CUDA(cudaMemsetAsync(sc.dWxc[0], 0, (size_t)H3 * (E + C) * sizeof(float), st));
     ARCVAE_CUDA(cudaMemsetAsync(sc.dbc[0], 0, (size_t)H3 * sizeof(float), st));
     ARCVAE_REQUIRE(scatter_onehot_supported(H3, V, C), "fused decoder backward: V + 2C <= 128");
-    ARCVAE_TRY(scatter_rows_onehot_tc(cur, tp.in_tok, R, H3, V, sc.onehot, sc.dtable, cond, B, C, sc.dwc, H, sc.dtable_tmp, st));
+    ARCVAE_TRY(scatter_rows_onehot_tc(cur, nullptr, R, H3, V, sc.onehot, sc.dtable, cond, B, C, sc.dwc, H, sc.dtable_tmp, st));
   } else {
   ARCVAE_TRY(gemm_any(precision, 0, 0, (int)R, H, V, Mat{dlogits_tm, bf ? sc.dlb : nullptr, V},
                       Mat{p->fc_out_w, tp.prep.Woutb, H}, dh, H, nullptr, false, id, R, st));

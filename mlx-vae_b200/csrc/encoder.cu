@@ -120,6 +120,7 @@ struct EncScratch {
   bf16* dlvhb;      // [B,2H]
   bf16* onehot;     // [T*B,SCATTER_NW] one-hot tokens (tensor-core scatter)
   void* xch;        // cluster backward: exchange buffers of the partial d h
+  float* segtmp;    // [4H,SCATTER_NW] one-hot segment of the fused weight-gradient GEMM (dtable0^T / bias row sums)
 };
 
 static size_t enc_scratch_layout(const arcvae_dims& d, int B, int T, int path, void* base, size_t cap, EncScratch* s) {
@@ -142,6 +143,7 @@ static size_t enc_scratch_layout(const arcvae_dims& d, int B, int T, int path, v
   }
   ss.onehot = (path != PATH_STEP_F32) ? a.take<bf16>((size_t)T * B * SCATTER_NW) : nullptr;
   ss.xch = (path != PATH_STEP_F32) ? a.take<char>(lstm_cluster_xch_bytes(B)) : nullptr;
+  ss.segtmp = (path != PATH_STEP_F32) ? a.take<float>((size_t)4 * d.H * SCATTER_NW) : nullptr;
   if (s) *s = ss;
   return align_up(a.off, 256);
 }
@@ -339,6 +341,11 @@ extern "C" int arcvae_encoder_backward(const arcvae_dims* d, const arcvae_encode
   ARCVAE_TRY(head_backward(*d, p, g, tp, sc, cond, B, dmu, dlogvar, precision, st));
 
   if (path == PATH_CLUSTER) {
+    // weight gradients that share dA^T (dWh, dWx, bias / table scatter) run as ONE multi-segment GEMM per layer: dA is read
+    // from HBM once.  The one-hot token operand serves the layer-0 table scatter AND, through its row sums, the bias
+    // gradients of the upper layers.
+    const bool fuse_dw = scatter_onehot_supported(G4, d->V, 0) && (H % 64) == 0 && H <= 256;
+    if (fuse_dw) ARCVAE_TRY(build_onehot(tp.xT, R, d->V, nullptr, B, 0, sc.onehot, st));
     for (int l = d->NL - 1; l >= 0; l--) {
       const bool top = (l == d->NL - 1);
       if (std::getenv("ARCVAE_BWD_ALLGATHER") == nullptr) {
@@ -348,6 +355,33 @@ extern "C" int arcvae_encoder_backward(const arcvae_dims* d, const arcvae_encode
         ARCVAE_TRY(transpose_to_bf16(p->Wh[l], G4, H, tp.WhTb[l], st));          // WhT[h][gate] = Wh[gate][h]
         ARCVAE_TRY(lstm_cluster_backward(B, T, H, tp.WhTb[l], tp.gates_b[l], tp.c[l], top ? nullptr : sc.dX,
                                          top ? sc.du : nullptr, H2, sc.dAb, tp.err, st));
+      }
+      if (fuse_dw) {
+        ARCVAE_CUDA(cudaMemsetAsync(sc.segtmp, 0, (size_t)G4 * SCATTER_NW * sizeof(float), st));
+        TcGemm q{};
+        q.M = G4; q.N = H; q.K = (int)R;
+        q.A = sc.dAb; q.lda = G4; q.a_mn = true; q.b_mn = true;
+        q.accumulate = true; q.rm = id; q.a_rows_total = R;
+        int ns = 0;
+        q.seg[ns++] = {tp.hb[l], H, H, B, g->Wh[l], H};                       // dWh += dA[t]^T h[t-1]  (rows shifted by B)
+        if (l > 0) q.seg[ns++] = {tp.hb[l - 1], H, H, 0, g->Wx[l], H};         // dWx += dA^T h_{l-1}
+        q.seg[ns++] = {sc.onehot, SCATTER_NW, SCATTER_NW, 0, sc.segtmp, SCATTER_NW};   // dA^T onehot(x)
+        q.nseg = ns;
+        const long tiles = (long)cdiv(G4, 128) * ns;
+        long sk = (2 * 148) / tiles;
+        const long maxs = cdiv(R, 64) / 8;
+        if (sk > maxs) sk = maxs;
+        q.splitk = sk < 1 ? 1 : (int)sk;
+        ARCVAE_TRY(gemm_tc(q, st));
+        if (l > 0) {
+          ARCVAE_TRY(rowsum_add(sc.segtmp, G4, SCATTER_NW, d->V, g->bias[l], st));
+          ARCVAE_TRY(gemm_any(precision, 0, 0, (int)R, H, G4, Mat{nullptr, sc.dAb, G4}, Mat{nullptr, tp.Wxb[l], H}, sc.dX, H,
+                              nullptr, false, id, R, st));
+        } else {
+          ARCVAE_TRY(transpose_f32(sc.segtmp, G4, SCATTER_NW, SCATTER_NW, sc.dtable0, st));   // -> [SCATTER_NW, 4H]
+          ARCVAE_TRY(layer0_input_backward(*d, p, g, sc, st));
+        }
+        continue;
       }
       // dWh += dA[1:]^T @ h[:-1]
       if (T > 1) {

@@ -43,6 +43,9 @@ struct TcParams {
   bf16* gates_b; bf16* hb_out; bf16* dg_out;
   const float* table; const float* wc; const int32_t* tok; const float* cond;
   int Bt, Cc, Hh;
+  // multi-segment B (weight gradients that share the A operand): column tile ni multiplies A with its own B matrix
+  // (rows shifted by seg_shift[ni]; negative TMA coordinates zero-fill) into its own C
+  int nseg; int segN[3]; int seg_shift[3]; float* segC[3]; int seg_ldc[3];
   int use_scratch;   // per-warp transposition scratch present after the TcShared block
   int scr_pitch;     // bytes per scratch row
 };
@@ -168,7 +171,8 @@ struct __align__(8) TcShared {
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-B alignment for SWIZZLE_128B tiles
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -223,7 +227,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc::mbar_wait(&sh->empty[stage], phase ^ 1);
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
           uint8_t* sb = sa + a_bytes;
-          tc::mbar_expect_tx(&sh->full[stage], stage_bytes);
+          const int bn_t = p.nseg > 1 ? p.segN[ni] : p.BN;
+          tc::mbar_expect_tx(&sh->full[stage], a_bytes + (uint32_t)bn_t * TC_BK * 2);
           const int k0 = kb * TC_BK;
           if (!p.a_mn) {
             tc::tma_load_2d(sa, &tmA, &sh->full[stage], k0, gm0);                       // box {64 k, 128 rows}
@@ -233,6 +238,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (!p.b_mn) {
             tc::tma_load_2d(sb, &tmB, &sh->full[stage], k0, n0);                        // box {64 k, BN rows}
+          } else if (p.nseg > 1) {
+            const CUtensorMap* tb = ni == 0 ? &tmB : (ni == 1 ? &tmB1 : &tmB2);
+            for (int j = 0; j < bn_t / 64; j++)
+              tc::tma_load_2d(sb + j * 8192, tb, &sh->full[stage], j * 64, k0 - p.seg_shift[ni]);
           } else {
             for (int j = 0; j < p.BN / 64; j++)
               tc::tma_load_2d(sb + j * 8192, &tmB, &sh->full[stage], n0 + j * 64, k0);  // box {64 n, 64 k}
@@ -243,11 +252,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    const uint32_t idesc = tc::make_idesc_bf16(TC_BM, p.BN, p.a_mn != 0, p.b_mn != 0);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+      const uint32_t idesc = tc::make_idesc_bf16(TC_BM, p.nseg > 1 ? p.segN[tile % p.nt] : p.BN, p.a_mn != 0, p.b_mn != 0);
       const int ks = tile / (p.mt * p.nt);
       const int kb0 = ks * p.kb_per;
       const int kb1 = min(kblocks, kb0 + p.kb_per);
@@ -283,14 +292,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================================================== epilogue (warps 2..9 -> TMEM lane quarters 2,3,0,1,2,3,0,1)
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;          // which half of the tile's 16-column chunks this warp handles
-    const int nchunks = p.BN >> 4;
-    const int ch_lo = half == 0 ? 0 : (nchunks + 1) >> 1;
-    const int ch_hi = half == 0 ? (nchunks + 1) >> 1 : nchunks;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
       const int ni = tile % p.nt;
       const int mi = (tile / p.nt) % p.mt;
-      const int m0 = mi * TC_BM, n0 = ni * p.BN;
+      const bool mseg = p.nseg > 1;
+      const int nchunks = (mseg ? p.segN[ni] : p.BN) >> 4;
+      const int ch_lo = half == 0 ? 0 : (nchunks + 1) >> 1;
+      const int ch_hi = half == 0 ? (nchunks + 1) >> 1 : nchunks;
+      const int m0 = mi * TC_BM, n0 = mseg ? 0 : ni * p.BN;
+      float* const Ct = mseg ? p.segC[ni] : p.C;           // output of this column tile
+      const int ldct = mseg ? p.seg_ldc[ni] : p.ldc;
+      const int Nt = mseg ? p.segN[ni] : p.N;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       tc::mbar_wait(&sh->tmem_full[acc], acc_phase);
@@ -471,15 +484,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 16; j++) {
             v[j] = __uint_as_float(r[j]);
-            if (add_bias && nbase + j < p.N) v[j] += p.bias[nbase + j];
+            if (add_bias && nbase + j < Nt) v[j] += p.bias[nbase + j];
           }
-          if (p.C != nullptr) {
-            float* dst = p.C + grow * p.ldc + nbase;
+          if (Ct != nullptr) {
+            float* dst = Ct + grow * ldct + nbase;
             if (atomic) {
 #pragma unroll
               for (int j = 0; j < 16; j++)
-                if (nbase + j < p.N) atomicAdd(dst + j, v[j]);
-            } else if (nbase + 16 <= p.N && ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                if (nbase + j < Nt) atomicAdd(dst + j, v[j]);
+            } else if (nbase + 16 <= Nt && ((ldct & 3) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
               for (int j = 0; j < 16; j += 4) {
                 float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -492,12 +505,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             } else {
 #pragma unroll
               for (int j = 0; j < 16; j++)
-                if (nbase + j < p.N) dst[j] = p.accumulate ? dst[j] + v[j] : v[j];
+                if (nbase + j < Nt) dst[j] = p.accumulate ? dst[j] + v[j] : v[j];
             }
           }
           if (p.Cb != nullptr) {
             bf16* dstb = p.Cb + grow * p.ldcb + nbase;
-            if (nbase + 16 <= p.N && ((p.ldcb & 7) == 0) && ((reinterpret_cast<uintptr_t>(dstb) & 15) == 0)) {
+            if (nbase + 16 <= Nt && ((p.ldcb & 7) == 0) && ((reinterpret_cast<uintptr_t>(dstb) & 15) == 0)) {
               uint32_t pk[8];
 #pragma unroll
               for (int j = 0; j < 8; j++) {
@@ -509,7 +522,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             } else {
 #pragma unroll
               for (int j = 0; j < 16; j++)
-                if (nbase + j < p.N) dstb[j] = __float2bfloat16(v[j]);
+                if (nbase + j < Nt) dstb[j] = __float2bfloat16(v[j]);
             }
           }
         }
@@ -599,24 +612,37 @@ int pick_splitk_tc(int M, int N, int K);
 
 int gemm_tc(const TcGemm& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return 0;
-  ARCVAE_REQUIRE(g.C != nullptr || g.Cb != nullptr || g.epi != TC_EPI_PLAIN, "gemm_tc needs an output");
+  ARCVAE_REQUIRE(g.C != nullptr || g.Cb != nullptr || g.epi != TC_EPI_PLAIN || g.nseg > 1, "gemm_tc needs an output");
   ARCVAE_REQUIRE(!(g.a_mn && g.rm.tlist != nullptr), "row map needs a K-major A");
   ARCVAE_REQUIRE(g.rm.tlist == nullptr || (g.rm.Bt % TC_BM) == 0, "row-mapped tiles must not straddle timesteps");
   TcParams p;
   p.M = g.M; p.N = g.N; p.K = g.K;
-  p.BN = pick_bn(g.N);
+  p.nseg = g.nseg;
+  for (int i = 0; i < 3; i++) { p.segN[i] = 0; p.seg_shift[i] = 0; p.segC[i] = nullptr; p.seg_ldc[i] = 0; }
+  if (g.nseg > 1) {
+    ARCVAE_REQUIRE(g.nseg <= 3 && g.a_mn && g.b_mn && g.accumulate && g.epi == TC_EPI_PLAIN && g.Cb == nullptr &&
+                   g.rm.tlist == nullptr, "multi-segment GEMM: MN-major operands, fp32 accumulate outputs");
+    int nmax = 0;
+    for (int i = 0; i < g.nseg; i++) {
+      ARCVAE_REQUIRE(g.seg[i].N % 64 == 0 && g.seg[i].N <= 256 && g.seg[i].C != nullptr, "segment N: multiple of 64, <= 256");
+      p.segN[i] = g.seg[i].N; p.seg_shift[i] = g.seg[i].k_shift; p.segC[i] = g.seg[i].C; p.seg_ldc[i] = g.seg[i].ldc;
+      if (g.seg[i].N > nmax) nmax = g.seg[i].N;
+    }
+    p.N = nmax;
+  }
+  p.BN = pick_bn(p.N);
   if (g.b_mn) {
-    ARCVAE_REQUIRE(g.N % 64 == 0 || g.N < 64, "MN-major B needs N multiple of 64");
-    p.BN = g.N >= 256 ? 256 : ((g.N + 63) / 64) * 64;
+    ARCVAE_REQUIRE(p.N % 64 == 0 || p.N < 64, "MN-major B needs N multiple of 64");
+    p.BN = p.N >= 256 ? 256 : ((p.N + 63) / 64) * 64;
   }
   p.a_mn = g.a_mn ? 1 : 0; p.b_mn = g.b_mn ? 1 : 0;
-  p.mt = cdiv(g.M, TC_BM); p.nt = cdiv(g.N, p.BN);
+  p.mt = cdiv(g.M, TC_BM); p.nt = g.nseg > 1 ? g.nseg : cdiv(g.N, p.BN);
   const int kblocks = cdiv(g.K, TC_BK);
   int splitk = g.splitk < 1 ? 1 : g.splitk;
   if (splitk > kblocks) splitk = kblocks;
   p.kb_per = cdiv(kblocks, splitk);
   p.splitk = cdiv(kblocks, p.kb_per);
-  ARCVAE_REQUIRE(p.splitk == 1 || (g.accumulate && g.C != nullptr && g.Cb == nullptr),
+  ARCVAE_REQUIRE(p.splitk == 1 || (g.accumulate && (g.C != nullptr || g.nseg > 1) && g.Cb == nullptr),
                  "split-K accumulates with fp32 atomics into C");
   p.C = g.C; p.ldc = g.ldc; p.Cb = g.Cb; p.ldcb = g.ldcb; p.bias = g.bias; p.accumulate = g.accumulate ? 1 : 0;
   p.rm = g.rm;
@@ -633,7 +659,7 @@ int gemm_tc(const TcGemm& g, cudaStream_t st) {
   }
   const size_t stage_bytes = (size_t)TC_BM * TC_BK * 2 + (size_t)p.BN * TC_BK * 2;
   // transposition scratch for the fused cells and for plain bf16-only outputs of full, aligned tiles
-  const bool plain_fast = g.epi == TC_EPI_PLAIN && g.Cb != nullptr && g.C == nullptr && p.splitk == 1 && (g.N % p.BN) == 0 &&
+  const bool plain_fast = g.nseg <= 1 && g.epi == TC_EPI_PLAIN && g.Cb != nullptr && g.C == nullptr && p.splitk == 1 && (g.N % p.BN) == 0 &&
                           (p.BN % 32) == 0 && p.BN * 2 / 2 <= 384 && (g.ldcb % 8) == 0 &&
                           ((reinterpret_cast<uintptr_t>(g.Cb) & 15) == 0) &&
                           (g.bias == nullptr || (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0);
@@ -657,8 +683,17 @@ int gemm_tc(const TcGemm& g, cudaStream_t st) {
   } else {
     ARCVAE_TRY(make_tmap_bf16(&tmA, g.A, g.K, g.M, g.lda, 64, TC_BK));
   }
-  if (!g.b_mn) ARCVAE_TRY(make_tmap_bf16(&tmB, g.B, g.N, g.K, g.ldb, TC_BK, p.BN));
-  else ARCVAE_TRY(make_tmap_bf16(&tmB, g.B, g.K, g.N, g.ldb, 64, TC_BK));
+  CUtensorMap tmB1, tmB2;
+  if (g.nseg > 1) {
+    ARCVAE_TRY(make_tmap_bf16(&tmB, g.seg[0].B, g.K, g.seg[0].N, g.seg[0].ldb, 64, TC_BK));
+    ARCVAE_TRY(make_tmap_bf16(&tmB1, g.seg[1].B, g.K, g.seg[1].N, g.seg[1].ldb, 64, TC_BK));
+    if (g.nseg > 2) ARCVAE_TRY(make_tmap_bf16(&tmB2, g.seg[2].B, g.K, g.seg[2].N, g.seg[2].ldb, 64, TC_BK));
+    else tmB2 = tmB1;
+  } else {
+    if (!g.b_mn) ARCVAE_TRY(make_tmap_bf16(&tmB, g.B, g.N, g.K, g.ldb, TC_BK, p.BN));
+    else ARCVAE_TRY(make_tmap_bf16(&tmB, g.B, g.K, g.N, g.ldb, 64, TC_BK));
+    tmB1 = tmB; tmB2 = tmB;
+  }
 
   static int num_sms = 0;
   static bool attr = false;
@@ -673,7 +708,7 @@ int gemm_tc(const TcGemm& g, cudaStream_t st) {
   const int total = p.mt * p.nt * p.splitk;
   const int grid = total < num_sms ? total : num_sms;
   TimeScope ts(TIME_GEMM_TC, st);
-  gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, p);
+  gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmB1, tmB2, p);
   ARCVAE_LAUNCHED();
   return 0;
 }

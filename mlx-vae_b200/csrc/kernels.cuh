@@ -94,6 +94,11 @@ struct TcGemm {
   const int32_t* tok = nullptr;                 // CELL0_BWD: [rows] tokens fed
   const float* cond = nullptr;                  // CELL0_BWD: [Bt,C]
   int Bt = 1, Cc = 0, Hh = 0;
+  // multi-segment B (nseg = 2 or 3): weight gradients that share the MN-major A operand (dA^T) run as ONE GEMM whose
+  // column tile i multiplies with seg[i].B (row k of A pairs with row k - k_shift of B; rows before 0 count as zero)
+  // and accumulates into seg[i].C — A is read from HBM once.  Requires a_mn, b_mn, accumulate.
+  int nseg = 1;
+  struct Seg { const __nv_bfloat16* B; int ldb; int N; int k_shift; float* C; int ldc; } seg[3] = {};
 };
 enum { TC_EPI_PLAIN = 0, TC_EPI_DEC_CELL_FWD = 1, TC_EPI_DEC_CELL_BWD = 2, TC_EPI_DEC_CELL0_BWD = 3 };
 int gemm_tc(const TcGemm& g, cudaStream_t st);
@@ -115,6 +120,12 @@ int lstm_cluster_backward2(int B, int T, int H, const __nv_bfloat16* Whb, const 
                            const float* dh_ext, const float* dh_last, int dh_last_ld, __nv_bfloat16* dAb, void* xch,
                            int* err_flag, cudaStream_t st);
 int colsum_bf16(const __nv_bfloat16* X, long R, int N, int ldx, float* out, cudaStream_t st);
+// out[m] += sum_{v < V} X[m*ldx + v]   (bias gradient from the one-hot segment of a multi-segment weight-gradient GEMM)
+int rowsum_add(const float* X, int M, int ldx, int V, float* out, cudaStream_t st);
+// dst[c*R + r] = src[r*ldx + c], r < R, c < Cn   (small fp32 transposes of table gradients)
+int transpose_f32(const float* src, int R, int ldx, int Cn, float* dst, cudaStream_t st);
+// one-hot operand of the tensor-core token scatter (see scatter_rows_onehot_tc); cond == nullptr: tokens only
+int build_onehot(const int32_t* tok, long R, int V, const float* cond, int B, int C, __nv_bfloat16* onehot, cudaStream_t st);
 int scatter_rows_by_token_bf16(const __nv_bfloat16* X, const int32_t* tok, long R, int N, int V, float* dtable,
                                cudaStream_t st);
 

@@ -692,6 +692,43 @@ __global__ void k_unpermute_cols(const float* __restrict__ src, int rows, int H,
     dst[r * H3 + (rem / 64) * H + j * 64 + (rem % 64)] = src[i];
   }
 }
+__global__ void k_rowsum_add(const float* __restrict__ X, int M, int ldx, int V, float* __restrict__ out) {
+  const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (m >= M) return;
+  float s = 0.f;
+  for (int v = lane; v < V; v += 32) s += X[(long)m * ldx + v];
+  s = warp_sum(s);
+  if (lane == 0) out[m] += s;
+}
+int rowsum_add(const float* X, int M, int ldx, int V, float* out, cudaStream_t st) {
+  k_rowsum_add<<<cdiv(M, 8), 256, 0, st>>>(X, M, ldx, V, out);
+  ARCVAE_LAUNCHED();
+  return 0;
+}
+__global__ void k_transpose_f32(const float* __restrict__ src, int R, int ldx, int Cn, float* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    if (r < R && c < Cn) tile[i][threadIdx.x] = src[(long)r * ldx + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < Cn) dst[(long)c * R + r] = tile[threadIdx.x][i];
+  }
+}
+int transpose_f32(const float* src, int R, int ldx, int Cn, float* dst, cudaStream_t st) {
+  k_transpose_f32<<<dim3(cdiv(Cn, 32), cdiv(R, 32)), dim3(32, 8), 0, st>>>(src, R, ldx, Cn, dst);
+  ARCVAE_LAUNCHED();
+  return 0;
+}
+int build_onehot(const int32_t* tok, long R, int V, const float* cond, int B, int C, __nv_bfloat16* onehot, cudaStream_t st) {
+  TimeScope ts(TIME_POINTWISE, st);
+  k_build_onehot<<<grid_for(R * (SCATTER_NW >> 3), 256, 16), 256, 0, st>>>(tok, R, V, SCATTER_NW, cond, B, C, onehot);
+  ARCVAE_LAUNCHED();
+  return 0;
+}
 bool scatter_onehot_supported(int N, int V, int C) { return (N % 64) == 0 && V + 2 * C <= SCATTER_NW; }
 // perm_H > 0: X's columns are in tile-permuted compact order (N = 3*perm_H); dtable_ext comes out in natural order and
 // `tmp` ([SCATTER_NW, N] floats) receives the permuted product first
@@ -706,11 +743,7 @@ int scatter_rows_onehot_tc(const __nv_bfloat16* X, const int32_t* tok, long R, i
   if (R <= 0) return 0;
   ARCVAE_REQUIRE(scatter_onehot_supported(N, V, cond != nullptr ? C : 0), "one-hot scatter: N % 64 == 0, V + 2C <= 128");
   const int NW = SCATTER_NW;
-  {
-    TimeScope ts(TIME_POINTWISE, st);
-    k_build_onehot<<<grid_for(R * (NW >> 3), 256, 16), 256, 0, st>>>(tok, R, V, NW, cond, B, C, onehot);
-    ARCVAE_LAUNCHED();
-  }
+  if (tok != nullptr) ARCVAE_TRY(build_onehot(tok, R, V, cond, B, C, onehot, st));   // tok == nullptr: `onehot` is already built
   ARCVAE_CUDA(cudaMemsetAsync(dtable_ext, 0, (size_t)NW * N * sizeof(float), st));
   TcGemm g{};
   g.M = NW; g.N = N; g.K = (int)R;
