@@ -12,6 +12,7 @@
 // Operand layouts (both served by TMA, no transposes in HBM):
 //   K-major   A[m*lda + k], B[n*ldb + k]   forward projections, input gradients against pre-transposed weights
 //   MN-major  A[k*lda + m], B[k*ldb + n]   weight gradients dW = dA^T @ H with K = B*T (split-K + fp32 atomics)
+#include <cstdlib>
 #include <mutex>
 
 #include "kernels.cuh"
@@ -46,6 +47,7 @@ struct TcParams {
   // multi-segment B (weight gradients that share the A operand): column tile ni multiplies A with its own B matrix
   // (rows shifted by seg_shift[ni]; negative TMA coordinates zero-fill) into its own C
   int nseg; int segN[3]; int seg_shift[3]; float* segC[3]; int seg_ldc[3];
+  int bm2;           // 256-row tiles (two M=128 MMAs share every B tile): halves the B re-reads of the long-K weight-gradient shapes
   int use_scratch;   // per-warp transposition scratch present after the TcShared block
   int scr_pitch;     // bytes per scratch row
 };
@@ -176,7 +178,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-B alignment for SWIZZLE_128B tiles
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const uint32_t a_bytes = TC_BM * TC_BK * 2;              // 16 KB
+  const int BMt = p.bm2 ? 2 * TC_BM : TC_BM;
+  const uint32_t a_bytes = (uint32_t)BMt * TC_BK * 2;       // 16 KB (32 KB for 256-row tiles)
   const uint32_t b_bytes = (uint32_t)p.BN * TC_BK * 2;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   TcShared* sh = reinterpret_cast<TcShared*>(smem + (size_t)p.stages * stage_bytes);
@@ -188,6 +191,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int kblocks = (p.K + TC_BK - 1) / TC_BK;
   uint32_t tmem_cols = 32;
   while (tmem_cols < 2u * (uint32_t)p.BN) tmem_cols <<= 1;
+  if (p.bm2) tmem_cols = 512;                              // two 256-column accumulators, one per row half
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmA);
@@ -219,7 +223,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int ni = tile % p.nt;
         const int mi = (tile / p.nt) % p.mt;
         const int ks = tile / (p.mt * p.nt);
-        const int m0 = mi * TC_BM, n0 = ni * p.BN;
+        const int m0 = mi * BMt, n0 = ni * p.BN;
         const int gm0 = (int)p.rm(m0);
         const int kb0 = ks * p.kb_per;
         const int kb1 = min(kblocks, kb0 + p.kb_per);
@@ -233,8 +237,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (!p.a_mn) {
             tc::tma_load_2d(sa, &tmA, &sh->full[stage], k0, gm0);                       // box {64 k, 128 rows}
           } else {
-            tc::tma_load_2d(sa, &tmA, &sh->full[stage], m0, k0);                        // box {64 m, 64 k} x 2
-            tc::tma_load_2d(sa + 8192, &tmA, &sh->full[stage], m0 + 64, k0);
+            for (int j = 0; j < BMt / 64; j++)                                          // box {64 m, 64 k} x 2 (x 4)
+              tc::tma_load_2d(sa + j * 8192, &tmA, &sh->full[stage], m0 + j * 64, k0);
           }
           if (!p.b_mn) {
             tc::tma_load_2d(sb, &tmB, &sh->full[stage], k0, n0);                        // box {64 k, BN rows}
@@ -260,8 +264,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int ks = tile / (p.mt * p.nt);
       const int kb0 = ks * p.kb_per;
       const int kb1 = min(kblocks, kb0 + p.kb_per);
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
+      const int acc = p.bm2 ? 0 : (it & 1);                  // 256-row tiles own all of TMEM: no accumulator double-buffering
+      const uint32_t acc_phase = p.bm2 ? (it & 1) : ((it >> 1) & 1);
       if (lane == 0) tc::mbar_wait(&sh->tmem_empty[acc], acc_phase ^ 1);
       __syncwarp();
       tc::tc_fence_after();
@@ -280,6 +284,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint64_t db = p.b_mn ? tc::make_smem_desc(sb + k * 2048, 8192, 1024)
                                        : tc::make_smem_desc(sb + k * 32, 16, 1024);
             tc::mma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (p.bm2)                                            // rows 128..255 of the tile against the same B
+              tc::mma_bf16(tmem_base + 256, tc::make_smem_desc(sa + 16384 + k * 2048, 8192, 1024), db, idesc,
+                           (kb > kb0 || k > 0) ? 1u : 0u);
           }
           tc::mma_commit(&sh->empty[stage]);                  // smem stage free once these MMAs have read it
           if (kb == kb1 - 1) tc::mma_commit(&sh->tmem_full[acc]);
@@ -300,18 +307,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int nchunks = (mseg ? p.segN[ni] : p.BN) >> 4;
       const int ch_lo = half == 0 ? 0 : (nchunks + 1) >> 1;
       const int ch_hi = half == 0 ? (nchunks + 1) >> 1 : nchunks;
-      const int m0 = mi * TC_BM, n0 = mseg ? 0 : ni * p.BN;
+      const int n0 = mseg ? 0 : ni * p.BN;
       float* const Ct = mseg ? p.segC[ni] : p.C;           // output of this column tile
       const int ldct = mseg ? p.seg_ldc[ni] : p.ldc;
       const int Nt = mseg ? p.segN[ni] : p.N;
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
+      const int acc = p.bm2 ? 0 : (it & 1);
+      const uint32_t acc_phase = p.bm2 ? (it & 1) : ((it >> 1) & 1);
       tc::mbar_wait(&sh->tmem_full[acc], acc_phase);
       tc::tc_fence_after();
+      for (int sub = 0; sub < (p.bm2 ? 2 : 1); sub++) {      // row halves of a 256-row tile (plain epilogue only)
+      const int m0 = mi * BMt + sub * TC_BM;
       const int row_local = m0 + q * 32 + lane;
       const bool row_ok = row_local < p.M;
       const long grow = row_ok ? p.rm(row_local) : 0;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.bm2 ? sub * 256 : acc * p.BN);
       const bool atomic = p.splitk > 1;
       const bool add_bias = p.bias != nullptr && (tile / (p.mt * p.nt)) == 0;
       const int TC_SCR_PITCH = p.scr_pitch;
@@ -528,6 +537,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       }
+      }   // sub
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&sh->tmem_empty[acc]);
@@ -636,9 +646,20 @@ int gemm_tc(const TcGemm& g, cudaStream_t st) {
     p.BN = p.N >= 256 ? 256 : ((p.N + 63) / 64) * 64;
   }
   p.a_mn = g.a_mn ? 1 : 0; p.b_mn = g.b_mn ? 1 : 0;
-  p.mt = cdiv(g.M, TC_BM); p.nt = g.nseg > 1 ? g.nseg : cdiv(g.N, p.BN);
+  // long-K weight-gradient shapes (both operands MN-major, fp32 atomics): 256-row tiles
+  p.bm2 = (g.a_mn && g.b_mn && g.epi == TC_EPI_PLAIN && g.Cb == nullptr && g.accumulate && (g.M % 256) == 0 &&
+           g.K >= 64 * 64 && std::getenv("ARCVAE_NO_BM256") == nullptr) ? 1 : 0;
+  p.mt = cdiv(g.M, p.bm2 ? 2 * TC_BM : TC_BM); p.nt = g.nseg > 1 ? g.nseg : cdiv(g.N, p.BN);
   const int kblocks = cdiv(g.K, TC_BK);
-  int splitk = g.splitk < 1 ? 1 : g.splitk;
+  int splitk = g.splitk;
+  if (splitk <= 0) {                        // auto: (tiles x splits) fills two waves of the 148 SMs
+    long sk = (2L * 148) / ((long)p.mt * p.nt);
+    const long maxs = kblocks / 8;
+    if (sk > maxs) sk = maxs;
+    splitk = sk < 1 ? 1 : (int)sk;
+  } else if (p.bm2) {
+    splitk *= 2;                            // the caller sized the split for 128-row tiles
+  }
   if (splitk > kblocks) splitk = kblocks;
   p.kb_per = cdiv(kblocks, splitk);
   p.splitk = cdiv(kblocks, p.kb_per);
@@ -657,7 +678,7 @@ int gemm_tc(const TcGemm& g, cudaStream_t st) {
     ARCVAE_REQUIRE(g.epi != TC_EPI_DEC_CELL_BWD || g.gates_b != nullptr, "saved gates");
     ARCVAE_REQUIRE(g.epi != TC_EPI_DEC_CELL0_BWD || (g.table && g.wc && g.tok && g.cond), "layer-0 recompute inputs");
   }
-  const size_t stage_bytes = (size_t)TC_BM * TC_BK * 2 + (size_t)p.BN * TC_BK * 2;
+  const size_t stage_bytes = (size_t)(p.bm2 ? 2 : 1) * TC_BM * TC_BK * 2 + (size_t)p.BN * TC_BK * 2;
   // transposition scratch for the fused cells and for plain bf16-only outputs of full, aligned tiles
   const bool plain_fast = g.nseg <= 1 && g.epi == TC_EPI_PLAIN && g.Cb != nullptr && g.C == nullptr && p.splitk == 1 && (g.N % p.BN) == 0 &&
                           (p.BN % 32) == 0 && p.BN * 2 / 2 <= 384 && (g.ldcb % 8) == 0 &&
