@@ -8,7 +8,8 @@ from .losses import (kl_divergence, mutual_information, posterior_collapse, prop
                      reconstruction_loss)
 from .models import ARCVAE, MLXAutoregressiveDecoder, MLXAutoregressiveDecoderSampling, MLXEncoder
 from .trainer import ARCVAETrainerWithLoss
+from .data import MoleculeDataset
 
 __all__ = ["ARCVAE", "MLXEncoder", "MLXAutoregressiveDecoder", "MLXAutoregressiveDecoderSampling",
            "complete_vae_loss", "loss_and_grad", "reconstruction_loss", "kl_divergence", "mutual_information",
-           "posterior_collapse", "property_prediction_loss", "ARCVAETrainerWithLoss"]
+           "posterior_collapse", "property_prediction_loss", "ARCVAETrainerWithLoss", "MoleculeDataset"]

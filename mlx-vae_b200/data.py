@@ -21,3 +21,74 @@ def synthetic_batch(B: int, T: int, vocab_size: int = 80, num_conditions: int = 
     eps = rng.standard_normal((B, latent_dim)).astype(np.float32)
     tf_mask = rng.random(T) < tf_ratio
     return x, cond, eps, tf_mask
+
+
+class MoleculeDataset:
+    """Drop-in for ``mlx_data/dataloader.py:4-111`` with the batching moved to the device.
+
+    Same constructor, normalisation and batch contract as the reference:
+      * properties are z-scored with the statistics passed in (the training set's, ``train.py:113-114``) or this
+        dataset's own, ``std < 1e-8 -> 1`` (dataloader.py:39-65);
+      * every sequence is right-padded with ``pad_token`` / truncated to ``max_length`` (:76-79);
+      * ``to_batches(batch_size, shuffle)`` draws ONE ``np.random.shuffle`` of ``arange(N)`` from the global NumPy RNG
+        (:90-94: same permutation as the reference for the same seed), walks it in ``batch_size`` strides and keeps
+        the ragged last batch (:96-97).
+    The reference builds each batch with a Python loop over samples (one ``mx.array`` per molecule); here the padded
+    token matrix and the normalised properties are uploaded ONCE and a batch is a single device gather, so the loader
+    keeps up with a step that consumes ~400 k molecules/s.  Tokens are int32 (reference: uint32)."""
+
+    def __init__(self, tokenized_molecules, properties, max_length: int = 120, pad_token: int = 0,
+                 properties_mean=None, properties_std=None, *, device=None):
+        import torch
+        self.molecules = tokenized_molecules
+        self.max_length = int(max_length)
+        self.pad_token = int(pad_token)
+        self.properties = np.array(properties, dtype=np.float32)
+        if self.properties.ndim == 1:
+            self.properties = self.properties[:, None]
+        if properties_mean is not None and properties_std is not None:
+            self.properties_mean = np.array(properties_mean, dtype=np.float32)
+            self.properties_std = np.array(properties_std, dtype=np.float32)
+        else:
+            self.properties_mean = self.properties.mean(axis=0, keepdims=True)
+            self.properties_std = self.properties.std(axis=0, keepdims=True)
+        if self.properties_mean.ndim == 1:
+            self.properties_mean = self.properties_mean[np.newaxis, :]
+        if self.properties_std.ndim == 1:
+            self.properties_std = self.properties_std[np.newaxis, :]
+        self.properties_std = np.where(self.properties_std < 1e-8, 1.0, self.properties_std).astype(np.float32)
+        self.properties_normalized = ((self.properties - self.properties_mean) / self.properties_std).astype(np.float32)
+        n = len(tokenized_molecules)
+        tok = np.full((n, self.max_length), self.pad_token, dtype=np.int32)
+        for i, mol in enumerate(tokenized_molecules):
+            m = min(len(mol), self.max_length)
+            tok[i, :m] = np.asarray(mol[:m], dtype=np.int64)
+        self.tokens = tok
+        if device is None:
+            device = "cuda" if torch.cuda.is_available() else "cpu"
+        self.device = torch.device(device)
+        self._dev = None
+
+    def __len__(self) -> int:
+        return len(self.molecules)
+
+    def __getitem__(self, idx: int) -> dict:
+        import torch
+        return {"molecule": torch.as_tensor(self.tokens[idx]), "properties": torch.as_tensor(self.properties_normalized[idx])}
+
+    def _resident(self):
+        import torch
+        if self._dev is None:
+            self._dev = (torch.as_tensor(self.tokens).to(self.device), torch.as_tensor(self.properties_normalized).to(self.device))
+        return self._dev
+
+    def to_batches(self, batch_size: int, shuffle: bool = True):
+        import torch
+        indices = np.arange(len(self))
+        if shuffle:
+            np.random.shuffle(indices)                                   # dataloader.py:93-94, global NumPy RNG
+        tok, props = self._resident()
+        idx_dev = torch.as_tensor(indices, dtype=torch.long).to(self.device)
+        for i in range(0, len(self), batch_size):
+            sel = idx_dev[i:i + batch_size]                              # ragged last batch kept (:96-97)
+            yield tok.index_select(0, sel), props.index_select(0, sel)

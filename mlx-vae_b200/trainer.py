@@ -101,6 +101,37 @@ class ARCVAETrainerWithLoss:
         self.step_count += 1
         return d
 
+    # ---- forward-only evaluation without teacher forcing (trainer.py:116-175, :418-487) --------
+    def _eval_batches(self, dataset, beta: float, max_batches: Optional[int]) -> Dict[str, float]:
+        from .complete_vae_loss import complete_vae_loss
+        keys = (("loss", "total_loss"), ("recon", "recon_loss"), ("kl", "kl_loss"), ("collapse", "collapse_penalty"),
+                ("prop", "prop_loss"))
+        acc = None
+        n = 0
+        for batch_idx, (molecules, conditions) in enumerate(dataset.to_batches(self.batch_size, shuffle=False)):
+            if max_batches is not None and batch_idx >= max_batches:
+                break
+            d = complete_vae_loss(self.encoder, self.decoder, self.property_predictor, molecules, conditions, beta=beta,
+                                  lambda_prop=self.lambda_prop, lambda_collapse=self.lambda_collapse,
+                                  teacher_forcing_ratio=0.0, free_bits=self.free_bits, lambda_mi=self.lambda_mi,
+                                  target_mi=4.85, seed=self.step_count + batch_idx, pad_mask=self.pad_mask)
+            v = torch.stack([d[k].detach().double() for _, k in keys])   # stays on the device: one sync at the end
+            acc = v if acc is None else acc + v
+            n += 1
+        if n == 0:
+            return {name: 0.0 for name, _ in keys}
+        host = (acc / n).cpu().tolist()
+        return {name: float(host[i]) for i, (name, _) in enumerate(keys)}
+
+    def _compute_true_train_loss(self, epoch: int, num_batches: int = 10) -> Dict[str, float]:
+        """trainer.py:116-175: the first ``num_batches`` unshuffled training batches, teacher_forcing_ratio = 0.0."""
+        return self._eval_batches(self.dataset, self.compute_beta(epoch), num_batches)
+
+    def _validate(self, val_dataset, beta: float) -> Dict[str, float]:
+        """trainer.py:418-487: every validation batch, teacher_forcing_ratio = 0.0 (greedy feedback chain), means of the
+        per-batch loss terms."""
+        return self._eval_batches(val_dataset, beta, None)
+
     def _train_epoch_batches(self, beta: float, teacher_forcing_ratio: float) -> Dict[str, float]:
         """trainer.py:242-416 without the tqdm / logging side paths: iterate ``dataset.to_batches`` and step."""
         total, n = 0.0, 0

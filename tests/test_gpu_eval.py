@@ -1,0 +1,67 @@
+"""GPU tests of the epoch-level evaluation mirrors (trainer.py:116-175 `_compute_true_train_loss`, :418-487 `_validate`;
+SURVEY §8f row N3) and of the device-side dataset feeding the trainer (row N2), against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+import arcvae_oracle as O
+import dataset_oracle as DO
+from _util import model_kwargs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def M():
+    import mlx_vae_b200
+    return mlx_vae_b200
+
+
+def test_validate_matches_oracle_and_dataset_feeds_training(M):
+    cfg = O.Config(23, 8, 16, 8, 1, 2)
+    p = O.init_params(cfg, seed=8, dtype=torch.float64)
+    p["decoder"] = O.tree_map(lambda t: t * 3.0, p["decoder"])
+    rng = np.random.default_rng(2)
+    n, T, bs = 21, 9, 8
+    mols = [list(rng.integers(3, cfg.vocab_size, size=int(rng.integers(2, 12))).tolist()) + [2] for _ in range(n)]
+    tpsa = rng.normal(70, 20, size=(n, 1))
+    kw = model_kwargs(cfg)
+    enc = M.MLXEncoder(**kw).load_parameters(p["encoder"])
+    dec = M.MLXAutoregressiveDecoder(**kw).load_parameters(p["decoder"])
+    ds = M.MoleculeDataset(mols, tpsa, max_length=T)
+    ref_ds = DO.MoleculeDatasetOracle(mols, tpsa, max_length=T)
+    hyper = dict(lambda_prop=0.1, lambda_collapse=0.001, free_bits=1.0, lambda_mi=0.01)
+    tr = M.ARCVAETrainerWithLoss(enc, dec, None, ds, learning_rate=1e-3, batch_size=bs, beta_start=0.0, beta_end=0.05,
+                                 beta_warmup_epochs=20, **hyper)
+    beta = 0.03
+    # oracle: every batch, teacher forcing off (all coins false), mean of the per-batch terms
+    acc = {k: 0.0 for k in ("total_loss", "recon_loss", "kl_loss", "collapse_penalty", "prop_loss")}
+    nb = 0
+    for mb, pb in ref_ds.to_batches(bs, shuffle=False):
+        x = torch.as_tensor(mb.astype(np.int64)); c = torch.as_tensor(pb).double()
+        d = O.complete_vae_loss(p, x, c, cfg.num_layers, torch.zeros(x.shape[0], cfg.latent_dim, dtype=torch.float64),
+                                np.zeros(T, dtype=bool), beta=beta, target_mi=4.85, **hyper)
+        for k in acc:
+            acc[k] += float(d[k])
+        nb += 1
+    ref = {"loss": acc["total_loss"] / nb, "recon": acc["recon_loss"] / nb, "kl": acc["kl_loss"] / nb,
+           "collapse": acc["collapse_penalty"] / nb, "prop": acc["prop_loss"] / nb}
+    got = tr._validate(ds, beta)
+    assert set(got) == set(ref)
+    for k in ref:
+        assert abs(got[k] - ref[k]) <= 1e-4 * max(1.0, abs(ref[k])), (k, got[k], ref[k])
+    # _compute_true_train_loss: first num_batches unshuffled batches at beta(epoch)
+    got2 = tr._compute_true_train_loss(epoch=12, num_batches=2)
+    acc2, nb2 = 0.0, 0
+    for mb, pb in ref_ds.to_batches(bs, shuffle=False):
+        if nb2 >= 2:
+            break
+        x = torch.as_tensor(mb.astype(np.int64)); c = torch.as_tensor(pb).double()
+        d = O.complete_vae_loss(p, x, c, cfg.num_layers, torch.zeros(x.shape[0], cfg.latent_dim, dtype=torch.float64),
+                                np.zeros(T, dtype=bool), beta=tr.compute_beta(12), target_mi=4.85, **hyper)
+        acc2 += float(d["total_loss"]); nb2 += 1
+    assert abs(got2["loss"] - acc2 / nb2) <= 1e-4 * max(1.0, abs(acc2 / nb2))
+    # one epoch of training straight from the device-resident dataset (ragged last batch of 5 included)
+    np.random.seed(3)
+    out = tr._train_epoch_batches(beta, 0.9)
+    assert np.isfinite(out["loss"]) and tr.step_count == 3
