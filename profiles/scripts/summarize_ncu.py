@@ -28,7 +28,33 @@ KEYS = [
 ]
 
 
+def traffic(reps):
+    """--traffic rec.ncu-rep gemm.ncu-rep loss.ncu-rep -> JSON {category: mean DRAM bytes (read+write) per launch}."""
+    import json
+    out = {}
+    for cat, rep in zip(("recurrence", "gemm_tc", "loss"), reps):
+        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
+        rows = list(csv.reader(io.StringIO(txt)))
+        hdr, units = rows[0], rows[1]
+        col = {n: i for i, n in enumerate(hdr)}
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot, n = 0.0, 0
+        for r in rows[2:]:
+            b = 0.0
+            for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                b += float(r[col[key]]) * scale[units[col[key]]]
+            tot += b
+            n += 1
+        out[cat] = tot / max(1, n)
+        out[cat + "_launches_captured"] = n
+    out["source"] = "ncu --set full --clock-control none, dram__bytes_read.sum + dram__bytes_write.sum, mean per captured launch"
+    print(json.dumps(out, indent=1))
+    return 0
+
+
 def main():
+    if sys.argv[1] == "--traffic":
+        return traffic(sys.argv[2:5])
     rep = sys.argv[1]
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
