@@ -132,6 +132,45 @@ class ARCVAETrainerWithLoss:
         per-batch loss terms."""
         return self._eval_batches(val_dataset, beta, None)
 
+    # ---- checkpoint interop (trainer.py:577-603, :685-736; SURVEY.md §8f row N1) ---------------------------------------
+    def save_checkpoint(self, path, epoch: int = 0) -> str:
+        """Flat ``.npz`` with the reference's parameter names: ``encoder/<module>.<leaf>``,
+        ``decoder/<module>.<leaf>``, Adam moments ``encoder_opt/m|v/<module>.<leaf>`` ..., ``epoch``.  The reference
+        pickles nested dicts of ``mx.array`` (unreadable without MLX); ``tools/convert_mlx_checkpoint.py`` re-saves such
+        a file in this flat format on a machine that has MLX."""
+        import numpy as np
+        out = {"epoch": np.int64(epoch), "format": np.array("arcvae-flat-v1")}
+        for tag, mod, opt in (("encoder", self.encoder, self.encoder_optimizer), ("decoder", self.decoder, self.decoder_optimizer)):
+            for name, view in mod.params.views.items():
+                out[f"{tag}/{name}"] = view.detach().cpu().numpy()
+            off = 0
+            for name, view in mod.params.views.items():
+                n = view.numel()
+                beg = view.data_ptr() - mod.params.flat.data_ptr()
+                beg //= 4
+                out[f"{tag}_opt/m/{name}"] = opt.m[beg:beg + n].reshape(view.shape).cpu().numpy()
+                out[f"{tag}_opt/v/{name}"] = opt.v[beg:beg + n].reshape(view.shape).cpu().numpy()
+                off += n
+        path = str(path)
+        np.savez(path, **out)
+        return path if path.endswith(".npz") else path + ".npz"
+
+    def load_checkpoint(self, path) -> int:
+        """Inverse of ``save_checkpoint``; returns the stored epoch (trainer.py:685-712).  Optimizer moments are optional
+        (a converted reference checkpoint may carry weights only)."""
+        import numpy as np
+        ck = np.load(str(path), allow_pickle=False)
+        for tag, mod, opt in (("encoder", self.encoder, self.encoder_optimizer), ("decoder", self.decoder, self.decoder_optimizer)):
+            mod.load_parameters({name: ck[f"{tag}/{name}"] for name in mod.params.views})
+            for name, view in mod.params.views.items():
+                n = view.numel()
+                beg = (view.data_ptr() - mod.params.flat.data_ptr()) // 4
+                for mom, buf in (("m", opt.m), ("v", opt.v)):
+                    key = f"{tag}_opt/{mom}/{name}"
+                    if key in ck.files:
+                        buf[beg:beg + n].copy_(torch.as_tensor(ck[key]).reshape(-1).to(buf.device))
+        return int(ck["epoch"]) if "epoch" in ck.files else 0
+
     def _train_epoch_batches(self, beta: float, teacher_forcing_ratio: float) -> Dict[str, float]:
         """trainer.py:242-416 without the tqdm / logging side paths: iterate ``dataset.to_batches`` and step."""
         total, n = 0.0, 0

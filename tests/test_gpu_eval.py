@@ -65,3 +65,23 @@ def test_validate_matches_oracle_and_dataset_feeds_training(M):
     np.random.seed(3)
     out = tr._train_epoch_batches(beta, 0.9)
     assert np.isfinite(out["loss"]) and tr.step_count == 3
+
+
+def test_checkpoint_roundtrip(M, tmp_path):
+    cfg = O.Config(23, 8, 16, 8, 1, 2)
+    kw = model_kwargs(cfg)
+    enc = M.MLXEncoder(**kw, seed=1); dec = M.MLXAutoregressiveDecoder(**kw, seed=2)
+    tr = M.ARCVAETrainerWithLoss(enc, dec, None, None, learning_rate=1e-3, batch_size=8)
+    x = torch.randint(0, 23, (8, 7), device="cuda"); c = torch.randn(8, 1, device="cuda")
+    tr.train_step(x, c, 0.05, 0.9, tf_mask=np.ones(7, dtype=bool))
+    path = tr.save_checkpoint(tmp_path / "ck", epoch=3)
+    ck = np.load(path)
+    assert "encoder/lstm_layer_0.Wh" in ck.files and "decoder/fc_out.weight" in ck.files and "encoder_opt/m/fc_mu.weight" in ck.files
+    enc2 = M.MLXEncoder(**kw, seed=7); dec2 = M.MLXAutoregressiveDecoder(**kw, seed=8)
+    tr2 = M.ARCVAETrainerWithLoss(enc2, dec2, None, None, learning_rate=1e-3, batch_size=8)
+    assert tr2.load_checkpoint(path) == 3
+    assert torch.equal(enc2.params.flat, enc.params.flat) and torch.equal(dec2.params.flat, dec.params.flat)
+    assert torch.equal(tr2.encoder_optimizer.m, tr.encoder_optimizer.m) and torch.equal(tr2.decoder_optimizer.v, tr.decoder_optimizer.v)
+    a = tr.train_step(x, c, 0.05, 0.9, tf_mask=np.ones(7, dtype=bool), seed=5)
+    b = tr2.train_step(x, c, 0.05, 0.9, tf_mask=np.ones(7, dtype=bool), seed=5)
+    assert float(a["total_loss"]) == float(b["total_loss"]) and torch.equal(enc2.params.flat, enc.params.flat)
