@@ -225,10 +225,25 @@ def main():
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-sampler", action="store_true", help="skip the sampled-molecules/s leg")
+    ap.add_argument("--config", default="default", choices=["default", "scaled"],
+                    help="scaled = BASELINE configs[3]: hidden 1024, latent 256, 3 layers, length 256 (not the headline; "
+                         "per-step tensor-core recurrence, B defaults to 1024)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
+    global T, FLOP_FWD_PER_MOLECULE, FLOP_STEP_PER_MOLECULE, LOSS_BYTES_PER_MOLECULE
+    if args.config == "scaled":
+        DIMS.update(hidden_dim=1024, latent_dim=256, num_layers=3)
+        T = 256
+        if args.batch == B_PER_GPU:
+            args.batch = 1024
+        args.no_sampler = True
+        args.no_cpu = True
+        # encoder 42,991,616 + decoder 17,997,824 FLOP per token, head 10,487,808 per molecule
+        FLOP_FWD_PER_MOLECULE = T * (42_991_616 + 17_997_824) + 10_487_808
+        FLOP_STEP_PER_MOLECULE = 3 * FLOP_FWD_PER_MOLECULE
+        LOSS_BYTES_PER_MOLECULE = T * 80 * 4 * 2 + T * 4
 
     import numpy as np
     import torch
@@ -373,8 +388,10 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16",
             "data": "synthetic",
-            "config": {"workload": f"default AR-CVAE (V80 E128 H256 L128 C1 NL2) full train step, B={B} x T={T} per GPU "
-                                   f"(configs[1]); global batch {B * world}",
+            "config": {"workload": (f"default AR-CVAE (V80 E128 H256 L128 C1 NL2) full train step, B={B} x T={T} per GPU "
+                                    f"(configs[1]); global batch {B * world}") if args.config == "default" else
+                                   (f"scaled AR-CVAE (V80 E128 H1024 L256 C1 NL3) full train step, B={B} x T={T} per GPU "
+                                    f"(configs[3]); global batch {B * world}"),
                        "parallelism": f"dp{world}", "teacher_forcing": 0.9,
                        "l2": "no explicit flush: every step streams >6 GB of activations (>> 126 MB L2)"},
             "e2e": {"value": B * world / (ms_e2e * 1e-3), "unit": "molecules/s", "h2d_bytes_per_step": h2d,

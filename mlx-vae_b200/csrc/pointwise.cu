@@ -212,8 +212,8 @@ __global__ void k_dec_cell0_fwd_v8(const float* __restrict__ table, const float*
 }
 // bf16 path, large row counts: the [V,3H] table is staged ONCE per CTA in shared memory as bf16 (V=80, H=256: 120 KB), so
 // the gather never leaves the SM (the global-memory version pulls 1.5-3 KB per row through L2: 1.6 GB at B*T = 524288)
-// and the kernel is bound by its h / gate-tape writes.  One persistent CTA per SM, 1024 threads, thread = 8 hidden units.
-__global__ void __launch_bounds__(1024, 1)
+// and the kernel is bound by its h / gate-tape writes.  One persistent CTA per SM, 768 threads, thread = 8 hidden units.
+__global__ void __launch_bounds__(768, 1)
 k_dec_cell0_fwd_smem(const float* __restrict__ table, const float* __restrict__ wc, const int32_t* __restrict__ tok,
                      const float* __restrict__ cond, int B, int C, int H, int V, int R, RowMap rm,
                      __nv_bfloat16* __restrict__ hb, __nv_bfloat16* __restrict__ gates_b) {
@@ -233,6 +233,17 @@ k_dec_cell0_fwd_smem(const float* __restrict__ table, const float* __restrict__ 
   // the token (and through it the table row) is a dependent load: fetch the NEXT item's token and condition while this
   // item's cell math runs, otherwise every item pays a full L2 round trip with nothing to overlap it
   long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  // the grid stride is a multiple of the chunks per row, so a thread always owns the SAME 8 hidden units: its 24 cond
+  // weights live in registers (C == 1; reading them from shared memory per item was an 8-way bank conflict)
+  const bool wreg_ok = (C == 1) && (stride % cpr) == 0;
+  float wreg[3][8];
+  if (wreg_ok && idx < total) {
+    const int j0 = (int)(idx % cpr) << 3;
+#pragma unroll
+    for (int g = 0; g < 3; g++)
+#pragma unroll
+      for (int k = 0; k < 8; k++) wreg[g][k] = wcs[g * H + j0 + k];
+  }
   long r_n = 0;
   int tok_n = 0, j_n = 0;
   float c0_n = 0.f;
@@ -268,13 +279,20 @@ k_dec_cell0_fwd_smem(const float* __restrict__ table, const float* __restrict__ 
         a[g][2 * k] = t.x; a[g][2 * k + 1] = t.y;
       }
     }
-    const float* crow = cond + (r % B) * C;
-    for (int c = 0; c < C; c++) {
-      const float cv = (c == 0) ? cond0 : __ldg(crow + c);
+    if (wreg_ok) {
 #pragma unroll
       for (int g = 0; g < 3; g++)
 #pragma unroll
-        for (int k = 0; k < 8; k++) a[g][k] = fmaf(cv, wcs[(g * H + j + k) * C + c], a[g][k]);
+        for (int k = 0; k < 8; k++) a[g][k] = fmaf(cond0, wreg[g][k], a[g][k]);
+    } else {
+      const float* crow = cond + (r % B) * C;
+      for (int c = 0; c < C; c++) {
+        const float cv = (c == 0) ? cond0 : __ldg(crow + c);
+#pragma unroll
+        for (int g = 0; g < 3; g++)
+#pragma unroll
+          for (int k = 0; k < 8; k++) a[g][k] = fmaf(cv, wcs[(g * H + j + k) * C + c], a[g][k]);
+      }
     }
     float hv[8];
 #pragma unroll
@@ -313,7 +331,7 @@ int dec_cell0_fwd(const float* table, const float* wc, const int32_t* tok, const
       ARCVAE_CUDA(cudaFuncSetAttribute(k_dec_cell0_fwd_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       attr = true;
     }
-    k_dec_cell0_fwd_smem<<<148, 1024, smem_tab, st>>>(table, wc, tok, cond, B, C, H, V, R, rm, hb, gates_b);
+    k_dec_cell0_fwd_smem<<<148, 768, smem_tab, st>>>(table, wc, tok, cond, B, C, H, V, R, rm, hb, gates_b);
     ARCVAE_LAUNCHED();
     return 0;
   }
