@@ -206,8 +206,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "AR-CVAE train molecules/s", "value": rate, "unit": "molecules/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": max(1, warmup), "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"default AR-CVAE train step, B={B_PER_GPU} x T={T} per GPU (configs[1])",
-                       "cpu_sample": sample},
+            "config": {"workload": f"default AR-CVAE (V80 E128 H256 L128 C1 NL2) full train step, B={B_PER_GPU} x T={T} per GPU "
+                                   f"(configs[1]); global batch {B_PER_GPU * max(1, args.gpus)}",
+                       "parallelism": f"dp{max(1, args.gpus)}", "teacher_forcing": 0.9, "cpu_sample": sample},
             "cpu_baseline": {"value": rate, "unit": "molecules/s", "cores": cores, "kind": "port", "sample": sample,
                              "note": "MLX is not installable in this image; this is oracle/arcvae_oracle.py, a torch-CPU "
                                      "fp32 restatement of the reference step"},
