@@ -120,7 +120,7 @@ struct DecScratch {
   float* dWxc[ARCVAE_MAX_LAYERS];     // compact weight grads
   float* dbc[ARCVAE_MAX_LAYERS];
   float* dwc;                         // [3H,C]
-  __nv_bfloat16* dlb;                 // bf16 [R,V] copy of dlogits
+  __nv_bfloat16* dlb;                 // bf16 [R,Vp] copy of dlogits, row pitch Vp = V rounded up to 8 (TMA needs 16-byte pitches)
   __nv_bfloat16* dGb;                 // bf16 [R,3H] copy of the pre-activation gradients
   __nv_bfloat16* dGb2;                // fused path: second [R,3H] buffer (ping-pong between layers, layer-0 dG)
   __nv_bfloat16* onehot;              // fused path: [R,SCATTER_NW] one-hot of the fed tokens + cond hi/lo columns
@@ -142,7 +142,7 @@ static size_t dec_scratch_layout(const arcvae_dims& d, int B, int T, void* base,
     ss.dbc[l] = a.take<float>((size_t)3 * d.H);
   }
   ss.dwc = a.take<float>((size_t)3 * d.H * d.C);
-  ss.dlb = a.take<__nv_bfloat16>(R * d.V);
+  ss.dlb = a.take<__nv_bfloat16>(R * (size_t)((d.V + 7) / 8 * 8));
   ss.dGb = a.take<__nv_bfloat16>(R * 3 * d.H);
   ss.dGb2 = a.take<__nv_bfloat16>(R * 3 * d.H);
   ss.onehot = a.take<__nv_bfloat16>(R * SCATTER_NW);
@@ -294,9 +294,10 @@ extern "C" int arcvae_decoder_backward(const arcvae_dims* d, const arcvae_decode
 
   const bool bf = precision == ARCVAE_PREC_BF16;
   const bool fused = dec_fused_ok(*d, precision, B, true);
-  if (bf) ARCVAE_TRY(f32_to_bf16(dlogits_tm, sc.dlb, R * V, st));
+  const int Vp = (V + 7) / 8 * 8;            // row pitch of the bf16 copy of dlogits
+  if (bf) ARCVAE_TRY(f32_to_bf16_pitched(dlogits_tm, R, V, sc.dlb, Vp, st));
   // fc_out: logits = h_top @ Wout^T + b
-  ARCVAE_TRY(gemm_any(precision, 1, 0, V, H, (int)R, Mat{dlogits_tm, bf ? sc.dlb : nullptr, V},
+  ARCVAE_TRY(gemm_any(precision, 1, 0, V, H, (int)R, Mat{dlogits_tm, bf ? sc.dlb : nullptr, bf && fused ? Vp : V},
                       Mat{fused ? nullptr : tp.hd[top], bf ? tp.hdb[top] : nullptr, H}, g->fc_out_w, H, nullptr, true, id, R, st));
   ARCVAE_TRY(colsum(dlogits_tm, R, V, V, g->fc_out_b, st));
   float* dh = sc.dh[0];
@@ -304,11 +305,11 @@ extern "C" int arcvae_decoder_backward(const arcvae_dims* d, const arcvae_decode
 
   if (fused) {
     // every "d h = dG_upper @ W" GEMM runs the cell-backward of the layer below in its epilogue; only bf16 dG is stored
-    auto fused_gemm = [&](const __nv_bfloat16* A, int K, const __nv_bfloat16* Bw, int layer_below,
+    auto fused_gemm = [&](const __nv_bfloat16* A, int K, int lda, const __nv_bfloat16* Bw, int layer_below,
                           __nv_bfloat16* out) -> int {
       TcGemm q{};
       q.M = (int)R; q.N = H; q.K = K;
-      q.A = A; q.lda = K; q.a_mn = false;
+      q.A = A; q.lda = lda; q.a_mn = false;
       q.B = Bw; q.ldb = H; q.b_mn = true;                       // B[k*H + n]: row-major [K,H]
       q.accumulate = false; q.splitk = 1; q.rm = id; q.a_rows_total = R; q.Hh = H; q.dg_out = out;
       q.epi = TC_EPI_DEC_CELL_BWD; q.gates_b = tp.gates_b[layer_below];      // layer 0 keeps its gate tape as well
@@ -320,7 +321,7 @@ extern "C" int arcvae_decoder_backward(const arcvae_dims* d, const arcvae_decode
     const bool fuse_dw = H <= 256;
     __nv_bfloat16* cur = sc.dGb;
     __nv_bfloat16* nxt = sc.dGb2;
-    ARCVAE_TRY(fused_gemm(sc.dlb, V, tp.prep.Woutb, top, cur));   // d h_top = dlogits @ Wout, then cell backward of `top`
+    ARCVAE_TRY(fused_gemm(sc.dlb, V, Vp, tp.prep.Woutb, top, cur));   // d h_top = dlogits @ Wout, then cell backward of `top`
     for (int l = top; l >= 1; l--) {
       // cur = dG_l (tile-permuted compact layout)
       ARCVAE_CUDA(cudaMemsetAsync(sc.dWxc[l], 0, (size_t)H3 * H * sizeof(float), st));
@@ -347,7 +348,7 @@ extern "C" int arcvae_decoder_backward(const arcvae_dims* d, const arcvae_decode
                             nullptr, true, id, R, st));
         ARCVAE_TRY(colsum_bf16(cur, R, H3, H3, sc.dbc[l], st));
       }
-      ARCVAE_TRY(fused_gemm(cur, H3, tp.prep.Wxpb[l], l - 1, nxt));
+      ARCVAE_TRY(fused_gemm(cur, H3, H3, tp.prep.Wxpb[l], l - 1, nxt));
       ARCVAE_TRY(expand_perm_gates_add(sc.dWxc[l], H, H, g->Wx[l], st));
       ARCVAE_TRY(expand_perm_gates_add(sc.dbc[l], H, 1, g->bias[l], st));
       __nv_bfloat16* tmp = cur; cur = nxt; nxt = tmp;

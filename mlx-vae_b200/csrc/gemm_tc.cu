@@ -793,6 +793,25 @@ int f32_to_bf16(const float* src, bf16* dst, long n, cudaStream_t st) {
   ARCVAE_LAUNCHED();
   return 0;
 }
+// rows of V floats -> rows of bf16 with pitch Vp >= V (pad columns zero): operands whose natural pitch is not a
+// multiple of 16 bytes cannot be described to the TMA unit
+__global__ void k_f32_to_bf16_pitched(const float* __restrict__ src, long R, int V, bf16* __restrict__ dst, int Vp) {
+  const long total = R * Vp;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / Vp;
+    const int c = (int)(i - r * Vp);
+    dst[i] = __float2bfloat16(c < V ? src[r * V + c] : 0.f);
+  }
+}
+int f32_to_bf16_pitched(const float* src, long R, int V, bf16* dst, int Vp, cudaStream_t st) {
+  if (Vp == V) return f32_to_bf16(src, dst, R * V, st);
+  long g = (R * Vp + 255) / 256;
+  if (g > 148 * 8) g = 148 * 8;
+  TimeScope ts(TIME_POINTWISE, st);
+  k_f32_to_bf16_pitched<<<(int)g, 256, 0, st>>>(src, R, V, dst, Vp);
+  ARCVAE_LAUNCHED();
+  return 0;
+}
 // dst[c*R + r] = bf16(src[r*C + c])   (weights only: small)
 __global__ void k_transpose_to_bf16(const float* __restrict__ src, int R, int C, bf16* __restrict__ dst) {
   __shared__ float tile[32][33];

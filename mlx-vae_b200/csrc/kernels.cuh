@@ -104,6 +104,7 @@ enum { TC_EPI_PLAIN = 0, TC_EPI_DEC_CELL_FWD = 1, TC_EPI_DEC_CELL_BWD = 2, TC_EP
 int gemm_tc(const TcGemm& g, cudaStream_t st);
 int pick_splitk_tc(int M, int N, int K);
 int f32_to_bf16(const float* src, __nv_bfloat16* dst, long n, cudaStream_t st);
+int f32_to_bf16_pitched(const float* src, long R, int V, __nv_bfloat16* dst, int Vp, cudaStream_t st);   // pad columns zero
 int transpose_to_bf16(const float* src, int R, int C, __nv_bfloat16* dst, cudaStream_t st);   // dst[c*R+r] = src[r*C+c]
 
 // persistent cluster LSTM recurrence (lstm_cluster.cu), H == 256

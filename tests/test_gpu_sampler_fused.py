@@ -131,3 +131,45 @@ def test_fused_multinomial_statistics_and_determinism(M):
     prob = torch.softmax(logits / 0.9, 0).numpy()
     freq = np.bincount(first.cpu().numpy(), minlength=cfg.vocab_size) / float(n)
     assert np.abs(freq - prob).max() < 0.012, np.abs(freq - prob).max()
+
+
+def test_fused_paths_with_two_conditions_and_odd_vocab(M):
+    """num_conditions = 2 and vocab 95 (the dims of the reference's test_loss_signs.py): the cond hi/lo columns of the
+    one-hot operand (V + 2C = 99 <= 128), the fused decoder cells and the permuted one-hot scatter, against fp32."""
+    cfg = O.Config(95, 64, 128, 32, 2, 2)
+    B, T = 256, 6
+    p = O.init_params(cfg, seed=21, dtype=torch.float32)
+    p["decoder"] = O.tree_map(lambda t: t * 3.0, p["decoder"])
+    kw = model_kwargs(cfg)
+    rng = np.random.default_rng(1)
+    x = torch.as_tensor(rng.integers(0, 95, size=(B, T)).astype(np.int32)).cuda()
+    cond = torch.as_tensor(rng.standard_normal((B, 2)).astype(np.float32)).cuda()
+    eps = torch.as_tensor(rng.standard_normal((B, 32)).astype(np.float32)).cuda()
+    mask = np.ones(T, dtype=bool)
+    hyper = dict(beta=0.05, lambda_prop=0.1, lambda_collapse=0.001, free_bits=1.0, lambda_mi=0.01, target_mi=4.85)
+    out = {}
+    for prec in ("fp32", "bf16"):
+        enc = M.MLXEncoder(**kw, precision=prec).load_parameters(p["encoder"])
+        dec = M.MLXAutoregressiveDecoder(**kw, precision=prec).load_parameters(p["decoder"])
+        d, (ge, gd) = M.loss_and_grad(enc, dec, None, x, cond, eps=eps, tf_mask=mask, **hyper)
+        out[prec] = (float(d["total_loss"]), {k: v.clone() for k, v in O.tree_flatten({"e": ge, "d": gd}).items()}, dec)
+    assert abs(out["fp32"][0] - out["bf16"][0]) / abs(out["fp32"][0]) < 2e-2
+    worst, name = 0.0, None
+    for n, g32 in out["fp32"][1].items():
+        s = float(g32.abs().max())
+        if s == 0.0:
+            assert float(out["bf16"][1][n].abs().max()) == 0.0, n
+            continue
+        e = float((g32 - out["bf16"][1][n]).abs().max()) / s
+        if e > worst:
+            worst, name = e, n
+    print("C=2, V=95: worst bf16 gradient rel err", worst, name)
+    assert worst < 5e-2, (worst, name)
+    # fused sampler with two conditions
+    s = M.MLXAutoregressiveDecoderSampling(**kw, decoder=out["bf16"][2])
+    toks = s.generate_with_temperature(None, cond, max_length=8, early_stopping=False)
+    logits = fp32_logits_of(M, cfg, p, toks, cond)
+    top = logits.max(dim=2).values
+    picked = logits.gather(2, toks.long().unsqueeze(2)).squeeze(2)
+    rng_ = (top - logits.min(dim=2).values).clamp_min(1e-6)
+    assert float(((top - picked) / rng_).max()) < TOL
