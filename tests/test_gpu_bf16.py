@@ -153,3 +153,32 @@ def test_scaled_config_bf16_matches_fp32(M):
             worst, name = e, n
     print("scaled config: worst gradient rel err", worst, name)
     assert worst < TOL_GRAD, (worst, name)
+
+
+def test_bf16_training_trajectory_tracks_fp32(M):
+    """30 optimizer steps on a fixed batch at the default dims: the loss must fall, and the bf16 tensor-core trajectory
+    (cluster recurrence, fused GEMM epilogues, multi-segment weight gradients, MLX-style Adam) must track the fp32 one."""
+    cfg = O.Config()
+    B, T = 256, 16
+    x, cond, eps, _ = O.synthetic_batch(B, T, cfg, seed=11, tf_ratio=1.0)
+    mask = np.ones(T, dtype=bool)
+    p = O.init_params(cfg, seed=12, dtype=torch.float32)
+    kw = model_kwargs(cfg)
+    traj = {}
+    for prec in ("fp32", "bf16"):
+        enc = M.MLXEncoder(**kw, precision=prec).load_parameters(p["encoder"])
+        dec = M.MLXAutoregressiveDecoder(**kw, precision=prec).load_parameters(p["decoder"])
+        tr = M.ARCVAETrainerWithLoss(enc, dec, None, None, learning_rate=2e-3, batch_size=B, lambda_prop=0.1,
+                                     lambda_collapse=0.001, free_bits=1.0, lambda_mi=0.01)
+        losses = []
+        for _ in range(30):
+            d = tr.train_step(cuda(x), cuda(cond), 0.05, 1.0, eps=cuda(eps), tf_mask=mask)
+            losses.append(float(d["total_loss"]))
+        traj[prec] = np.array(losses)
+        if prec == "bf16":
+            enc.check()
+    a, b = traj["fp32"], traj["bf16"]
+    print("fp32 loss:", a[[0, 9, 19, 29]], "bf16 loss:", b[[0, 9, 19, 29]])
+    assert a[-1] < 0.8 * a[0] and b[-1] < 0.8 * b[0], (a[0], a[-1], b[0], b[-1])
+    assert np.all(np.isfinite(b))
+    assert np.max(np.abs(a - b) / np.abs(a)) < 5e-2, np.max(np.abs(a - b) / np.abs(a))
