@@ -43,7 +43,7 @@ def run_encoder(M, p, x, cond, prec, cluster, dmu=None, dlv=None):
         os.environ.pop("ARCVAE_NO_CLUSTER", None)
 
 
-@pytest.mark.parametrize("B,T", [(128, 2), (128, 9), (256, 24), (200, 16), (4096, 128)])
+@pytest.mark.parametrize("B,T", [(64, 1), (130, 3), (128, 2), (128, 9), (256, 24), (200, 16), (4096, 128)])
 def test_cluster_matches_per_step_paths(M, B, T):
     cfg = O.Config()
     p = O.init_params(cfg, seed=3, dtype=torch.float32)
