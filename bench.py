@@ -226,6 +226,9 @@ def main():
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-sampler", action="store_true", help="skip the sampled-molecules/s leg")
+    ap.add_argument("--workload", default="train", choices=["train", "sample"],
+                    help="sample = BASELINE configs[4]: TPSA-conditioned sampling of 1M molecules sharded over the GPUs "
+                         "(125k per GPU, max length 128, greedy and multinomial); prints its own JSON line")
     ap.add_argument("--config", default="default", choices=["default", "scaled"],
                     help="scaled = BASELINE configs[3]: hidden 1024, latent 256, 3 layers, length 256 (not the headline; "
                          "per-step tensor-core recurrence, B defaults to 1024)")
@@ -298,6 +301,43 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), M._lib.launch_count() - l0, out
 
+    if args.workload == "sample":
+        # every rank samples its own shard (no communication: replicas); whole-job rate = sum of shards / max time
+        clk = ClockSampler(local) if rank == 0 else None
+        if clk:
+            clk.start()
+        barrier()
+        res = bench_sampler(M, vae, steps=max(1, min(args.steps, 5)), warmup=1, cpu=(rank == 0 and not args.no_cpu))
+        barrier()
+        clocks = clk.stop() if clk else None
+        out = {}
+        for name in ("greedy", "multinomial"):
+            t = torch.tensor([res[name]["ms"], res[name]["e2e_ms"]], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            out[name] = (float(t[0]), float(t[1]))
+        if rank == 0:
+            n = SAMPLE_B_PER_GPU * world
+            line = {"metric": "AR-CVAE sampled molecules/s", "value": n / (out["greedy"][0] * 1e-3), "unit": "molecules/s",
+                    "n_gpus": world, "steps": max(1, min(args.steps, 5)), "warmup": 1, "ms_per_step": out["greedy"][0],
+                    "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                    "config": {"workload": f"TPSA-conditioned greedy sampling, {SAMPLE_B_PER_GPU} molecules x max_length "
+                                           f"{SAMPLE_T} per GPU (configs[4]: {n} molecules over {world} GPUs), early stopping off",
+                               "parallelism": f"replicas x{world}"},
+                    "e2e": {"value": n / (out["greedy"][1] * 1e-3), "unit": "molecules/s",
+                            "h2d_bytes_per_step": res["greedy"]["h2d_bytes"], "d2h_bytes_per_step": res["greedy"]["d2h_bytes"],
+                            "ms_per_step": out["greedy"][1]},
+                    "multinomial": {"value": n / (out["multinomial"][0] * 1e-3), "e2e": n / (out["multinomial"][1] * 1e-3)},
+                    "gpu_launches": res["greedy"]["gpu_launches"], "clocks": clocks,
+                    "roofline": {"kernel": "sampler_fused_kernel", "bound": "mufu", "achieved": res["greedy"]["us_per_step_per_128_rows"],
+                                 "peak": 8.3, "unit": "us per step per 128-row tile (lower is better)",
+                                 "frac": 8.3 / res["greedy"]["us_per_step_per_128_rows"], "traffic": None,
+                                 "note": "floor = 8 MUFU.TANH per hidden unit and step at 16/clk/SM; not an HBM or tensor bound"},
+                    "cpu_baseline": res.get("cpu_baseline")}
+            print(json.dumps(line))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     for _ in range(args.warmup):
         step_resident()
     sampler = ClockSampler(local) if rank == 0 else None
