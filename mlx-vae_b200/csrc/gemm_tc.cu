@@ -42,8 +42,7 @@ struct TcParams {
   // fused decoder epilogues
   int epi;
   bf16* gates_b; bf16* hb_out; bf16* dg_out;
-  const float* table; const float* wc; const int32_t* tok; const float* cond;
-  int Bt, Cc, Hh;
+  int Hh;
   // multi-segment B (weight gradients that share the A operand): column tile ni multiplies A with its own B matrix
   // (rows shifted by seg_shift[ni]; negative TMA coordinates zero-fill) into its own C
   int nseg; int segN[3]; int seg_shift[3]; float* segC[3]; int seg_ldc[3];
@@ -54,29 +53,6 @@ struct TcParams {
 
 __device__ __forceinline__ float tanh_fast_(float x) { return tanh_approx_(x); }
 __device__ __forceinline__ float sigmoid_fast_(float x) { return sigmoid_approx_(x); }
-__device__ __forceinline__ void store16_bf16(bf16* dst, const float (&v)[16]) {
-  uint32_t pk[8];
-#pragma unroll
-  for (int j = 0; j < 8; j++) {
-    __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-    pk[j] = *reinterpret_cast<uint32_t*>(&t);
-  }
-  *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-  *reinterpret_cast<uint4*>(dst + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-}
-__device__ __forceinline__ void load16_bf16(const bf16* src, float (&v)[16]) {
-  const uint4 a = __ldg(reinterpret_cast<const uint4*>(src));
-  const uint4 b = __ldg(reinterpret_cast<const uint4*>(src + 8));
-  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
-  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
-#pragma unroll
-  for (int j = 0; j < 4; j++) {
-    float2 t = __bfloat1622float2(pa[j]);
-    v[2 * j] = t.x; v[2 * j + 1] = t.y;
-    float2 w = __bfloat1622float2(pb[j]);
-    v[8 + 2 * j] = w.x; v[8 + 2 * j + 1] = w.y;
-  }
-}
 // zero-state decoder cell backward: (i, g, o activated, dh) -> pre-activation gradients
 __device__ __forceinline__ void dec_cell_grads_fast(float i_, float g_, float o_, float dh, float& dai, float& dag,
                                                     float& dao) {
@@ -405,61 +381,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             scr_store_rows(scr, TC_SCR_PITCH, reinterpret_cast<uint8_t*>(p.dg_out + goff), 3L * H * 2, 384, rows_here, lane);
           __syncwarp();
         }
-      } else if (p.epi == TC_EPI_DEC_CELL0_BWD) {
-        // layer-0 gates recomputed from the table (used when the layer-0 gate tape is not kept)
-        const int H = p.Hh;
-        int tokv = 0;
-        const float* crow = nullptr;
-        if (row_ok) {
-          tokv = p.tok[grow];
-          crow = p.cond + (grow % p.Bt) * p.Cc;
-        }
-        for (int c0 = ch_lo * 16; c0 < ch_hi * 16; c0 += 16) {
-          uint32_t r[16];
-          tc::tmem_ld16(taddr + c0, r);
-          tc::tmem_ld_wait();
-          const int n = n0 + c0;
-          if (row_ok && n < H) {
-            float dai[16], dag[16], dao[16];
-            const float* trow = p.table + (long)tokv * 3 * H + n;
-            float a3[3][16];
-#pragma unroll
-            for (int g = 0; g < 3; g++)
-#pragma unroll
-              for (int k4 = 0; k4 < 4; k4++) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(trow + g * H) + k4);
-                a3[g][4 * k4] = v.x; a3[g][4 * k4 + 1] = v.y; a3[g][4 * k4 + 2] = v.z; a3[g][4 * k4 + 3] = v.w;
-              }
-            if (p.Cc == 1) {
-              const float cv = __ldg(crow);
-#pragma unroll
-              for (int g = 0; g < 3; g++)
-#pragma unroll
-                for (int k4 = 0; k4 < 4; k4++) {
-                  const float4 w = __ldg(reinterpret_cast<const float4*>(p.wc + g * H + n) + k4);
-                  a3[g][4 * k4] = fmaf(cv, w.x, a3[g][4 * k4]); a3[g][4 * k4 + 1] = fmaf(cv, w.y, a3[g][4 * k4 + 1]);
-                  a3[g][4 * k4 + 2] = fmaf(cv, w.z, a3[g][4 * k4 + 2]); a3[g][4 * k4 + 3] = fmaf(cv, w.w, a3[g][4 * k4 + 3]);
-                }
-            } else {
-              for (int c = 0; c < p.Cc; c++) {
-                const float cv = __ldg(crow + c);
-#pragma unroll
-                for (int g = 0; g < 3; g++)
-#pragma unroll
-                  for (int k = 0; k < 16; k++)
-                    a3[g][k] = fmaf(cv, __ldg(p.wc + (long)(g * H + n + k) * p.Cc + c), a3[g][k]);
-              }
-            }
-#pragma unroll
-            for (int k = 0; k < 16; k++)
-              dec_cell_grads_fast(sigmoid_fast_(a3[0][k]), tanh_fast_(a3[1][k]), sigmoid_fast_(a3[2][k]),
-                                  __uint_as_float(r[k]), dai[k], dag[k], dao[k]);
-            bf16* dst = p.dg_out + grow * 3L * H + n;
-            store16_bf16(dst, dai);
-            store16_bf16(dst + H, dag);
-            store16_bf16(dst + 2 * H, dao);
-          }
-        }
       } else if (p.use_scratch) {
         // plain bf16 output, full tiles: this warp's half of the tile's columns, staged and written along the rows
         const int nb = (ch_hi - ch_lo) * 32;                    // bytes per row
@@ -668,15 +589,14 @@ int gemm_tc(const TcGemm& g, cudaStream_t st) {
   p.C = g.C; p.ldc = g.ldc; p.Cb = g.Cb; p.ldcb = g.ldcb; p.bias = g.bias; p.accumulate = g.accumulate ? 1 : 0;
   p.rm = g.rm;
   p.epi = g.epi; p.gates_b = g.gates_b; p.hb_out = g.hb_out; p.dg_out = g.dg_out;
-  p.table = g.table; p.wc = g.wc; p.tok = g.tok; p.cond = g.cond; p.Bt = g.Bt; p.Cc = g.Cc; p.Hh = g.Hh;
+  p.Hh = g.Hh;
   if (g.epi == TC_EPI_DEC_CELL_FWD) {
     ARCVAE_REQUIRE(g.N % 192 == 0 && g.Hh * 3 == g.N && !g.b_mn && g.bias != nullptr && g.gates_b && g.hb_out,
                    "fused decoder cell (forward): N = 3H tile-permuted, K-major B, bias");
     p.BN = 192; p.nt = g.N / 192;
-  } else if (g.epi == TC_EPI_DEC_CELL_BWD || g.epi == TC_EPI_DEC_CELL0_BWD) {
+  } else if (g.epi == TC_EPI_DEC_CELL_BWD) {
     ARCVAE_REQUIRE(g.N == g.Hh && g.Hh % 64 == 0 && g.dg_out != nullptr && p.splitk == 1, "fused decoder cell (backward): N = H");
-    ARCVAE_REQUIRE(g.epi != TC_EPI_DEC_CELL_BWD || g.gates_b != nullptr, "saved gates");
-    ARCVAE_REQUIRE(g.epi != TC_EPI_DEC_CELL0_BWD || (g.table && g.wc && g.tok && g.cond), "layer-0 recompute inputs");
+    ARCVAE_REQUIRE(g.gates_b != nullptr, "saved gates");
   }
   const size_t stage_bytes = (size_t)(p.bm2 ? 2 : 1) * TC_BM * TC_BK * 2 + (size_t)p.BN * TC_BK * 2;
   // transposition scratch for the fused cells and for plain bf16-only outputs of full, aligned tiles

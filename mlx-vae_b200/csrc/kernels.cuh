@@ -88,19 +88,15 @@ struct TcGemm {
   int epi = 0;                                  // TC_EPI_*
   __nv_bfloat16* gates_b = nullptr;             // [rows,3H] activated gates (written by CELL_FWD, read by CELL_BWD)
   __nv_bfloat16* hb_out = nullptr;              // [rows,H]  CELL_FWD: h
-  __nv_bfloat16* dg_out = nullptr;              // [rows,3H] CELL_BWD / CELL0_BWD: pre-activation gradients
-  const float* table = nullptr;                 // CELL0_BWD: [V,3H] layer-0 table (i|g|o)
-  const float* wc = nullptr;                    // CELL0_BWD: [3H,C]
-  const int32_t* tok = nullptr;                 // CELL0_BWD: [rows] tokens fed
-  const float* cond = nullptr;                  // CELL0_BWD: [Bt,C]
-  int Bt = 1, Cc = 0, Hh = 0;
+  __nv_bfloat16* dg_out = nullptr;              // [rows,3H] CELL_BWD: pre-activation gradients (same layout as gates_b)
+  int Hh = 0;
   // multi-segment B (nseg = 2 or 3): weight gradients that share the MN-major A operand (dA^T) run as ONE GEMM whose
   // column tile i multiplies with seg[i].B (row k of A pairs with row k - k_shift of B; rows before 0 count as zero)
   // and accumulates into seg[i].C — A is read from HBM once.  Requires a_mn, b_mn, accumulate.
   int nseg = 1;
   struct Seg { const __nv_bfloat16* B; int ldb; int N; int k_shift; float* C; int ldc; } seg[3] = {};
 };
-enum { TC_EPI_PLAIN = 0, TC_EPI_DEC_CELL_FWD = 1, TC_EPI_DEC_CELL_BWD = 2, TC_EPI_DEC_CELL0_BWD = 3 };
+enum { TC_EPI_PLAIN = 0, TC_EPI_DEC_CELL_FWD = 1, TC_EPI_DEC_CELL_BWD = 2 };
 int gemm_tc(const TcGemm& g, cudaStream_t st);
 int pick_splitk_tc(int M, int N, int K);
 int f32_to_bf16(const float* src, __nv_bfloat16* dst, long n, cudaStream_t st);
