@@ -381,12 +381,20 @@ def main():
         n = max(1.0, launches_cat["recurrence"])
         ach = flop / (t_ms * 1e-3) / 1e12
         tape = NL * R * (4 * H * 2 * 2 + H * 4 * 2 + H * 2 + 4 * H * 2 + H * 4)   # gates w+r, c w+r, h w, dA w, P/dX r (bf16/fp32 mix)
-        roofs["recurrence"] = {"kernel": "lstm_fwd2_kernel+lstm_bwd2_kernel", "bound": "tensor", "achieved": ach,
+        roofs["recurrence"] = {"kernel": "lstm_fwd2_kernel+lstm_bwd2_kernel" if H == 256 else "per-step gemm_tc_kernel + k_lstm_cell_*",
+                               "bound": "tensor", "achieved": ach,
                                "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"],
                                "traffic": traffic.get("recurrence"), "peak_source": pk["src"] + " (sustained bf16)",
                                "launches_per_step": n, "avg_launch_ms": t_ms / n, "ms_per_step": t_ms,
                                "share_of_step": t_ms / ms, "algorithmic_flop_per_launch": flop / n,
                                "hbm_tape_gbs": tape / (t_ms * 1e-3) / 1e9, "hbm_tape_frac": tape / (t_ms * 1e-3) / 1e9 / pk["hbm"],
+                               # cluster kernels (H = 256): per step and 128-row tile the tensor core reads the h / dA operand
+                               # tile (64 KB) and the resident W_hh slice (128 KB) from shared memory in each of the 4 CTAs;
+                               # the exchange moves 3 x 16 KB per CTA into peer shared memory (forward: TMA multicast) or
+                               # 3 x 16 KB of bf16 partials per CTA through L2 (backward)
+                               "smem_operand_gbs": (NL * 2 * T * ((B + 127) // 128) * 4 * 192 * 1024) / (t_ms * 1e-3) / 1e9 if H == 256 else None,
+                               "cluster_exchange_gbs": (NL * 2 * T * ((B + 127) // 128) * 4 * 48 * 1024) / (t_ms * 1e-3) / 1e9 if H == 256 else None,
+                               "us_per_timestep": 1e3 * t_ms / (NL * 2 * T),
                                "note": "latency-bound by construction (T sequential cluster exchanges); algorithmic FLOP = "
                                        "2*4H*H per row-step, forward + d h backward, both layers"}
     if "gemm_tc" in per_step:
