@@ -164,6 +164,22 @@ __global__ void k_init_dec_inputs(const int32_t* __restrict__ target, const uint
   }
 }
 
+struct IntChunk { int v[512]; };
+__global__ void k_write_ints(int* __restrict__ dst, IntChunk c, int n) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = c.v[i];
+}
+// small host arrays -> device through kernel parameters (2 KB per launch)
+static int upload_ints(int* dst, const int* src, int n, cudaStream_t st) {
+  for (int off = 0; off < n; off += 512) {
+    IntChunk c;
+    const int m = n - off < 512 ? n - off : 512;
+    for (int i = 0; i < m; i++) c.v[i] = src[off + i];
+    k_write_ints<<<1, 128, 0, st>>>(dst + off, c, m);
+    ARCVAE_LAUNCHED();
+  }
+  return 0;
+}
+
 // one batched pass of the decoder stack over the rows selected by `rm`
 static int dec_stack_forward(const arcvae_dims& d, const arcvae_decoder_params* p, const DecPrep& pr, const float* cond,
                              const int32_t* in_tok, int B, int nrows, RowMap rm, long rows_total, float* const* hd,
@@ -248,10 +264,14 @@ extern "C" int arcvae_decoder_forward(const arcvae_dims* d, const arcvae_decoder
     n_f[lv] = (int)lists.size() - off_f[lv];
   }
   ARCVAE_REQUIRE((int)lists.size() <= 2 * T + 2, "internal: list overflow");
-  ARCVAE_CUDA(cudaMemcpyAsync(tp.tlists, lists.data(), lists.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-  ARCVAE_CUDA(cudaMemcpyAsync(tp.mask, coin.data(), (size_t)T, cudaMemcpyHostToDevice, st));
-  // pageable-source async copies are staged before returning, but be explicit: the vectors die with this frame
-  ARCVAE_CUDA(cudaStreamSynchronize(st));
+  // the schedule travels as KERNEL ARGUMENTS (copied at launch): no host buffer has to outlive this call and, unlike a
+  // pageable cudaMemcpyAsync + synchronize, the host never waits for the stream, so a whole step can be enqueued ahead
+  ARCVAE_TRY(upload_ints(tp.tlists, lists.data(), (int)lists.size(), st));
+  {
+    std::vector<int> packed((T + 3) / 4, 0);
+    for (int t = 0; t < T; t++) packed[t >> 2] |= (int)coin[t] << (8 * (t & 3));
+    ARCVAE_TRY(upload_ints(reinterpret_cast<int*>(tp.mask), packed.data(), (int)packed.size(), st));
+  }
 
   ARCVAE_TRY(dec_prepare(*d, p, tp.prep, precision, st));
   {
