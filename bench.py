@@ -345,6 +345,7 @@ def main():
         sampler.start()
     ms, launches, last = timed(step_resident, args.steps)
     clocks = sampler.stop() if sampler else None
+    vae.encoder.check()          # the cluster kernels use bounded waits: a protocol time-out raises here instead of going unnoticed
     for _ in range(2):
         step_e2e()
     ms_e2e, _, loss_val = timed(step_e2e, args.steps)
