@@ -172,7 +172,7 @@ __device__ __forceinline__ float philox_normal(uint64_t seed, uint64_t ctr) {
   return sqrtf(-2.0f * logf(u1)) * cosf(6.283185307179586f * u2);
 }
 
-__global__ void __launch_bounds__(256, 3) k_loss_fused(LossArgs a) {
+__global__ void __launch_bounds__(256, 4) k_loss_fused(LossArgs a) {
   __shared__ double shd[8];
   const int L = a.L;
   double* st_mu = a.stats;            // [L]
