@@ -29,7 +29,7 @@ extern "C" {
 #endif
 
 #define ARCVAE_MAX_LAYERS 8
-#define ARCVAE_ABI_VERSION 1
+#define ARCVAE_ABI_VERSION 2
 
 /* model dimensions: train.py:26-31 (argparse defaults V80 E128 H256 L128 C1 NL2) */
 typedef struct {
@@ -116,8 +116,19 @@ int arcvae_encoder_backward(const arcvae_dims* d, const arcvae_encoder_params* p
                             const arcvae_encoder_params* g, void* scratch, size_t scratch_bytes, int precision,
                             void* stream);
 
-/* returns non-zero if a persistent cluster kernel of the last forward/backward hit a barrier time-out
- * (bounded waits instead of hangs).  Synchronises the stream.  Test / debug aid. */
+/* Error channel of the persistent kernels.  They wait with BOUNDED spins; a wait that runs out raises a STICKY
+ * per-device flag (the library never clears it) and the kernel's results are garbage.  arcvae_adam_step refuses to
+ * update while the flag is set, so a time-out cannot corrupt the weights; the host polls the flag when it wants
+ * (the trainer mirror: every N steps and at the end of an epoch).
+ *   arcvae_device_error_read : *flag_host = flag of the current device; synchronises `stream`
+ *   arcvae_device_error_clear: resets it (after the caller has dealt with the failure)
+ *   arcvae_debug_raise_device_error: test hook, raises it as a timed-out kernel would */
+int arcvae_device_error_read(int* flag_host, void* stream);
+int arcvae_device_error_clear(void* stream);
+int arcvae_debug_raise_device_error(void* stream);
+
+/* returns non-zero if the flag above is set (kept from ABI v1; the tape arguments are unused since v2).
+ * Synchronises the stream. */
 int arcvae_encoder_check(const arcvae_dims* d, int B, int T, void* tape, size_t tape_bytes, int precision, void* stream);
 
 /* debug aid: clock64 stamps of CTA 0 of the cluster kernels into buf[64*16] (device, int64); NULL switches it off */
@@ -165,7 +176,8 @@ int arcvae_sample(const arcvae_dims* d, const arcvae_decoder_params* p, const fl
                   float temperature, int early_stopping, int multinomial, uint64_t seed, int32_t* tokens,
                   int32_t* t_stop, void* workspace, size_t workspace_bytes, int precision, void* stream);
 
-/* ---- optimizer: mlx.optimizers.Adam as used by trainer.py:75-76, :320-324 (no bias correction) */
+/* ---- optimizer: mlx.optimizers.Adam as used by trainer.py:75-76, :320-324 (no bias correction).
+ * A no-op while the device error flag is set (see arcvae_device_error_read). */
 int arcvae_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2,
                      float eps, float grad_scale, void* stream);
 /* sum of squares of g into *out (device double, accumulated) — for clip_mode='global_norm' (not the reference's

@@ -68,6 +68,9 @@ SIGNATURES = {
                                           C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "arcvae_encoder_check": (C.c_int, [C.POINTER(Dims), C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "arcvae_debug_set_rc_stamps": (C.c_int, [C.c_void_p]),
+    "arcvae_device_error_read": (C.c_int, [C.POINTER(C.c_int), C.c_void_p]),
+    "arcvae_device_error_clear": (C.c_int, [C.c_void_p]),
+    "arcvae_debug_raise_device_error": (C.c_int, [C.c_void_p]),
     "arcvae_reparameterize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint64,
                                         C.c_void_p, C.c_void_p]),
     "arcvae_decoder_tape_bytes": (C.c_size_t, [C.POINTER(Dims), C.c_int, C.c_int]),
@@ -145,6 +148,23 @@ def timing_read():
     cnt = (C.c_int * 8)()
     check(load().arcvae_timing_read(ms, cnt, 8))
     return {k: (ms[i], cnt[i]) for i, k in enumerate(TIME_CATEGORIES)}
+
+
+def device_error_flag() -> int:
+    """The sticky per-device error flag of the persistent kernels (0 = healthy).  Synchronises the current stream."""
+    flag = C.c_int(0)
+    check(load().arcvae_device_error_read(C.byref(flag), stream_ptr()))
+    return int(flag.value)
+
+
+def check_device_error():
+    if device_error_flag() != 0:
+        raise ArcvaeError("a persistent cluster kernel reported a barrier time-out on this device: the results of that "
+                          "step are invalid and Adam updates are refused until arcvae_device_error_clear()")
+
+
+def clear_device_error():
+    check(load().arcvae_device_error_clear(stream_ptr()))
 
 
 def launch_count() -> int:

@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, Optional
 
 import torch
@@ -33,7 +34,8 @@ class Module:
         self._dims = _lib.Dims(**dims)
         self.params = FlatParams(spec, self.device)
         gen = torch.Generator()
-        gen.manual_seed(int(seed) if seed is not None else int(torch.seed() % (2 ** 31)))
+        # seed=None: fresh entropy WITHOUT touching torch's global generator (torch.seed() would reseed it)
+        gen.manual_seed(int(seed) if seed is not None else int.from_bytes(os.urandom(4), "little") % (2 ** 31))
         init_mlx_style(self.params, gen)
         self.grads = self.params.like()
         self.ws = Workspace(self.device)
@@ -91,7 +93,7 @@ class Module:
         return self
 
     def zero_grad(self):
-        _lib.check(_lib.load().arcvae_zero(self.grads.flat.data_ptr(), self.grads.flat.numel() * 4, _lib.stream_ptr()))
+        _lib.check(_lib.load().arcvae_zero(self.grads.storage.data_ptr(), self.grads.storage.numel() * 4, _lib.stream_ptr()))
 
     def num_parameters(self) -> int:
         import math

@@ -30,8 +30,15 @@ def _align(n, a=64):
     return (n + a - 1) // a * a
 
 
+AUX = 64  # floats appended to every flat buffer (not parameters: see FlatParams.aux)
+
+
 class FlatParams:
-    """Flat buffer + named views.  Every tensor starts at a 256-byte boundary."""
+    """Flat buffer + named views.  Every tensor starts at a 256-byte boundary.
+
+    ``storage`` = ``flat`` (the parameters, what Adam and the clip see) followed by ``aux``, AUX spare floats.  The
+    gradient copy of the decoder uses its aux tail to carry this rank's partial reconstruction loss through the SAME
+    all-reduce as the gradients (data parallelism: no extra collective for the loss values)."""
 
     def __init__(self, spec: Spec, device):
         self.spec = spec
@@ -41,14 +48,18 @@ class FlatParams:
             self.offsets[name] = (off, shape)
             off += _align(int(math.prod(shape)))
         self.numel = off
-        self.flat = torch.zeros(off, dtype=torch.float32, device=device)
+        self._alloc(torch.zeros(off + AUX, dtype=torch.float32, device=device))
+
+    def _alloc(self, storage):
+        self.storage = storage
+        self.flat = storage[:self.numel]
+        self.aux = storage[self.numel:]
         self.views = OrderedDict((n, self.flat[o:o + math.prod(s)].view(*s)) for n, (o, s) in self.offsets.items())
 
     def like(self):
         other = FlatParams.__new__(FlatParams)
         other.spec, other.offsets, other.numel = self.spec, self.offsets, self.numel
-        other.flat = torch.zeros_like(self.flat)
-        other.views = OrderedDict((n, other.flat[o:o + math.prod(s)].view(*s)) for n, (o, s) in self.offsets.items())
+        other._alloc(torch.zeros_like(self.storage))
         return other
 
     def tree(self):

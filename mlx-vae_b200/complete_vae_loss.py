@@ -12,7 +12,7 @@ from .losses._fused import fused_loss, make_hyper
 
 def _run(encoder, decoder, property_predictor, x, conditions, beta, lambda_prop, lambda_collapse,
          teacher_forcing_ratio, free_bits, lambda_mi, target_mi, eps, tf_mask, seed, pad_mask, backward, allreduce,
-         return_logits=False, backward_hooks=None):
+         return_logits=False, backward_hooks=None, eps_offset=0):
     if property_predictor is not None:
         # the reference would raise TypeError here (complete_vae_loss.py:63-67 vs losses/prop.py:5-11, F10)
         raise NotImplementedError("property_predictor must be None, as in train.py:186")
@@ -21,17 +21,23 @@ def _run(encoder, decoder, property_predictor, x, conditions, beta, lambda_prop,
                      tf_mask=tf_mask)                                                           # :42
     hp = make_hyper(beta, lambda_prop, lambda_collapse, free_bits, lambda_mi, target_mi, 4.85, pad_mask)
     targets = encoder._tokens(x)
-    out = fused_loss(logits, targets, mu, logvar, hp, eps=eps, seed=seed, pad_token=decoder.pad_token,
+    out = fused_loss(logits, targets, mu, logvar, hp, eps=eps, seed=seed, offset=eps_offset, pad_token=decoder.pad_token,
                      want_grads=backward, want_z=True, inplace_dlogits=backward and not return_logits,
                      allreduce=allreduce)                                                       # :39, :45-82
     d = {k: out.losses[i] for i, k in enumerate(_lib.LOSS_KEYS)}                                # :86-99
     d.update(mu=mu, logvar=logvar, z=out.z)
     if return_logits:
         d["logits"] = logits
+    if allreduce is not None and not backward:
+        # forward-only under data parallelism: the kernel reports local_CE / global_tokens (see trainer.train_step)
+        recon = d["recon_loss"].clone()
+        allreduce(recon.reshape(1))
+        d["recon_loss"] = recon
+        d["total_loss"] = recon + d["weighted_kl"] + d["collapse_penalty"] + d["weighted_prop_loss"] + d["mi_penalty"]
     if backward:
         decoder.backward(out.dlogits)
         if backward_hooks is not None:
-            backward_hooks.after_decoder_backward(decoder)
+            backward_hooks.after_decoder_backward(decoder, d)
         encoder.backward(out.dmu, out.dlogvar)
     return d
 

@@ -8,7 +8,9 @@ namespace arcvae {
 
 __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                               float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps,
-                                              float gscale) {
+                                              float gscale, const int* __restrict__ err) {
+  // a persistent kernel of this step timed out (sticky device flag): its gradients are garbage, keep the weights
+  if (err != nullptr && *err != 0) return;
   size_t n4 = n >> 2;
   size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -68,7 +70,7 @@ extern "C" int arcvae_adam_step(float* p, const float* g, float* m, float* v, si
   int grid = (int)((work + 255) / 256);
   if (grid > 148 * 8) grid = 148 * 8;
   TimeScope ts(TIME_ADAM, (cudaStream_t)stream);
-  k_adam<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, grad_scale);
+  k_adam<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, grad_scale, device_error_flag());
   ARCVAE_LAUNCHED();
   return 0;
 }

@@ -1,4 +1,5 @@
 // api.cu — process-wide plumbing of the C ABI: error string, launch counter, version.
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -7,6 +8,43 @@ namespace arcvae {
 static thread_local std::string g_error;
 std::atomic<uint64_t> g_launches{0};
 void set_error(const std::string& msg) { g_error = msg; }
+
+// ---- per-device state ------------------------------------------------------------------------------------------
+static constexpr int MAX_DEV = 64;
+static std::atomic<int> g_once[MAX_DEV][ONCE_NSLOTS];
+static std::atomic<int> g_sms[MAX_DEV];
+static std::atomic<int*> g_errflag[MAX_DEV];
+static std::mutex g_dev_mutex;
+static int cur_dev() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < MAX_DEV) ? dev : 0;
+}
+bool first_use_on_device(int slot) { return g_once[cur_dev()][slot].exchange(1) == 0; }
+int device_sm_count() {
+  const int dev = cur_dev();
+  int n = g_sms[dev].load();
+  if (n == 0) {
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+    g_sms[dev].store(n);
+  }
+  return n;
+}
+int* device_error_flag() {
+  const int dev = cur_dev();
+  int* p = g_errflag[dev].load();
+  if (p == nullptr) {
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
+    p = g_errflag[dev].load();
+    if (p == nullptr) {
+      if (cudaMalloc(&p, 256) != cudaSuccess) return nullptr;
+      cudaMemset(p, 0, 256);
+      g_errflag[dev].store(p);
+    }
+  }
+  return p;
+}
 
 // ---- per-category event timing -------------------------------------------------------------------------------
 static bool g_timing = false;
@@ -51,6 +89,31 @@ extern "C" int arcvae_timing_read(double* ms, int* counts, int ncat) {
     g_free.push_back(p);
   }
   g_pairs.clear();
+  return 0;
+}
+
+extern "C" int arcvae_device_error_read(int* flag, void* stream) {
+  using namespace arcvae;
+  ARCVAE_REQUIRE(flag != nullptr, "flag");
+  int* p = device_error_flag();
+  ARCVAE_REQUIRE(p != nullptr, "device error flag allocation failed");
+  ARCVAE_CUDA(cudaMemcpyAsync(flag, p, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  ARCVAE_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+extern "C" int arcvae_device_error_clear(void* stream) {
+  using namespace arcvae;
+  int* p = device_error_flag();
+  ARCVAE_REQUIRE(p != nullptr, "device error flag allocation failed");
+  ARCVAE_CUDA(cudaMemsetAsync(p, 0, sizeof(int), (cudaStream_t)stream));
+  return 0;
+}
+// test hook: raise the flag the way a timed-out kernel would
+extern "C" int arcvae_debug_raise_device_error(void* stream) {
+  using namespace arcvae;
+  int* p = device_error_flag();
+  ARCVAE_REQUIRE(p != nullptr, "device error flag allocation failed");
+  ARCVAE_CUDA(cudaMemsetAsync(p, 1, 1, (cudaStream_t)stream));
   return 0;
 }
 

@@ -45,6 +45,16 @@ extern std::atomic<uint64_t> g_launches;
     ARCVAE_CUDA(cudaGetLastError());                                                              \
   } while (0)
 
+// ---- per-device one-time state (the library is usable from several devices of one process) ----------------------
+// true exactly once per (slot, current device): guards cudaFuncSetAttribute calls and other per-device set-up
+enum { ONCE_GEMM_TC = 0, ONCE_REC1, ONCE_FWD2, ONCE_BWD2, ONCE_CELL0, ONCE_SCATTER_F32, ONCE_SCATTER_BF16, ONCE_SAMPLER,
+       ONCE_FWD1K, ONCE_BWD1K, ONCE_NSLOTS = 16 };
+bool first_use_on_device(int slot);
+int device_sm_count();            // multiprocessors of the current device (cached per device)
+// STICKY per-device error flag raised by the bounded waits of the persistent kernels; the library never clears it except
+// through arcvae_device_error_clear().  k_adam refuses to update while it is set.
+int* device_error_flag();
+
 // ---- optional per-category device timing (CUDA events on the launch stream; off by default) ------------------
 enum { TIME_GEMM_F32 = 0, TIME_RECURRENCE = 1, TIME_LOSS = 2, TIME_ADAM = 3, TIME_GEMM_TC = 4, TIME_POINTWISE = 5,
        TIME_SAMPLER = 6, TIME_NCAT = 8 };

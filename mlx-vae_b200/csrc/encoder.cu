@@ -273,7 +273,8 @@ extern "C" int arcvae_encoder_forward(const arcvae_dims* d, const arcvae_encoder
   }
 
   if (path == PATH_CLUSTER) {
-    ARCVAE_CUDA(cudaMemsetAsync(tp.err, 0, sizeof(int), st));
+    int* const errf = device_error_flag();      // sticky: raised by a bounded wait that ran out, never cleared here
+    ARCVAE_REQUIRE(errf != nullptr, "device error flag allocation failed");
     ARCVAE_TRY(f32_to_bf16(tp.table0, tp.table0b, (long)d->V * G4, st));
     for (int l = 0; l < d->NL; l++) {
       if (l >= 1) {
@@ -287,7 +288,7 @@ extern "C" int arcvae_encoder_forward(const arcvae_dims* d, const arcvae_encoder
         ARCVAE_TRY(gemm_tc(g, st));
       }
       ARCVAE_TRY(lstm_cluster_forward(B, T, H, tp.Whb[l], tp.xT, l == 0 ? tp.table0b : nullptr, l == 0 ? nullptr : tp.Pb,
-                                      tp.hb[l], tp.gates_b[l], tp.c[l], l == d->NL - 1 ? tp.h_last : nullptr, tp.err, st));
+                                      tp.hb[l], tp.gates_b[l], tp.c[l], l == d->NL - 1 ? tp.h_last : nullptr, errf, st));
     }
     return head_forward(*d, p, tp, tp.h_last, cond, B, mu, logvar, precision, st);
   }
@@ -344,17 +345,19 @@ extern "C" int arcvae_encoder_backward(const arcvae_dims* d, const arcvae_encode
     // weight gradients that share dA^T (dWh, dWx, bias / table scatter) run as ONE multi-segment GEMM per layer: dA is read
     // from HBM once.  The one-hot token operand serves the layer-0 table scatter AND, through its row sums, the bias
     // gradients of the upper layers.
+    int* const errf = device_error_flag();
+    ARCVAE_REQUIRE(errf != nullptr, "device error flag allocation failed");
     const bool fuse_dw = scatter_onehot_supported(G4, d->V, 0) && (H % 64) == 0 && H <= 256;
     if (fuse_dw) ARCVAE_TRY(build_onehot(tp.xT, R, d->V, nullptr, B, 0, sc.onehot, st));
     for (int l = d->NL - 1; l >= 0; l--) {
       const bool top = (l == d->NL - 1);
       if (std::getenv("ARCVAE_BWD_ALLGATHER") == nullptr) {
         ARCVAE_TRY(lstm_cluster_backward2(B, T, H, tp.Whb[l], tp.gates_b[l], tp.c[l], top ? nullptr : sc.dX,
-                                          top ? sc.du : nullptr, H2, sc.dAb, sc.xch, tp.err, st));
+                                          top ? sc.du : nullptr, H2, sc.dAb, sc.xch, errf, st));
       } else {
         ARCVAE_TRY(transpose_to_bf16(p->Wh[l], G4, H, tp.WhTb[l], st));          // WhT[h][gate] = Wh[gate][h]
         ARCVAE_TRY(lstm_cluster_backward(B, T, H, tp.WhTb[l], tp.gates_b[l], tp.c[l], top ? nullptr : sc.dX,
-                                         top ? sc.du : nullptr, H2, sc.dAb, tp.err, st));
+                                         top ? sc.du : nullptr, H2, sc.dAb, errf, st));
       }
       if (fuse_dw) {
         ARCVAE_CUDA(cudaMemsetAsync(sc.segtmp, 0, (size_t)G4 * SCATTER_NW * sizeof(float), st));
@@ -461,17 +464,15 @@ extern "C" int arcvae_encoder_backward(const arcvae_dims* d, const arcvae_encode
   return 0;
 }
 
-// raised by the cluster kernels' bounded waits (0 = healthy).  Synchronises the stream.
+// raised by the cluster kernels' bounded waits (0 = healthy).  Synchronises the stream.  Since ABI v2 the flag is the
+// sticky per-device one (arcvae_device_error_read); the tape arguments are kept for source compatibility.
 extern "C" int arcvae_encoder_check(const arcvae_dims* d, int B, int T, void* tape, size_t tape_bytes, int precision,
                                     void* stream) {
   ARCVAE_TRY(check_dims(d));
-  const int path = pick_path(*d, precision);
-  if (path != PATH_CLUSTER) return 0;
-  EncTape tp;
-  enc_tape_layout(*d, B, T, path, tape, tape_bytes, &tp);
+  (void)B; (void)T; (void)tape; (void)tape_bytes; (void)precision;
   int flag = 0;
-  ARCVAE_CUDA(cudaMemcpyAsync(&flag, tp.err, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-  ARCVAE_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
-  ARCVAE_REQUIRE(flag == 0, "cluster recurrence kernel reported a barrier time-out");
+  ARCVAE_TRY(arcvae_device_error_read(&flag, stream));
+  ARCVAE_REQUIRE(flag == 0, "cluster recurrence kernel reported a barrier time-out (sticky device flag; "
+                            "arcvae_device_error_clear() resets it)");
   return 0;
 }

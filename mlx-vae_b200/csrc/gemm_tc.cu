@@ -636,15 +636,9 @@ int gemm_tc(const TcGemm& g, cudaStream_t st) {
     tmB1 = tmB; tmB2 = tmB;
   }
 
-  static int num_sms = 0;
-  static bool attr = false;
-  if (!attr) {
-    int dev = 0;
-    ARCVAE_CUDA(cudaGetDevice(&dev));
-    ARCVAE_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  const int num_sms = device_sm_count();
+  if (first_use_on_device(ONCE_GEMM_TC))
     ARCVAE_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
-  }
   ARCVAE_REQUIRE(smem <= 227 * 1024, "gemm_tc shared memory budget");
   const int total = p.mt * p.nt * p.splitk;
   const int grid = total < num_sms ? total : num_sms;

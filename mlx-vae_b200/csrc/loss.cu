@@ -349,15 +349,17 @@ extern "C" int arcvae_loss_fwd_bwd(const float* logits, int64_t ls_b, int64_t ls
   a.hp = *hyper; a.seed = seed; a.offset = offset; a.phases = phases;
   a.stats = stats; a.losses = losses; a.dlogits = dlogits; a.dmu = dmu; a.dlogvar = dlogvar; a.z = z;
 
-  static int max_blocks = 0;
-  if (max_blocks == 0) {
-    int dev = 0, sms = 0, per = 0;
-    ARCVAE_CUDA(cudaGetDevice(&dev));
-    ARCVAE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  // co-resident blocks (cooperative launch): the kernel's occupancy is a property of the code (sm_100a only), the SM
+  // count is the current device's
+  static std::atomic<int> per_sm{0};
+  int per = per_sm.load();
+  if (per == 0) {
     ARCVAE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_loss_fused, 256, 0));
     if (per > 8) per = 8;
-    max_blocks = sms * (per > 0 ? per : 1);
+    if (per < 1) per = 1;
+    per_sm.store(per);
   }
+  const int max_blocks = device_sm_count() * per;
   long rows = (logits != nullptr) ? (long)B * T : 0;
   long want = (rows * 4 + 255) / 256;       // 4 lanes per row on the float4 path
   if (want < B) want = B;

@@ -1101,11 +1101,9 @@ static int launch_rec(bool bwd, const CUtensorMap& tmW, const CUtensorMap& tmX, 
   RecParams p = p_in;
   p.dbg = g_rc_dbg;
   const size_t smem = RC_W_BYTES + RC_NSTG * RC_STAGE_BYTES + 256 + 8 * 2560 + 1024;   // + RecShared + transpose scratch
-  static bool attr = false;
-  if (!attr) {
+  if (first_use_on_device(ONCE_REC1)) {
     ARCVAE_CUDA(cudaFuncSetAttribute(lstm_rec_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ARCVAE_CUDA(cudaFuncSetAttribute(lstm_rec_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
   }
   const int tiles = cdiv(p.B, RC_ROWS);
   cudaLaunchConfig_t cfg{};
@@ -1164,11 +1162,8 @@ static int lstm_cluster_forward2(int B, int T, int H, const bf16* Whb, const int
   p.err_flag = err_flag;
   p.dbg = g_rc_dbg;
   const size_t smem = RC_W_BYTES + RC_CL * RC_STAGE_BYTES + sizeof(Fwd2Shared) + 1024;
-  static bool attr = false;
-  if (!attr) {
+  if (first_use_on_device(ONCE_FWD2))
     ARCVAE_CUDA(cudaFuncSetAttribute(lstm_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
   return launch_cluster384((const void*)lstm_fwd2_kernel, smem, B, tmW, tmH, p, st);
 }
 
@@ -1203,11 +1198,8 @@ int lstm_cluster_backward2(int B, int T, int H, const bf16* Whb, const bf16* gat
   p.xch = reinterpret_cast<uint4*>(xch);
   p.dbg = g_rc_dbg;
   const size_t smem = RC_W_BYTES + 4 * RC_STAGE_BYTES + sizeof(Bwd2Shared) + 1024;
-  static bool attr = false;
-  if (!attr) {
+  if (first_use_on_device(ONCE_BWD2))
     ARCVAE_CUDA(cudaFuncSetAttribute(lstm_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(cdiv(B, RC_ROWS) * RC_CL);
   cfg.blockDim = dim3(RC_THREADS2);

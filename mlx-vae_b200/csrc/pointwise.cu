@@ -326,11 +326,8 @@ int dec_cell0_fwd(const float* table, const float* wc, const int32_t* tok, const
   ARCVAE_REQUIRE(gates_b == nullptr || (h == nullptr && (H % 64) == 0), "layer-0 gate tape: fused bf16 path, H % 64 == 0");
   const size_t smem_tab = (size_t)V * 3 * H * sizeof(__nv_bfloat16) + (size_t)3 * H * C * sizeof(float);
   if (h == nullptr && hb != nullptr && (H & 7) == 0 && V > 0 && smem_tab <= 200 * 1024 && (long)R * H >= (1L << 24)) {
-    static bool attr = false;
-    if (!attr) {
+    if (first_use_on_device(ONCE_CELL0))
       ARCVAE_CUDA(cudaFuncSetAttribute(k_dec_cell0_fwd_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr = true;
-    }
     k_dec_cell0_fwd_smem<<<148, 768, smem_tab, st>>>(table, wc, tok, cond, B, C, H, V, R, rm, hb, gates_b);
     ARCVAE_LAUNCHED();
     return 0;
@@ -634,11 +631,8 @@ static int scatter_t(const TIn* X, const int32_t* tok, long R, int N, int V, flo
   ARCVAE_REQUIRE(dwc == nullptr || C <= 4, "num_conditions > 4 not supported by the fused cond-weight reduction");
   size_t smem = (size_t)V * 128 * sizeof(float);
   ARCVAE_REQUIRE(smem <= 200 * 1024, "vocab too large for the smem scatter accumulator");
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (first_use_on_device(sizeof(TIn) == 4 ? ONCE_SCATTER_F32 : ONCE_SCATTER_BF16))
     ARCVAE_CUDA(cudaFuncSetAttribute(k_scatter_rows_by_token<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
   int gx = cdiv(N, 128);
   long want = (148L * 4 + gx - 1) / gx;
   long rpb = (R + want - 1) / want;

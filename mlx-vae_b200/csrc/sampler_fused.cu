@@ -460,15 +460,9 @@ int sampler_fused_run(const arcvae_dims& d, const float* table, const float* wc,
     const size_t smem = (size_t)(KP + (KP > VP ? KP : VP)) * SF_PANEL + (size_t)SF_STAGES * SF_STAGE_BYTES +
                         sizeof(SfShared) + 1024;
     ARCVAE_REQUIRE(smem <= 227 * 1024, "fused sampler shared-memory budget");
-    static bool attr = false;
-    static int num_sms = 148;
-    if (!attr) {
-      int dev = 0;
-      ARCVAE_CUDA(cudaGetDevice(&dev));
-      ARCVAE_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    const int num_sms = device_sm_count();
+    if (first_use_on_device(ONCE_SAMPLER))
       ARCVAE_CUDA(cudaFuncSetAttribute(sampler_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      attr = true;
-    }
     const int ntiles = cdiv(B, SF_ROWS);
     sampler_fused_kernel<<<ntiles < num_sms ? ntiles : num_sms, SF_THREADS, smem, st>>>(maps, p);
     ARCVAE_LAUNCHED();

@@ -50,8 +50,8 @@ class GradSync:
             w.wait()
         self._pending.clear()
 
-    def allreduce_losses(self, losses: torch.Tensor, weight: float):
-        """Average the per-rank scalar dict (mean of shard means weighted by shard size)."""
+    def broadcast(self, t: torch.Tensor, src: int = 0):
+        """Rank `src` of the group overwrites `t` everywhere (initial parameters / optimizer moments of the replicas)."""
         if self.enabled:
-            losses.mul_(weight)
-            dist.all_reduce(losses, op=dist.ReduceOp.SUM, group=self.group)
+            dist.broadcast(t, src=dist.get_global_rank(self.group, src) if self.group is not None else src,
+                           group=self.group)

@@ -39,7 +39,8 @@ class ARCVAETrainerWithLoss:
                  batch_size: int = 32, beta_start: float = 0.0, beta_end: float = 0.4, beta_warmup_epochs: int = 100,
                  lambda_prop: float = 0.1, lambda_collapse: float = 0.01, free_bits: float = 0.5,
                  lambda_mi: float = 0.01, grad_clip: float = 1.0, checkpoint_dir: str = "./checkpoints", *,
-                 clip_mode: str = "reference_noop", pad_mask: bool = False, process_group=None):
+                 clip_mode: str = "reference_noop", pad_mask: bool = False, process_group=None,
+                 broadcast_parameters: bool = True, error_check_every: int = 64):
         if clip_mode not in ("reference_noop", "global_norm"):
             raise ValueError("clip_mode must be 'reference_noop' or 'global_norm'")
         self.encoder, self.decoder, self.property_predictor, self.dataset = encoder, decoder, property_predictor, dataset
@@ -53,6 +54,17 @@ class ARCVAETrainerWithLoss:
         self.clip_mode, self.pad_mask = clip_mode, pad_mask
         self.sync = GradSync(process_group)
         self.step_count = 0
+        self.checkpoint_dir = checkpoint_dir                      # created on the first save (trainer.py:80-81 creates it eagerly)
+        self.history = {k: [] for k in ("epoch", "train_loss", "train_recon", "train_kl", "train_collapse", "train_prop",
+                                        "val_loss", "val_recon", "val_kl", "val_collapse", "val_prop", "beta",
+                                        "teacher_forcing", "learning_rate", "mutual_info")}       # trainer.py:84-100
+        self.error_check_every = int(error_check_every)
+        if self.sync.enabled and broadcast_parameters:
+            # replicas must start from ONE model: rank 0's parameters and Adam moments win (a seed=None construction
+            # initialises every rank differently)
+            for t in (encoder.params.flat, decoder.params.flat, self.encoder_optimizer.m, self.encoder_optimizer.v,
+                      self.decoder_optimizer.m, self.decoder_optimizer.v):
+                self.sync.broadcast(t)
 
     # ---- schedules (trainer.py:102-114) -----------------------------------------------------------------
     def compute_beta(self, epoch: int) -> float:
@@ -65,28 +77,42 @@ class ARCVAETrainerWithLoss:
 
     # ---- one optimizer step (trainer.py:305-333) ----------------------------------------------------------
     def train_step(self, molecules: torch.Tensor, conditions: torch.Tensor, beta: float, teacher_forcing_ratio: float,
-                   *, eps: Optional[torch.Tensor] = None, tf_mask=None, seed: Optional[int] = None) -> Dict[str, torch.Tensor]:
+                   *, eps: Optional[torch.Tensor] = None, tf_mask=None, seed: Optional[int] = None,
+                   global_row_start: Optional[int] = None) -> Dict[str, torch.Tensor]:
         """value_and_grad -> clip -> two Adam updates.  Returns the loss dict (0-d CUDA tensors; nothing is synced).
 
         Clipping: the reference's ``_clip_gradients`` sums only arrays at the top level of each gradient dict, every
         leaf is one level down, so the norm is 0 and nothing is ever scaled (trainer.py:502-514).
         ``clip_mode='reference_noop'`` reproduces that; ``'global_norm'`` is a real global-norm clip (one host sync).
-        Under data parallelism `molecules` is this rank's shard; losses and gradients are those of the GLOBAL batch."""
+
+        Data parallelism: ``molecules`` is this rank's shard.  Every scalar of the returned dict and every gradient is
+        that of the GLOBAL batch (what a single device would compute on the concatenated shards):
+          * KL / MI / penalties come from the all-reduced batch statistics inside the loss kernel;
+          * the kernel reports recon = (this rank's CE sum) / (global token count); the partial rides in the aux tail of
+            the decoder's flat gradient buffer through the gradient all-reduce and is summed there;
+          * the Philox draw of eps is indexed by the GLOBAL row (``global_row_start``, default rank x local batch: even
+            shards), so replicas do not repeat each other's noise and N ranks reproduce the single-device draw."""
         enc, dec, sync = self.encoder, self.decoder, self.sync
         enc.zero_grad()
         dec.zero_grad()
         if seed is None:
             seed = self.step_count
         dp = sync.enabled
+        if global_row_start is None:
+            global_row_start = sync.rank * int(molecules.shape[0])
         # forward + loss + decoder reverse pass; under DP the decoder gradients start their all-reduce while the
         # encoder BPTT is still being computed
         hooks = _DPHooks(sync) if dp else None
         d = _run(enc, dec, self.property_predictor, molecules, conditions, beta, self.lambda_prop, self.lambda_collapse,
                  teacher_forcing_ratio, self.free_bits, self.lambda_mi, 4.85, eps, tf_mask, seed, self.pad_mask, True,
-                 sync.allreduce_stats if dp else None, backward_hooks=hooks)
+                 sync.allreduce_stats if dp else None, backward_hooks=hooks,
+                 eps_offset=int(global_row_start) * enc.latent_dim)
         if dp:
             sync.allreduce_async(enc.grads.flat)
             sync.wait()
+            recon = dec.grads.aux[0].clone()                       # sum over ranks of local_CE / global_tokens
+            d["recon_loss"] = recon
+            d["total_loss"] = recon + d["weighted_kl"] + d["collapse_penalty"] + d["weighted_prop_loss"] + d["mi_penalty"]
         scale = 1.0
         if self.clip_mode == "global_norm" and self.grad_clip > 0:
             acc = torch.zeros(1, dtype=torch.float64, device=enc.device)
@@ -99,7 +125,15 @@ class ARCVAETrainerWithLoss:
         self.encoder_optimizer.update(scale)     # trainer.py:320
         self.decoder_optimizer.update(scale)     # trainer.py:324
         self.step_count += 1
+        if self.error_check_every > 0 and self.step_count % self.error_check_every == 0:
+            self.check_device_error()
         return d
+
+    def check_device_error(self):
+        """The persistent cluster kernels wait with bounded spins; a protocol time-out raises a STICKY per-device flag
+        (never cleared by the library) and the Adam kernel refuses to apply gradients while it is set, so the weights
+        are not corrupted.  This reads the flag (one 4-byte D2H, synchronises the stream) and raises."""
+        _lib.check_device_error()
 
     # ---- forward-only evaluation without teacher forcing (trainer.py:116-175, :418-487; SURVEY.md §8f row N3) --------
     def _eval_batches(self, dataset, beta: float, max_batches: Optional[int]) -> Dict[str, float]:
@@ -133,13 +167,25 @@ class ARCVAETrainerWithLoss:
         return self._eval_batches(val_dataset, beta, None)
 
     # ---- checkpoint interop (trainer.py:577-603, :685-736) ---------------------------------------
-    def save_checkpoint(self, path, epoch: int = 0) -> str:
+    def save_checkpoint(self, epoch: int, is_best: bool = False) -> str:
+        """trainer.py:577-597 call surface: writes ``<checkpoint_dir>/checkpoint_epoch_{epoch:03d}.npz`` and, with
+        ``is_best``, ``<checkpoint_dir>/checkpoint_best.npz``; returns the epoch file's path.  The FILE FORMAT is the flat
+        one of ``save_checkpoint_to`` (the reference pickles nested dicts of ``mx.array``)."""
+        import os
+        os.makedirs(str(self.checkpoint_dir), exist_ok=True)
+        if is_best:
+            self.save_checkpoint_to(os.path.join(str(self.checkpoint_dir), "checkpoint_best.npz"), epoch)
+        return self.save_checkpoint_to(os.path.join(str(self.checkpoint_dir), f"checkpoint_epoch_{int(epoch):03d}.npz"), epoch)
+
+    def save_checkpoint_to(self, path, epoch: int = 0) -> str:
         """Flat ``.npz`` with the reference's parameter names: ``encoder/<module>.<leaf>``,
         ``decoder/<module>.<leaf>``, Adam moments ``encoder_opt/m|v/<module>.<leaf>`` ..., ``epoch``.  The reference
         pickles nested dicts of ``mx.array`` (unreadable without MLX); ``tools/convert_mlx_checkpoint.py`` re-saves such
         a file in this flat format on a machine that has MLX."""
         import numpy as np
-        out = {"epoch": np.int64(epoch), "format": np.array("arcvae-flat-v1")}
+        import json
+        out = {"epoch": np.int64(epoch), "format": np.array("arcvae-flat-v1"),
+               "history_json": np.array(json.dumps(self.history))}
         for tag, mod, opt in (("encoder", self.encoder, self.encoder_optimizer), ("decoder", self.decoder, self.decoder_optimizer)):
             for name, view in mod.params.views.items():
                 out[f"{tag}/{name}"] = view.detach().cpu().numpy()
@@ -169,6 +215,9 @@ class ARCVAETrainerWithLoss:
                     key = f"{tag}_opt/{mom}/{name}"
                     if key in ck.files:
                         buf[beg:beg + n].copy_(torch.as_tensor(ck[key]).reshape(-1).to(buf.device))
+        if "history_json" in ck.files:
+            import json
+            self.history = json.loads(str(ck["history_json"]))
         return int(ck["epoch"]) if "epoch" in ck.files else 0
 
     def _train_epoch_batches(self, beta: float, teacher_forcing_ratio: float) -> Dict[str, float]:
@@ -178,6 +227,7 @@ class ARCVAETrainerWithLoss:
             d = self.train_step(molecules, conditions, beta, teacher_forcing_ratio)
             total += float(d["total_loss"])
             n += 1
+        self.check_device_error()
         return {"loss": total / max(1, n)}
 
 
@@ -187,5 +237,7 @@ class _DPHooks:
     def __init__(self, sync: GradSync):
         self.sync = sync
 
-    def after_decoder_backward(self, decoder):
-        self.sync.allreduce_async(decoder.grads.flat)
+    def after_decoder_backward(self, decoder, losses):
+        # this rank's partial reconstruction loss travels with the gradients (FlatParams.aux)
+        decoder.grads.aux[0:1].copy_(losses["recon_loss"].reshape(1))
+        self.sync.allreduce_async(decoder.grads.storage)

@@ -34,7 +34,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/arcvae_b200.h but not exported"
         assert n in mlx_vae_b200._lib.SIGNATURES, f"{n} has no ctypes signature"
-    assert lib.arcvae_abi_version() == 1
+    assert lib.arcvae_abi_version() == 2
 
 
 def test_sizing_entry_points_run_without_a_gpu(lib):

@@ -74,12 +74,18 @@ def test_checkpoint_roundtrip(M, tmp_path):
     tr = M.ARCVAETrainerWithLoss(enc, dec, None, None, learning_rate=1e-3, batch_size=8)
     x = torch.randint(0, 23, (8, 7), device="cuda"); c = torch.randn(8, 1, device="cuda")
     tr.train_step(x, c, 0.05, 0.9, tf_mask=np.ones(7, dtype=bool))
-    path = tr.save_checkpoint(tmp_path / "ck", epoch=3)
+    tr.checkpoint_dir = str(tmp_path / "ckdir")
+    tr.history["epoch"].append(3); tr.history["train_loss"].append(1.25)
+    path = tr.save_checkpoint(3, is_best=True)            # reference call surface (trainer.py:577)
+    import os
+    assert path.endswith("checkpoint_epoch_003.npz") and os.path.exists(os.path.join(tr.checkpoint_dir, "checkpoint_best.npz"))
     ck = np.load(path)
     assert "encoder/lstm_layer_0.Wh" in ck.files and "decoder/fc_out.weight" in ck.files and "encoder_opt/m/fc_mu.weight" in ck.files
     enc2 = M.MLXEncoder(**kw, seed=7); dec2 = M.MLXAutoregressiveDecoder(**kw, seed=8)
     tr2 = M.ARCVAETrainerWithLoss(enc2, dec2, None, None, learning_rate=1e-3, batch_size=8)
     assert tr2.load_checkpoint(path) == 3
+    assert tr2.history["epoch"] == [3] and tr2.history["train_loss"] == [1.25]
+    assert tr.save_checkpoint_to(tmp_path / "explicit", epoch=4).endswith("explicit.npz")
     assert torch.equal(enc2.params.flat, enc.params.flat) and torch.equal(dec2.params.flat, dec.params.flat)
     assert torch.equal(tr2.encoder_optimizer.m, tr.encoder_optimizer.m) and torch.equal(tr2.decoder_optimizer.v, tr.decoder_optimizer.v)
     a = tr.train_step(x, c, 0.05, 0.9, tf_mask=np.ones(7, dtype=bool), seed=5)

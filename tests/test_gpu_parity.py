@@ -153,8 +153,14 @@ def test_loss_two_phase_equals_fused(M):
     assert rel_err(dl.cpu(), full.dlogits.cpu()) < 1e-5
     assert rel_err(dm.cpu(), full.dmu.cpu()) < 1e-5
     for o in outs:
-        for k in ("kl_loss", "mutual_info", "mi_penalty", "collapse_penalty"):
+        for k in ("kl_loss", "mutual_info", "mi_penalty", "collapse_penalty", "weighted_kl"):
             assert abs(float(o.scalar(k)) - float(full.scalar(k))) < 1e-5
+    # every shard reports recon = (its CE sum) / (GLOBAL token count): the partials ADD UP to the global mean, and
+    # total = recon + the global terms (what trainer.train_step reassembles after the gradient all-reduce)
+    recon = sum(float(o.scalar("recon_loss")) for o in outs)
+    assert abs(recon - float(full.scalar("recon_loss"))) < 1e-5 * float(full.scalar("recon_loss"))
+    rest = sum(float(outs[0].scalar(k)) for k in ("weighted_kl", "collapse_penalty", "weighted_prop_loss", "mi_penalty"))
+    assert abs(recon + rest - float(full.scalar("total_loss"))) < 1e-5 * float(full.scalar("total_loss"))
 
 
 def test_philox_reparameterize(M):
