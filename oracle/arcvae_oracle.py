@@ -5,18 +5,21 @@ THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only ``tests/``,
 ``--impl reference`` legs may import it.  The shipped path
 (``mlx-vae_b200/``) never routes through this file and has no CPU fallback.
 
-PARITY UNPINNED.  The reference is pure Python over Apple MLX
-(``requirements.txt:193`` ``mlx>=0.11.0``); MLX is not importable in this image
-and cannot be installed (no network), the bundled dataset is absent
-(``.MISSING_LARGE_BLOBS:1``) and the reference holds no tests, golden vectors or
-known-answer fixtures for this path (its three diagnostic scripts print signs
-only).  This file is therefore a literal restatement of the reference's Python
-plus the published semantics of the MLX primitives it calls (``nn.LSTM``,
-``nn.Linear``, ``nn.Embedding``, ``optim.Adam``, ``mx.maximum``/``mx.argmax``),
-cross-validated by independent means in ``tests/test_oracle.py``
-(``torch.nn.LSTM``, finite differences, fp32-vs-fp64, the reference's implied
-invariants).  Fixtures under ``tests/golden/`` are generated by THIS oracle in
-fp64 (``oracle/make_golden.py``).
+PARITY: PINNED TO THE REFERENCE'S OWN PYTHON, MLX PRIMITIVES RESTATED.  The reference is pure Python over Apple
+MLX (``requirements.txt:193`` ``mlx>=0.11.0``); MLX is not importable in this image and cannot be installed (no
+network), the bundled dataset is absent (``.MISSING_LARGE_BLOBS:1``) and the reference holds no tests or golden
+vectors for this path.  What pins this file:
+  * ``tests/golden/ref_*.npz`` — outputs of the UNMODIFIED reference sources (models/*.py, losses/*.py,
+    complete_vae_loss.py, trainer.py, mlx_data/dataloader.py) executed under the ``mlx`` stand-in of
+    ``oracle/mlx_stub`` in fp64 (``oracle/make_ref_golden.py``); ``tests/test_ref_pin.py`` requires this oracle to
+    reproduce every entry (forward values, the 12-key loss dict, both gradient trees, the no-op clip, a 3-batch
+    trainer epoch with Adam, greedy tokens, dataset batches) to 1e-10, and re-runs the reference live where it is
+    mounted;
+  * ``tests/test_oracle.py`` — ``torch.nn.LSTM``, finite differences, fp32-vs-fp64, the reference's implied invariants,
+    Random123 known answers for Philox.
+What is still a restatement rather than a measurement: the MLX primitives the reference calls (``nn.LSTM``,
+``nn.Linear``, ``nn.Embedding``, ``optim.Adam`` without bias correction, the ``mx.maximum`` VJP tie rule,
+``mx.argmax`` tie-break, ``mx.value_and_grad`` over ``nn.Module`` trees) — SURVEY.md App. B; no MLX binary exists here.
 
 Every function cites the reference file:line it restates (paths relative to
 ``/root/reference``).  The arithmetic is written with torch CPU tensors so the

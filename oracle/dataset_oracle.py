@@ -1,6 +1,7 @@
 """TEST INFRASTRUCTURE — CPU restatement of the reference's data path (mlx_data/dataloader.py), NumPy only.
-Only tests/ may import this.  Parity unpinned: the reference holds no fixtures for it and MLX is not installable here;
-the restatement follows the file line by line (citations below)."""
+Only tests/ and oracle/ref_runner.py may import this.  Pinned by tests/test_ref_pin.py: the unmodified
+mlx_data/dataloader.py runs under oracle/mlx_stub and its normalised properties, padded items and shuffled ragged batches
+must equal this restatement's (tests/golden/ref_*.npz, keys ds/*)."""
 import numpy as np
 
 

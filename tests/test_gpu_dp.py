@@ -99,7 +99,9 @@ def test_two_ranks_equal_single_gpu_global_batch(dims, precision, B, T, tol):
         for k in ("penc", "pdec"):                # one Adam step of 1e-3 * O(3) on weights of O(0.2)
             assert _rel(o[k], ref[k]) <= (1e-4 if precision == "fp32" else 2e-2), (rank, k, _rel(o[k], ref[k]))
         lo, hi = o["lo_hi"]
-        assert np.array_equal(o["z"], ref["z"][lo:hi]), "Philox eps must be indexed by the global row"
+        # Philox eps is indexed by the GLOBAL row: the shard's z equals the single-device z up to the rounding of mu/logvar
+        # (a wrong offset gives unrelated N(0,1) draws, differences of O(1))
+        assert np.abs(o["z"] - ref["z"][lo:hi]).max() < (1e-4 if precision == "fp32" else 5e-2)
     # the replicas hold identical weights after the step
     assert np.array_equal(res[0]["penc"], res[1]["penc"]) and np.array_equal(res[0]["pdec"], res[1]["pdec"])
 
