@@ -26,7 +26,8 @@ DIMS = dict(vocab_size=80, embedding_dim=128, hidden_dim=256, latent_dim=128, nu
 HYPER = dict(beta=0.05, lambda_prop=0.1, lambda_collapse=0.001, free_bits=1.0, lambda_mi=0.01)
 LR = 2e-4
 B_PER_GPU, T = 4096, 128
-CPU_SAMPLE_B = 64
+CPU_SAMPLE_B = 256            # molecules per CPU step (the CPU figure may be taken at B >= 256 of the same workload)
+CPU_BUDGET_S = 240.0          # the reference arm shrinks its per-step sample if K+W steps would not fit this
 # algorithmic FLOP of the reference formulation
 FLOP_FWD_PER_MOLECULE = 128 * (1_835_008 + 829_440) + 786_944          # 341,836,288 at T=128
 FLOP_STEP_PER_MOLECULE = 3 * FLOP_FWD_PER_MOLECULE                     # fwd + bwd = 3x
@@ -114,27 +115,38 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvml"}
 
 
-def cpu_step_rate(steps, warmup, B=CPU_SAMPLE_B):
-    """molecules/s of the CPU restatement of the reference step (trainer.py:292-333) on this host's cores."""
+def cpu_step_rate(steps, warmup, B=CPU_SAMPLE_B, budget_s=None):
+    """molecules/s of the CPU restatement of the reference step (trainer.py:292-333: value_and_grad, no-op clip, two
+    Adam updates) on this host's cores, torch fp32, all threads.  Every step processes B molecules of the benched
+    workload (same dims, same T).  With `budget_s`, B is halved (not below 32) until warmup + steps fit the budget,
+    judged from the first step.  Returns (molecules/s, ms per step, threads, B used)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import torch
     import arcvae_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     cfg = O.Config(**DIMS)
-    params = O.init_params(cfg, seed=67, dtype=torch.float32)
-    state = O.adam_init(params)
-    x, cond, eps, tf_mask = O.synthetic_batch(B, T, cfg, seed=67, tf_ratio=0.9)
-    xt, ct, et = torch.as_tensor(x), torch.as_tensor(cond), torch.as_tensor(eps)
-    times = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        vals, grads, params, state = O.train_step(params, state, xt, ct, cfg.num_layers, et, tf_mask, LR,
-                                                  target_mi=4.85, **HYPER)
-        float(vals["total_loss"])
-        if i >= warmup:
-            times.append(time.perf_counter() - t0)
+    while True:
+        params = O.init_params(cfg, seed=67, dtype=torch.float32)
+        state = O.adam_init(params)
+        x, cond, eps, tf_mask = O.synthetic_batch(B, T, cfg, seed=67, tf_ratio=0.9)
+        xt, ct, et = torch.as_tensor(x), torch.as_tensor(cond), torch.as_tensor(eps)
+        times, shrink = [], False
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            vals, grads, params, state = O.train_step(params, state, xt, ct, cfg.num_layers, et, tf_mask, LR,
+                                                      target_mi=4.85, **HYPER)
+            float(vals["total_loss"])
+            dt = time.perf_counter() - t0
+            if i == 0 and budget_s is not None and dt * (warmup + steps) > budget_s and B > 32:
+                shrink = True
+                break
+            if i >= warmup:
+                times.append(dt)
+        if not shrink:
+            break
+        B //= 2
     ms = 1e3 * sum(times) / len(times)
-    return B / (ms / 1e3), ms, torch.get_num_threads()
+    return B / (ms / 1e3), ms, torch.get_num_threads(), B
 
 
 SAMPLE_B_PER_GPU, SAMPLE_T = 125_000, 128       # BASELINE configs[4]: 1M molecules over 8 GPUs, max length 128
@@ -196,22 +208,36 @@ def bench_sampler(M, vae, steps=3, warmup=1, B=SAMPLE_B_PER_GPU, T=SAMPLE_T, cpu
     return out
 
 
+def workload_config(args, B, world):
+    """The `config` object of the JSON line — identical in both arms (the driver compares them)."""
+    if args.config == "scaled":
+        wl = f"scaled AR-CVAE (V80 E128 H1024 L256 C1 NL3) full train step, B={B} x T={T} per GPU (configs[3]); global batch {B * world}"
+    else:
+        wl = f"default AR-CVAE (V80 E128 H256 L128 C1 NL2) full train step, B={B} x T={T} per GPU (configs[1]); global batch {B * world}"
+    return {"workload": wl, "parallelism": f"dp{world}", "teacher_forcing": 0.9,
+            "l2": "no explicit flush: every step streams >6 GB of activations (>> 126 MB L2)"}
+
+
 def run_reference(args):
+    """--impl reference: the reference's CPU path for the same metric and config.  MLX is not installable in this image,
+    so this times oracle/arcvae_oracle.py (pinned to the unmodified reference sources by tests/test_ref_pin.py), torch
+    fp32 on all host threads; exactly --steps timed steps after --warmup, each a bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = min(args.steps, 8), min(args.warmup, 2)
-    rate, ms, cores = cpu_step_rate(steps, max(1, warmup))
-    sample = f"B={CPU_SAMPLE_B} molecules per step of the B={B_PER_GPU} x T={T} workload (same dims), {steps} timed steps"
+    world = max(1, args.gpus)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    rate, ms, cores, b_used = cpu_step_rate(steps, warmup, budget_s=CPU_BUDGET_S)
+    sample = (f"{b_used} molecules per step (a slice of the B={args.batch} x T={T} batch, same dims and length), "
+              f"{steps} timed steps after {warmup} warm-up, torch fp32 eager on {cores} threads")
     line = {"impl": "reference", "metric": "AR-CVAE train molecules/s", "value": rate, "unit": "molecules/s",
-            "n_gpus": args.gpus, "steps": steps, "warmup": max(1, warmup), "ms_per_step": ms, "higher_is_better": True,
+            "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"default AR-CVAE (V80 E128 H256 L128 C1 NL2) full train step, B={B_PER_GPU} x T={T} per GPU "
-                                   f"(configs[1]); global batch {B_PER_GPU * max(1, args.gpus)}",
-                       "parallelism": f"dp{max(1, args.gpus)}", "teacher_forcing": 0.9, "cpu_sample": sample},
+            "config": workload_config(args, args.batch, world),
             "cpu_baseline": {"value": rate, "unit": "molecules/s", "cores": cores, "kind": "port", "sample": sample,
-                             "note": "MLX is not installable in this image; this is oracle/arcvae_oracle.py, a torch-CPU "
-                                     "fp32 restatement of the reference step"},
+                             "note": "MLX is not installable in this image; this is oracle/arcvae_oracle.py, the torch-CPU "
+                                     "restatement pinned to the unmodified reference sources (tests/test_ref_pin.py). "
+                                     "molecules/s of a CPU step is flat in B for B >= 64 (time is linear in B)"},
             "e2e": {"value": rate, "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -226,6 +252,7 @@ def main():
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-sampler", action="store_true", help="skip the sampled-molecules/s leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the fp32-mode and C1 (batch 64 through the dataset) legs")
     ap.add_argument("--workload", default="train", choices=["train", "sample"],
                     help="sample = BASELINE configs[4]: TPSA-conditioned sampling of 1M molecules sharded over the GPUs "
                          "(125k per GPU, max length 128, greedy and multinomial); prints its own JSON line")
@@ -345,19 +372,35 @@ def main():
         sampler.start()
     ms, launches, last = timed(step_resident, args.steps)
     clocks = sampler.stop() if sampler else None
-    vae.encoder.check()          # the cluster kernels use bounded waits: a protocol time-out raises here instead of going unnoticed
+    trainer.check_device_error()    # the cluster kernels use bounded waits: a protocol time-out raises here instead of going unnoticed
     for _ in range(2):
         step_e2e()
     ms_e2e, _, loss_val = timed(step_e2e, args.steps)
 
-    # instrumented pass: per-category device time (CUDA events on the launch stream around every launch scope)
+    # instrumented pass: per-category device time (CUDA events on the launch stream around every launch scope) and the
+    # tensor-core FLOP the library actually issued
     M._lib.timing_enable(True)
     M._lib.timing_read()
     nprof = min(args.steps, 3)
+    f0 = {k: M._lib.flop_count(k) for k in ("gemm_tc", "recurrence")}
     for _ in range(nprof):
         step_resident()
     cats = M._lib.timing_read()
+    executed = {k: (M._lib.flop_count(k) - f0[k]) / nprof for k in f0}
     M._lib.timing_enable(False)
+
+    # configs[2] as written: global batch 32768 at EVERY N (the headline line keeps 4096 per GPU = weak scaling)
+    configs2 = None
+    if args.config == "default" and world in (2, 4) and B == B_PER_GPU:
+        Bc = 32768 // world
+        cx, cc, ce, _ = synthetic_batch(Bc, T, seed=167 + rank, tf_ratio=0.9)
+        gx, gc, ge = (torch.as_tensor(a).cuda() for a in (cx, cc, ce))
+        for _ in range(3):
+            trainer.train_step(gx, gc, beta, tf, eps=ge, tf_mask=tf_mask)
+        ms_c2, _, _ = timed(lambda: trainer.train_step(gx, gc, beta, tf, eps=ge, tf_mask=tf_mask), min(args.steps, 5))
+        configs2 = {"global_batch": 32768, "per_gpu_batch": Bc, "ms_per_step": ms_c2, "value": 32768 / (ms_c2 * 1e-3),
+                    "unit": "molecules/s", "note": "BASELINE configs[2] (strong-scaling reading: fixed global batch)"}
+        del gx, gc, ge
 
     if rank != 0:
         if world > 1:
@@ -372,7 +415,7 @@ def main():
     # capture by profiles/scripts/summarize_ncu.py --traffic); only valid for the default B x T
     traffic = {}
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tpath) and B == B_PER_GPU:
+    if os.path.exists(tpath) and B == B_PER_GPU and args.config == "default":
         traffic = json.load(open(tpath))
     roofs = {}
     if "recurrence" in per_step:
@@ -382,12 +425,15 @@ def main():
         n = max(1.0, launches_cat["recurrence"])
         ach = flop / (t_ms * 1e-3) / 1e12
         tape = NL * R * (4 * H * 2 * 2 + H * 4 * 2 + H * 2 + 4 * H * 2 + H * 4)   # gates w+r, c w+r, h w, dA w, P/dX r (bf16/fp32 mix)
-        roofs["recurrence"] = {"kernel": "lstm_fwd2_kernel+lstm_bwd2_kernel" if H == 256 else "per-step gemm_tc_kernel + k_lstm_cell_*",
+        cluster = M._lib.load().arcvae_recurrence_is_persistent(H) != 0
+        roofs["recurrence"] = {"kernel": "lstm_fwd2_kernel+lstm_bwd2_kernel" if H == 256 else
+                                         ("lstm_wide_fwd_kernel+lstm_wide_bwd_kernel" if cluster else "per-step gemm_tc_kernel + k_lstm_cell_*"),
                                "bound": "tensor", "achieved": ach,
                                "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"],
                                "traffic": traffic.get("recurrence"), "peak_source": pk["src"] + " (sustained bf16)",
                                "launches_per_step": n, "avg_launch_ms": t_ms / n, "ms_per_step": t_ms,
                                "share_of_step": t_ms / ms, "algorithmic_flop_per_launch": flop / n,
+                               "executed_flop_per_step": executed.get("recurrence"),
                                "hbm_tape_gbs": tape / (t_ms * 1e-3) / 1e9, "hbm_tape_frac": tape / (t_ms * 1e-3) / 1e9 / pk["hbm"],
                                # cluster kernels (H = 256): per step and 128-row tile the tensor core reads the h / dA operand
                                # tile (64 KB) and the resident W_hh slice (128 KB) from shared memory in each of the 4 CTAs;
@@ -397,19 +443,26 @@ def main():
                                "cluster_exchange_gbs": (NL * 2 * T * ((B + 127) // 128) * 4 * 48 * 1024) / (t_ms * 1e-3) / 1e9 if H == 256 else None,
                                "us_per_timestep": 1e3 * t_ms / (NL * 2 * T),
                                "note": "latency-bound by construction (T sequential cluster exchanges); algorithmic FLOP = "
-                                       "2*4H*H per row-step, forward + d h backward, both layers"}
+                                       "2*4H*H per row-step, forward + d h backward, all layers"}
     if "gemm_tc" in per_step:
-        # time-parallel contractions: everything of SURVEY 8d's 3 x 341.8 MFLOP/molecule that is not the recurrence
+        # time-parallel contractions: everything of SURVEY 8d's 3 x 341.8 MFLOP/molecule that is not the recurrence.
+        # `achieved` / `frac` use the ALGORITHMIC FLOP of the reference formulation (tier contract); `executed_*` use what the
+        # tcgen05 GEMMs really issued (layer-0 projections are table gathers, the decoder's forget gate is never computed)
         flop = FLOP_STEP_PER_MOLECULE * B - NL * 2 * (2.0 * 4 * H * H) * R
-        t_ms = per_step["gemm_tc"] + per_step.get("gemm_f32", 0.0)
-        n = max(1.0, launches_cat.get("gemm_tc", 0) + launches_cat.get("gemm_f32", 0))
+        t_ms = per_step["gemm_tc"]
+        n = max(1.0, launches_cat.get("gemm_tc", 0))
         ach = flop / (t_ms * 1e-3) / 1e12
-        roofs["gemm"] = {"kernel": "gemm_tc_kernel(+gemm_f32_kernel)", "bound": "tensor", "achieved": ach,
-                         "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"],
-                         "traffic": traffic.get("gemm_tc"), "peak_source": pk["src"] + " (sustained bf16)",
-                         "launches_per_step": n, "avg_launch_ms": t_ms / n, "ms_per_step": t_ms, "share_of_step": t_ms / ms,
-                         "note": "K <= 768 projections are HBM-bound on B200 (2K FLOP per 2-byte output element, machine "
-                                 "balance ~210 FLOP/B); algorithmic FLOP of the reference formulation"}
+        ex = executed.get("gemm_tc", 0.0)
+        roofs["gemm_tc"] = {"kernel": "gemm_tc_kernel", "bound": "tensor", "achieved": ach,
+                            "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"],
+                            "executed_flop_per_step": ex, "executed_tflops": ex / (t_ms * 1e-3) / 1e12,
+                            "executed_frac": ex / (t_ms * 1e-3) / 1e12 / pk["bf16_sustained"],
+                            "traffic": traffic.get("gemm_tc"), "peak_source": pk["src"] + " (sustained bf16)",
+                            "launches_per_step": n, "avg_launch_ms": t_ms / n, "ms_per_step": t_ms, "share_of_step": t_ms / ms,
+                            "note": "K <= 768 projections are HBM-bound on B200 (2K FLOP per 2-byte output element, machine "
+                                    "balance ~210 FLOP/B); `frac` = algorithmic FLOP of the reference formulation (incl. work "
+                                    "this design does not execute), `executed_frac` = issued tensor FLOP; gemm_f32_kernel "
+                                    "time is NOT folded in"}
     if "loss" in per_step:
         t_ms = per_step["loss"]
         by = LOSS_BYTES_PER_MOLECULE * B
@@ -418,32 +471,46 @@ def main():
                          "frac": ach / pk["hbm"], "traffic": traffic.get("loss"), "peak_source": pk["src"],
                          "avg_launch_ms": t_ms, "share_of_step": t_ms / ms,
                          "note": "algorithmic bytes = logits read + dlogits write + tokens (SURVEY 8d: 82.4 KB/molecule)"}
-    dom = max(("recurrence", "gemm"), key=lambda k: roofs[k]["ms_per_step"] if k in roofs else -1.0) if roofs else None
+    # headline roofline = the category that takes the larger share of the step, nothing folded into either
+    dom = max(("recurrence", "gemm_tc"), key=lambda k: roofs[k]["ms_per_step"] if k in roofs else -1.0) if roofs else None
     roof = roofs.get(dom)
-    extra = {"per_category_ms": per_step, "rooflines": roofs}
+    whole = {"algorithmic_tflops": FLOP_STEP_PER_MOLECULE * B / (ms * 1e-3) / 1e12,
+             "algorithmic_frac_of_bf16_peak": FLOP_STEP_PER_MOLECULE * B / (ms * 1e-3) / 1e12 / pk["bf16_sustained"],
+             "executed_tflops": sum(executed.values()) / (ms * 1e-3) / 1e12,
+             "executed_frac_of_bf16_peak": sum(executed.values()) / (ms * 1e-3) / 1e12 / pk["bf16_sustained"]}
+    extra = {"per_category_ms": per_step, "rooflines": roofs, "whole_step": whole}
+    if configs2 is not None:
+        extra["configs2_global_32768"] = configs2
     if "loss" in roofs:
         extra["loss_kernel_gbs"] = roofs["loss"]["achieved"]
         extra["loss_kernel_frac_of_hbm_peak"] = roofs["loss"]["frac"]
 
+    # fp32 mode (north_star's 1e-3 path) on the same workload, and C1 = configs[0]: batch 64 through MoleculeDataset built
+    # from a ChEMBL-schema stand-in (the bundled JSON is absent from the reference mount)
+    if args.config == "default" and world == 1 and not args.no_extras:
+        try:
+            extra["fp32_mode"] = bench_fp32(M, B, dx, dc, de, tf_mask, beta, tf)
+        except Exception as e:  # noqa: BLE001
+            extra["fp32_mode"] = {"error": repr(e)}
+        try:
+            extra["c1_batch64_dataset"] = bench_c1(M, args.precision)
+        except Exception as e:  # noqa: BLE001
+            extra["c1_batch64_dataset"] = {"error": repr(e)}
+
     cpu = None
     if not args.no_cpu:
-        rate, cms, cores = cpu_step_rate(steps=4, warmup=1)
+        rate, cms, cores, b_used = cpu_step_rate(steps=4, warmup=1)
         cpu = {"value": rate, "unit": "molecules/s", "cores": cores, "kind": "port",
-               "sample": f"B={CPU_SAMPLE_B} molecules per step of the same workload (T={T}, same dims), 4 timed steps",
+               "sample": f"{b_used} molecules per step of the same workload (T={T}, same dims), 4 timed steps after 1 warm-up",
                "ms_per_step": cms,
-               "note": "MLX not installable here; oracle/arcvae_oracle.py torch-CPU fp32 restatement of the reference step"}
+               "note": "MLX not installable here; oracle/arcvae_oracle.py torch-CPU fp32 restatement of the reference step, "
+                       "pinned to the unmodified reference sources by tests/test_ref_pin.py"}
 
     h2d = hx.numel() * 4 + hc.numel() * 4 + he.numel() * 4
     line = {"metric": "AR-CVAE train molecules/s", "value": B * world / (ms * 1e-3), "unit": "molecules/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16",
-            "data": "synthetic",
-            "config": {"workload": (f"default AR-CVAE (V80 E128 H256 L128 C1 NL2) full train step, B={B} x T={T} per GPU "
-                                    f"(configs[1]); global batch {B * world}") if args.config == "default" else
-                                   (f"scaled AR-CVAE (V80 E128 H1024 L256 C1 NL3) full train step, B={B} x T={T} per GPU "
-                                    f"(configs[3]); global batch {B * world}"),
-                       "parallelism": f"dp{world}", "teacher_forcing": 0.9,
-                       "l2": "no explicit flush: every step streams >6 GB of activations (>> 126 MB L2)"},
+            "data": "synthetic", "config": workload_config(args, B, world),
             "e2e": {"value": B * world / (ms_e2e * 1e-3), "unit": "molecules/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
             "gpu_launches": launches, "gpu_launches_per_step": launches // args.steps, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
@@ -456,6 +523,69 @@ def main():
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_fp32(M, B, dx, dc, de, tf_mask, beta, tf, steps=2):
+    """The same step with precision='fp32' (every contraction as fp32 FFMA tiles, full-precision activations)."""
+    import torch
+    vae = M.ARCVAE(**DIMS, seed=67, precision="fp32")
+    tr = M.ARCVAETrainerWithLoss(vae.encoder, vae.decoder, None, None, learning_rate=LR, batch_size=B,
+                                 lambda_prop=HYPER["lambda_prop"], lambda_collapse=HYPER["lambda_collapse"],
+                                 free_bits=HYPER["free_bits"], lambda_mi=HYPER["lambda_mi"])
+    tr.train_step(dx, dc, beta, tf, eps=de, tf_mask=tf_mask)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        d = tr.train_step(dx, dc, beta, tf, eps=de, tf_mask=tf_mask)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    out = {"ms_per_step": ms, "value": B / (ms * 1e-3), "unit": "molecules/s", "steps": steps, "final_loss": float(d["total_loss"])}
+    del vae, tr
+    torch.cuda.empty_cache()
+    return out
+
+
+def bench_c1(M, precision, n_molecules=4096, batch=64, steps=40):
+    """BASELINE configs[0] on the GPU: default model, batch 64, batches drawn from MoleculeDataset.to_batches exactly as
+    trainer.py:303 does, data = a synthetic stand-in with the schema of mlx_data/chembl_cns_selfies.json
+    (train.py:79-124; the real file is absent from the reference mount).  Host coins (decoder.py:180) are drawn per step."""
+    import numpy as np
+    import torch
+    from mlx_vae_b200.data import load_splits, make_chembl_standin
+    np.random.seed(67)                                                        # train.py:75
+    train, val, _ = load_splits(make_chembl_standin(n_molecules, max_length=T))
+    vae = M.ARCVAE(**DIMS, seed=67, precision=precision)
+    tr = M.ARCVAETrainerWithLoss(vae.encoder, vae.decoder, None, train, learning_rate=LR, batch_size=batch,
+                                 lambda_prop=HYPER["lambda_prop"], lambda_collapse=HYPER["lambda_collapse"],
+                                 free_bits=HYPER["free_bits"], lambda_mi=HYPER["lambda_mi"])
+    beta, tfr = tr.compute_beta(0), tr.compute_teacher_forcing_ratio(0, 30)
+    it = train.to_batches(batch, shuffle=True)
+    for _ in range(5):
+        m, c = next(it)
+        tr.train_step(m, c, beta, tfr)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    n = 0
+    for m, c in it:
+        if n >= steps or m.shape[0] < batch:
+            break
+        d = tr.train_step(m, c, beta, tfr)
+        n += 1
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    ms = e0.elapsed_time(e1) / max(1, n)
+    tr.check_device_error()
+    val_loss = tr._validate(val, beta)
+    return {"workload": f"default model, batch {batch} x T={T} through MoleculeDataset.to_batches on a ChEMBL-schema synthetic "
+                        f"stand-in of {n_molecules} molecules (80/10/10 split, train-set normalisation), teacher forcing "
+                        f"{tfr} with host coins", "ms_per_step": ms, "value": batch / (ms * 1e-3), "unit": "molecules/s",
+            "steps": n, "wall_ms_per_step": 1e3 * wall / max(1, n), "final_loss": float(d["total_loss"]),
+            "val_loss_tf0": val_loss["loss"]}
 
 
 if __name__ == "__main__":

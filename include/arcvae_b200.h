@@ -94,6 +94,9 @@ const char* arcvae_last_error(void);
 int arcvae_abi_version(void);
 /* number of kernels this library has launched in the calling process (for bench.py's gpu_launches) */
 uint64_t arcvae_launch_count(void);
+/* tensor-core FLOP (2*M*N*K) this library has actually issued in the calling process for a timing category
+ * (4 = tcgen05 GEMMs, 1 = cluster recurrence): bench.py's executed-FLOP roofline fraction */
+double arcvae_flop_count(int category);
 int arcvae_zero(void* ptr, size_t bytes, void* stream);
 /* optional per-category device timing with CUDA events on the launch stream (bench.py's roofline leg).
  * categories: 0 fp32 GEMM, 1 recurrence, 2 fused loss, 3 Adam, 4 tcgen05 GEMM, 5 pointwise, 6 sampler.
@@ -115,6 +118,10 @@ int arcvae_encoder_backward(const arcvae_dims* d, const arcvae_encoder_params* p
                             const float* dmu, const float* dlogvar, void* tape, size_t tape_bytes,
                             const arcvae_encoder_params* g, void* scratch, size_t scratch_bytes, int precision,
                             void* stream);
+
+/* 1 if the bf16 encoder recurrence for hidden size H runs as ONE persistent kernel per layer and direction (W_hh resident
+ * on chip for all T steps), 0 if it falls back to one tcgen05 GEMM + cell launch per timestep */
+int arcvae_recurrence_is_persistent(int H);
 
 /* Error channel of the persistent kernels.  They wait with BOUNDED spins; a wait that runs out raises a STICKY
  * per-device flag (the library never clears it) and the kernel's results are garbage.  arcvae_adam_step refuses to

@@ -56,6 +56,7 @@ SIGNATURES = {
     "arcvae_last_error": (C.c_char_p, []),
     "arcvae_abi_version": (C.c_int, []),
     "arcvae_launch_count": (C.c_uint64, []),
+    "arcvae_flop_count": (C.c_double, [C.c_int]),
     "arcvae_zero": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p]),
     "arcvae_timing_enable": (C.c_int, [C.c_int]),
     "arcvae_timing_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]),
@@ -68,6 +69,7 @@ SIGNATURES = {
                                           C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "arcvae_encoder_check": (C.c_int, [C.POINTER(Dims), C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "arcvae_debug_set_rc_stamps": (C.c_int, [C.c_void_p]),
+    "arcvae_recurrence_is_persistent": (C.c_int, [C.c_int]),
     "arcvae_device_error_read": (C.c_int, [C.POINTER(C.c_int), C.c_void_p]),
     "arcvae_device_error_clear": (C.c_int, [C.c_void_p]),
     "arcvae_debug_raise_device_error": (C.c_int, [C.c_void_p]),
@@ -165,6 +167,10 @@ def check_device_error():
 
 def clear_device_error():
     check(load().arcvae_device_error_clear(stream_ptr()))
+
+
+def flop_count(category: str) -> float:
+    return float(load().arcvae_flop_count(TIME_CATEGORIES.index(category)))
 
 
 def launch_count() -> int:

@@ -46,6 +46,9 @@ int* device_error_flag() {
   return p;
 }
 
+static std::atomic<uint64_t> g_flops[TIME_NCAT];      // in MFLOP to stay integral
+void count_flops(int cat, double flop) { g_flops[cat].fetch_add((uint64_t)(flop * 1e-6), std::memory_order_relaxed); }
+
 // ---- per-category event timing -------------------------------------------------------------------------------
 static bool g_timing = false;
 struct Pair { cudaEvent_t a, b; int cat; };
@@ -115,6 +118,11 @@ extern "C" int arcvae_debug_raise_device_error(void* stream) {
   ARCVAE_REQUIRE(p != nullptr, "device error flag allocation failed");
   ARCVAE_CUDA(cudaMemsetAsync(p, 1, 1, (cudaStream_t)stream));
   return 0;
+}
+
+extern "C" double arcvae_flop_count(int category) {
+  if (category < 0 || category >= arcvae::TIME_NCAT) return 0.0;
+  return (double)arcvae::g_flops[category].load() * 1e6;
 }
 
 extern "C" const char* arcvae_last_error(void) { return arcvae::g_error.c_str(); }

@@ -58,6 +58,8 @@ int* device_error_flag();
 // ---- optional per-category device timing (CUDA events on the launch stream; off by default) ------------------
 enum { TIME_GEMM_F32 = 0, TIME_RECURRENCE = 1, TIME_LOSS = 2, TIME_ADAM = 3, TIME_GEMM_TC = 4, TIME_POINTWISE = 5,
        TIME_SAMPLER = 6, TIME_NCAT = 8 };
+// executed tensor-core FLOP (2*M*N*K of every tcgen05 GEMM / recurrence launch), for bench.py's executed-FLOP fraction
+void count_flops(int cat, double flop);
 void timing_begin(int cat, cudaStream_t st);
 void timing_end(int cat, cudaStream_t st);
 struct TimeScope {

@@ -37,7 +37,6 @@ struct EncTape {
   float* mu;         // [B,L]
   float* logvar;     // [B,L]
   float* h_last;     // [B,H]   h_{T-1} of the top layer (cluster path)
-  int* err;          // device flag raised by the cluster kernels' bounded waits
   float* c[ARCVAE_MAX_LAYERS];      // [T*B,H] fp32 cell state (all paths)
   // per-step paths
   float* gates[ARCVAE_MAX_LAYERS];  // [T*B,4H]  activated gates after forward, dA after backward
@@ -48,7 +47,6 @@ struct EncTape {
   bf16* Wxb[ARCVAE_MAX_LAYERS];     // [4H,H], l >= 1
   // cluster path
   bf16* gates_b[ARCVAE_MAX_LAYERS]; // [T*B,4H] activated gates
-  bf16* WhTb[ARCVAE_MAX_LAYERS];    // [H,4H]
   // bf16 operands of the tensor-core head products (bf16 paths)
   bf16* ub;          // [B,2H]
   bf16* lvhb;        // [B,2H]
@@ -72,7 +70,6 @@ static size_t enc_tape_layout(const arcvae_dims& d, int B, int T, int path, void
   tt.mu = a.take<float>((size_t)B * d.L);
   tt.logvar = a.take<float>((size_t)B * d.L);
   tt.h_last = a.take<float>((size_t)B * H);
-  tt.err = a.take<int>(4);
   if (path != PATH_STEP_F32) {
     tt.ub = a.take<bf16>((size_t)B * 2 * H);
     tt.lvhb = a.take<bf16>((size_t)B * 2 * H);
@@ -94,7 +91,6 @@ static size_t enc_tape_layout(const arcvae_dims& d, int B, int T, int path, void
     }
     if (path == PATH_CLUSTER) {
       tt.gates_b[l] = a.take<bf16>(Rpad * 4 * H);
-      tt.WhTb[l] = a.take<bf16>(4 * H * H);
     }
   }
   if (path == PATH_CLUSTER) {
@@ -351,14 +347,8 @@ extern "C" int arcvae_encoder_backward(const arcvae_dims* d, const arcvae_encode
     if (fuse_dw) ARCVAE_TRY(build_onehot(tp.xT, R, d->V, nullptr, B, 0, sc.onehot, st));
     for (int l = d->NL - 1; l >= 0; l--) {
       const bool top = (l == d->NL - 1);
-      if (std::getenv("ARCVAE_BWD_ALLGATHER") == nullptr) {
-        ARCVAE_TRY(lstm_cluster_backward2(B, T, H, tp.Whb[l], tp.gates_b[l], tp.c[l], top ? nullptr : sc.dX,
-                                          top ? sc.du : nullptr, H2, sc.dAb, sc.xch, errf, st));
-      } else {
-        ARCVAE_TRY(transpose_to_bf16(p->Wh[l], G4, H, tp.WhTb[l], st));          // WhT[h][gate] = Wh[gate][h]
-        ARCVAE_TRY(lstm_cluster_backward(B, T, H, tp.WhTb[l], tp.gates_b[l], tp.c[l], top ? nullptr : sc.dX,
-                                         top ? sc.du : nullptr, H2, sc.dAb, errf, st));
-      }
+      ARCVAE_TRY(lstm_cluster_backward2(B, T, H, tp.Whb[l], tp.gates_b[l], tp.c[l], top ? nullptr : sc.dX,
+                                        top ? sc.du : nullptr, H2, sc.dAb, sc.xch, errf, st));
       if (fuse_dw) {
         ARCVAE_CUDA(cudaMemsetAsync(sc.segtmp, 0, (size_t)G4 * SCATTER_NW * sizeof(float), st));
         TcGemm q{};
@@ -463,6 +453,8 @@ extern "C" int arcvae_encoder_backward(const arcvae_dims* d, const arcvae_encode
   }
   return 0;
 }
+
+extern "C" int arcvae_recurrence_is_persistent(int H) { return lstm_cluster_supported(H) ? 1 : 0; }
 
 // raised by the cluster kernels' bounded waits (0 = healthy).  Synchronises the stream.  Since ABI v2 the flag is the
 // sticky per-device one (arcvae_device_error_read); the tape arguments are kept for source compatibility.

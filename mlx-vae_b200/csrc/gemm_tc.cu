@@ -643,6 +643,12 @@ int gemm_tc(const TcGemm& g, cudaStream_t st) {
   const int total = p.mt * p.nt * p.splitk;
   const int grid = total < num_sms ? total : num_sms;
   TimeScope ts(TIME_GEMM_TC, st);
+  {
+    double ncols = 0.0;
+    if (g.nseg > 1) for (int i = 0; i < g.nseg; i++) ncols += g.seg[i].N;
+    else ncols = g.N;
+    count_flops(TIME_GEMM_TC, 2.0 * g.M * ncols * g.K);
+  }
   gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmB1, tmB2, p);
   ARCVAE_LAUNCHED();
   return 0;

@@ -108,9 +108,6 @@ bool lstm_cluster_supported(int H);
 int lstm_cluster_forward(int B, int T, int H, const __nv_bfloat16* Whb, const int32_t* xT, const __nv_bfloat16* table0b,
                          const __nv_bfloat16* Pb, __nv_bfloat16* hb, __nv_bfloat16* gates_b, float* c, float* h_last,
                          int* err_flag, cudaStream_t st);
-int lstm_cluster_backward(int B, int T, int H, const __nv_bfloat16* WhTb, const __nv_bfloat16* gates_b, const float* c,
-                          const float* dh_ext, const float* dh_last, int dh_last_ld, __nv_bfloat16* dAb, int* err_flag,
-                          cudaStream_t st);
 // K-split backward: every CTA multiplies its own dA slice, partial d h reduce-scattered through `xch`
 size_t lstm_cluster_xch_bytes(int B);
 int lstm_cluster_backward2(int B, int T, int H, const __nv_bfloat16* Whb, const __nv_bfloat16* gates_b, const float* c,

@@ -124,352 +124,6 @@ __device__ __forceinline__ float sigmoid_fast(float x) { return sigmoid_approx_(
 
 #define RC_STAMP(slot) do { if (p.dbg != nullptr && blockIdx.x < 4 && it < 64) { unsigned long long _gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_gt)); p.dbg[(blockIdx.x * 64 + it) * 16 + (slot)] = (long long)_gt; } } while (0)
 
-template <bool BWD>
-__global__ void __launch_bounds__(RC_THREADS, 1)
-lstm_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, const RecParams p) {
-  constexpr int NCH = BWD ? 16 : 4;        // 64-wide K chunks per step
-  constexpr int BN = BWD ? 64 : 256;       // accumulator columns = MMA N
-  constexpr int WPANEL = BN * 128;         // bytes of one K-panel of the resident weight slice
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* Wsm = smem;
-  uint8_t* ring = smem + RC_W_BYTES;
-  RecShared* sh = reinterpret_cast<RecShared*>(ring + RC_NSTG * RC_STAGE_BYTES);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rank = (int)rc::cluster_ctarank();
-  const int tile = blockIdx.x / RC_CL;
-  const int row0 = tile * RC_ROWS;
-  const int B = p.B, T = p.T, H = p.H;
-  const uint16_t ALL = (uint16_t)((1u << RC_CL) - 1);
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < RC_NSTG; s++) {
-      tc::mbar_init(&sh->full[s], 1);
-      tc::mbar_init(&sh->empty[s], RC_CL);
-    }
-    tc::mbar_init(&sh->w_ready, 1);
-    tc::mbar_init(&sh->acc_full, 1);
-    tc::mbar_init(&sh->epi_done, 8);
-    sh->failed = 0;
-    tc::fence_barrier_init();
-    tc::prefetch_tmap(&tmW);
-    tc::prefetch_tmap(&tmX);
-  }
-  if (warp == 9) tc::tmem_alloc(&sh->tmem_base, BN);
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  rc::cluster_sync_all();                    // every CTA's barriers exist before any multicast / remote arrive
-  const uint32_t tmem_base = sh->tmem_base;
-
-  if (warp == 8) {
-    // =========================================================== control: weights once, then the MMAs of every step
-    if (lane == 0) {
-      tc::mbar_expect_tx(&sh->w_ready, RC_W_BYTES);
-      if (!BWD) {
-        for (int kp = 0; kp < 4; kp++)
-          for (int g = 0; g < 4; g++)
-            tc::tma_load_2d(Wsm + kp * WPANEL + g * 8192, &tmW, &sh->w_ready, 64 * kp, g * H + 64 * rank);
-      } else {
-        for (int kq = 0; kq < 16; kq++) tc::tma_load_2d(Wsm + kq * WPANEL, &tmW, &sh->w_ready, 64 * kq, 64 * rank);
-      }
-      bool ok = rc::wait_or_fail(&sh->w_ready, 0, sh);
-      const uint32_t idesc = tc::make_idesc_bf16(RC_ROWS, BN, false, false);
-      uint32_t use[RC_NSTG] = {0, 0, 0, 0};
-      for (int it = 1; it < T && ok; it++) {
-        if (!BWD) {
-          // all four chunks of h_{t-1}: arm every slot first, then wait, then one uninterrupted burst of 16 MMAs
-#pragma unroll
-          for (int s = 0; s < RC_NSTG; s++) tc::mbar_expect_tx(&sh->full[s], RC_STAGE_BYTES);
-#pragma unroll
-          for (int s = 0; s < RC_NSTG; s++) {
-            ok = ok && rc::wait_or_fail(&sh->full[s], use[s] & 1, sh);
-            if (s == 0) RC_STAMP(0);
-          }
-          RC_STAMP(1);
-          if (!ok) break;
-          tc::tc_fence_after();
-#pragma unroll
-          for (int kq = 0; kq < NCH; kq++) {
-            const uint32_t a_addr = tc::smem_u32(ring + kq * RC_STAGE_BYTES);
-            const uint32_t b_addr = tc::smem_u32(Wsm + kq * WPANEL);
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-              tc::mma_bf16(tmem_base, tc::make_smem_desc(a_addr + 32 * j, 16, 1024),
-                           tc::make_smem_desc(b_addr + 32 * j, 16, 1024), idesc, (kq > 0 || j > 0) ? 1u : 0u);
-          }
-#pragma unroll
-          for (int s = 0; s < RC_NSTG; s++) {
-            rc::mma_commit_mc(&sh->empty[s], ALL);
-            use[s]++;
-          }
-        } else {
-          for (int kq = 0; kq < NCH && ok; kq++) {
-            const int s = kq % RC_NSTG;
-            tc::mbar_expect_tx(&sh->full[s], RC_STAGE_BYTES);          // arm this use (bytes may already have landed)
-            ok = rc::wait_or_fail(&sh->full[s], use[s] & 1, sh);
-            if (!ok) break;
-            if (kq == 0) RC_STAMP(0);
-            if (kq == NCH - 1) RC_STAMP(1);
-            tc::tc_fence_after();
-            const uint32_t a_addr = tc::smem_u32(ring + s * RC_STAGE_BYTES);
-            const uint32_t b_addr = tc::smem_u32(Wsm + kq * WPANEL);
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-              tc::mma_bf16(tmem_base, tc::make_smem_desc(a_addr + 32 * j, 16, 1024),
-                           tc::make_smem_desc(b_addr + 32 * j, 16, 1024), idesc, (kq > 0 || j > 0) ? 1u : 0u);
-            rc::mma_commit_mc(&sh->empty[s], ALL);                     // slot free in ALL CTAs once these MMAs retire
-            use[s]++;
-          }
-        }
-        if (ok) tc::mma_commit(&sh->acc_full);
-        RC_STAMP(2);
-      }
-    }
-  } else if (warp == 9) {
-    // =========================================================== sender: multicast this CTA's fresh chunk(s)
-    if (lane == 0) {
-      uint32_t sent = 0;
-      bool ok = true;
-      for (int it = 0; it < T - 1 && ok; it++) {
-        ok = rc::wait_or_fail(&sh->epi_done, it & 1, sh);
-        if (!ok) break;
-        RC_STAMP(8);
-        const int t = BWD ? (T - 1 - it) : it;
-        for (int g = 0; g < NCH / RC_CL && ok; g++) {
-          if (sent > 0) ok = rc::wait_or_fail(&sh->empty[rank], (sent - 1) & 1, sh);
-          if (!ok) break;
-          const int col = (BWD ? g * H : 0) + 64 * rank;
-          rc::tma_load_2d_mc(ring + rank * RC_STAGE_BYTES, &tmX, &sh->full[rank], col, t * B + row0, ALL);
-          sent++;
-        }
-        RC_STAMP(9);
-      }
-    }
-  } else {
-    // =========================================================== epilogue: gate math, state in registers
-    const int q = warp & 3;                  // TMEM lane quarter this warp may read
-    const int hs = warp >> 2;                // which 32 of the CTA's 64 hidden units
-    const int row = row0 + q * 32 + lane;
-    const bool valid = row < B;
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const int ub = 64 * rank + hs * 32;      // first global hidden unit of this thread
-    const int ntiles = gridDim.x / RC_CL;
-    // Tape layout ("thread friendly"): the gates / cell-state tape is written by the forward kernel and read back only
-    // by the backward kernel with the SAME thread <-> (row, unit) mapping, so it is stored as
-    // [t][tile][rank][q][hs][...][lane][16 B]: a warp-wide 16-byte access is 512 contiguous bytes (4 wavefronts)
-    // instead of 32 scattered sectors of a row-major [row][4H] layout.
-    const long warp_slot = ((((long)tile * RC_CL + rank) * 4 + q) * 2 + hs);
-    const long slots_per_t = (long)ntiles * RC_CL * 4 * 2;
-    auto gate_tape = [&](int tt, int g, int cu) -> uint4* {        // 16 uint4-vectors per thread per step
-      return reinterpret_cast<uint4*>(p.gates_b) + (((long)tt * slots_per_t + warp_slot) * 16 + g * 4 + cu) * 32 + lane;
-    };
-    auto c_tape = [&](int tt, int i) -> float4* {                    // 8 float4 per thread per step
-      return reinterpret_cast<float4*>(p.c) + (((long)tt * slots_per_t + warp_slot) * 8 + i) * 32 + lane;
-    };
-    // per-warp smem scratch [32 rows][80 B] for the row-major outputs the GEMMs / TMA need (hb, dAb): the thread=row
-    // data is transposed so that 4 lanes cover the 64 contiguous bytes of one row (8 rows, 8 wavefronts per store)
-    uint8_t* scratch = reinterpret_cast<uint8_t*>(sh) + 256 + warp * 2560;
-    auto store_rowmajor = [&](const uint4 (&v)[4], bf16* base, long ld, int tt) {
-      // v[c] = this row's units [8c, 8c+8) of the thread's 32; base -> element (row 0 of the timestep, unit ub)
-      __syncwarp();
-#pragma unroll
-      for (int c = 0; c < 4; c++) *reinterpret_cast<uint4*>(scratch + lane * 80 + c * 16) = v[c];
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        const int rl = 8 * i + (lane >> 2);
-        const uint4 x = *reinterpret_cast<const uint4*>(scratch + rl * 80 + (lane & 3) * 16);
-        const int grow_ = row0 + q * 32 + rl;
-        if (grow_ < B) *reinterpret_cast<uint4*>(base + ((long)tt * B + grow_) * ld + (lane & 3) * 8) = x;
-      }
-    };
-    float state[32];                         // forward: c_{t-1}; backward: dL/dc_t carried to t-1
-#pragma unroll
-    for (int i = 0; i < 32; i++) state[i] = 0.f;
-    // operands of the NEXT step are prefetched right after this step's results are published, so their latency
-    // hides behind the exchange + MMA of the next step
-    uint4 pf[4][4];                          // [chunk][gate] 8 x bf16: forward P_t, backward activated gates
-    float cnow[32];                          // backward only: c_t (this step) = c_{t-1} loaded one step earlier
-    float4 cpf[8];                           // backward only: c_{t-1}
-#pragma unroll
-    for (int i = 0; i < 32; i++) cnow[i] = 0.f;
-    auto prefetch = [&](int tt) {
-      if (!valid) return;
-      const long rr = (long)tt * B + row;
-      if (!BWD) {
-        const bf16* prow = (p.table0b != nullptr ? p.table0b + (long)__ldg(p.xT + rr) * 4 * H : p.Pb + rr * 4 * H) + ub;
-#pragma unroll
-        for (int cu = 0; cu < 4; cu++)
-#pragma unroll
-          for (int g = 0; g < 4; g++) pf[cu][g] = __ldg(reinterpret_cast<const uint4*>(prow + g * H + cu * 8));
-      } else {
-#pragma unroll
-        for (int cu = 0; cu < 4; cu++)
-#pragma unroll
-          for (int g = 0; g < 4; g++) pf[cu][g] = __ldg(gate_tape(tt, g, cu));
-        if (tt > 0) {
-#pragma unroll
-          for (int i = 0; i < 8; i++) cpf[i] = __ldg(c_tape(tt - 1, i));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; i++) cpf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-    };
-    if (BWD && valid) {                      // c_{T-1}
-#pragma unroll
-      for (int i = 0; i < 8; i++) {
-        const float4 v = __ldg(c_tape(T - 1, i));
-        cnow[4 * i] = v.x; cnow[4 * i + 1] = v.y; cnow[4 * i + 2] = v.z; cnow[4 * i + 3] = v.w;
-      }
-    }
-    prefetch(BWD ? T - 1 : 0);
-    bool ok = true;
-    for (int it = 0; it < T && ok; it++) {
-      const int t = BWD ? (T - 1 - it) : it;
-      const long r = (long)t * B + row;
-      if (it > 0) {
-        ok = rc::wait_or_fail(&sh->acc_full, (it - 1) & 1, sh);
-        if (!ok) break;
-        tc::tc_fence_after();
-      }
-      if (threadIdx.x == 0) RC_STAMP(4);
-      uint4 outq[4][4];                      // forward: activated gates [gate][chunk]; backward: dA [gate][chunk]
-      uint4 hq[4];                           // forward: h_t
-#pragma unroll
-      for (int cu = 0; cu < 4; cu++) {
-        const int u0 = hs * 32 + cu * 8;             // unit offset inside the CTA's 64
-        const int ug = 64 * rank + u0;               // global hidden-unit index
-        if (!BWD) {
-          float a[4][8];
-          if (it > 0) {
-#pragma unroll
-            for (int g = 0; g < 4; g++) {
-              uint32_t rr[8];
-              rc::tmem_ld8(taddr + (uint32_t)(g * 64 + u0), rr);
-#pragma unroll
-              for (int j = 0; j < 8; j++) a[g][j] = __uint_as_float(rr[j]);
-            }
-            tc::tmem_ld_wait();
-          } else {
-#pragma unroll
-            for (int g = 0; g < 4; g++)
-#pragma unroll
-              for (int j = 0; j < 8; j++) a[g][j] = 0.f;
-          }
-#pragma unroll
-          for (int g = 0; g < 4; g++) {
-            float f[8];
-            rc::unpack8(pf[cu][g], f);
-#pragma unroll
-            for (int j = 0; j < 8; j++) a[g][j] += f[j];
-          }
-          float hv[8], gi[8], gf[8], gg[8], go[8];
-#pragma unroll
-          for (int j = 0; j < 8; j++) {
-            gi[j] = rc::sigmoid_fast(a[0][j]);
-            gf[j] = rc::sigmoid_fast(a[1][j]);
-            gg[j] = rc::tanh_fast(a[2][j]);
-            go[j] = rc::sigmoid_fast(a[3][j]);
-            const float cn = fmaf(gf[j], state[cu * 8 + j], gi[j] * gg[j]);   // t = 0: state = 0 -> c = i*g
-            state[cu * 8 + j] = cn;
-            hv[j] = go[j] * rc::tanh_fast(cn);
-          }
-          hq[cu] = rc::pack8(hv);
-          outq[0][cu] = rc::pack8(gi); outq[1][cu] = rc::pack8(gf); outq[2][cu] = rc::pack8(gg); outq[3][cu] = rc::pack8(go);
-          if (valid && t == T - 1 && p.h_last != nullptr) {
-            float* hl = p.h_last + (long)row * H + ug;
-            *reinterpret_cast<float4*>(hl) = make_float4(hv[0], hv[1], hv[2], hv[3]);
-            *reinterpret_cast<float4*>(hl + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
-          }
-        } else {
-          float dh[8];
-          if (it > 0) {
-            uint32_t rr[8];
-            rc::tmem_ld8(taddr + (uint32_t)u0, rr);
-            tc::tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 8; j++) dh[j] = __uint_as_float(rr[j]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; j++) dh[j] = 0.f;
-          }
-          if (valid) {
-            if (p.dh_ext != nullptr) {
-              const float* e = p.dh_ext + r * H + ug;
-              const float4 v0 = __ldg(reinterpret_cast<const float4*>(e));
-              const float4 v1 = __ldg(reinterpret_cast<const float4*>(e + 4));
-              dh[0] += v0.x; dh[1] += v0.y; dh[2] += v0.z; dh[3] += v0.w;
-              dh[4] += v1.x; dh[5] += v1.y; dh[6] += v1.z; dh[7] += v1.w;
-            }
-            if (t == T - 1 && p.dh_last != nullptr) {
-              const float* e = p.dh_last + (long)row * p.dh_last_ld + ug;
-#pragma unroll
-              for (int j = 0; j < 8; j++) dh[j] += e[j];
-            }
-          }
-          float gi[8], gf[8], gg[8], go[8], cp[8];
-          rc::unpack8(pf[cu][0], gi);
-          rc::unpack8(pf[cu][1], gf);
-          rc::unpack8(pf[cu][2], gg);
-          rc::unpack8(pf[cu][3], go);
-          cp[0] = cpf[2 * cu].x; cp[1] = cpf[2 * cu].y; cp[2] = cpf[2 * cu].z; cp[3] = cpf[2 * cu].w;
-          cp[4] = cpf[2 * cu + 1].x; cp[5] = cpf[2 * cu + 1].y; cp[6] = cpf[2 * cu + 1].z; cp[7] = cpf[2 * cu + 1].w;
-          float ai[8], af[8], ag[8], ao[8];
-#pragma unroll
-          for (int j = 0; j < 8; j++) {
-            const float tcv = rc::tanh_fast(cnow[cu * 8 + j]);
-            const float dct = state[cu * 8 + j] + dh[j] * go[j] * (1.f - tcv * tcv);
-            ao[j] = dh[j] * tcv * go[j] * (1.f - go[j]);
-            ai[j] = dct * gg[j] * gi[j] * (1.f - gi[j]);
-            ag[j] = dct * gi[j] * (1.f - gg[j] * gg[j]);
-            af[j] = dct * cp[j] * gf[j] * (1.f - gf[j]);
-            state[cu * 8 + j] = dct * gf[j];
-            cnow[cu * 8 + j] = cp[j];              // c_{t-1} is next iteration's c_t
-          }
-          outq[0][cu] = rc::pack8(ai); outq[1][cu] = rc::pack8(af); outq[2][cu] = rc::pack8(ag); outq[3][cu] = rc::pack8(ao);
-        }
-      }
-      // ---- publish what the exchange needs (row-major h_t / dA_t), then signal the sender
-      if (!BWD) {
-        store_rowmajor(hq, p.hb + ub, H, t);
-      } else {
-#pragma unroll
-        for (int g = 0; g < 4; g++) store_rowmajor(outq[g], p.dAb + g * H + ub, 4L * H, t);
-      }
-      if (threadIdx.x == 0) RC_STAMP(5);
-      rc::fence_proxy_async_all();           // generic-proxy global writes -> visible to the sender's TMA (async proxy)
-      if (threadIdx.x == 0) RC_STAMP(6);
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&sh->epi_done);
-      if (threadIdx.x == 0) RC_STAMP(7);
-      // ---- off the critical path: the tape, then the operands of the next step
-      if (!BWD && valid) {
-#pragma unroll
-        for (int g = 0; g < 4; g++)
-#pragma unroll
-          for (int cu = 0; cu < 4; cu++) *gate_tape(t, g, cu) = outq[g][cu];
-#pragma unroll
-        for (int i = 0; i < 8; i++)
-          *c_tape(t, i) = make_float4(state[4 * i], state[4 * i + 1], state[4 * i + 2], state[4 * i + 3]);
-      }
-      if (it + 1 < T) prefetch(BWD ? t - 1 : t + 1);
-    }
-  }
-
-  tc::tc_fence_before();
-  __syncthreads();
-  if (threadIdx.x == 0 && sh->failed && p.err_flag != nullptr) atomicExch(p.err_flag, 1);
-  rc::cluster_sync_all();                    // nobody exits while a peer may still multicast into / arrive on its smem
-  if (warp == 9) {
-    tc::tc_fence_after();
-    tc::tmem_dealloc(tmem_base, BN);
-  }
-}
-
 long long* g_rc_dbg = nullptr;   // set by arcvae_debug_set_rc_stamps (tests only)
 
 // =====================================================================================================================
@@ -1097,34 +751,6 @@ lstm_fwd2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
 int make_tmap_bf16(CUtensorMap* m, const bf16* ptr, long rows, long cols, long ld, int box_cols, int box_rows);
 
 
-static int launch_rec(bool bwd, const CUtensorMap& tmW, const CUtensorMap& tmX, const RecParams& p_in, cudaStream_t st) {
-  RecParams p = p_in;
-  p.dbg = g_rc_dbg;
-  const size_t smem = RC_W_BYTES + RC_NSTG * RC_STAGE_BYTES + 256 + 8 * 2560 + 1024;   // + RecShared + transpose scratch
-  if (first_use_on_device(ONCE_REC1)) {
-    ARCVAE_CUDA(cudaFuncSetAttribute(lstm_rec_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ARCVAE_CUDA(cudaFuncSetAttribute(lstm_rec_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
-  const int tiles = cdiv(p.B, RC_ROWS);
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(tiles * RC_CL);
-  cfg.blockDim = dim3(RC_THREADS);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = RC_CL;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  TimeScope ts(TIME_RECURRENCE, st);
-  if (!bwd) ARCVAE_CUDA(cudaLaunchKernelEx(&cfg, lstm_rec_kernel<false>, tmW, tmX, p));
-  else ARCVAE_CUDA(cudaLaunchKernelEx(&cfg, lstm_rec_kernel<true>, tmW, tmX, p));
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  return 0;
-}
-
 bool lstm_cluster_supported(int H) { return H == 256; }
 
 int make_tmap_bf16_3d(CUtensorMap* m, const bf16* ptr, long T, long rows_per_t, long cols, long ld, int box_cols, int box_rows);
@@ -1145,6 +771,7 @@ static int launch_cluster384(const void* fn, size_t smem, int B, const CUtensorM
   cfg.numAttrs = 1;
   void* args[3] = {(void*)&a, (void*)&b, (void*)&p};
   TimeScope ts(TIME_RECURRENCE, st);
+  count_flops(TIME_RECURRENCE, 2.0 * 4 * p.H * p.H * (double)cdiv(B, RC_ROWS) * RC_ROWS * p.T);
   ARCVAE_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
@@ -1170,16 +797,7 @@ static int lstm_cluster_forward2(int B, int T, int H, const bf16* Whb, const int
 int lstm_cluster_forward(int B, int T, int H, const bf16* Whb, const int32_t* xT, const bf16* table0b, const bf16* Pb,
                          bf16* hb, bf16* gates_b, float* c, float* h_last, int* err_flag, cudaStream_t st) {
   ARCVAE_REQUIRE(lstm_cluster_supported(H), "cluster recurrence kernel is built for hidden_dim 256");
-  if (std::getenv("ARCVAE_FWD_MULTICAST") == nullptr)
-    return lstm_cluster_forward2(B, T, H, Whb, xT, table0b, Pb, hb, gates_b, c, h_last, err_flag, st);
-  CUtensorMap tmW, tmX;
-  ARCVAE_TRY(make_tmap_bf16(&tmW, Whb, 4L * H, H, H, 64, 64));
-  ARCVAE_TRY(make_tmap_bf16(&tmX, hb, (long)T * B, H, H, 64, RC_ROWS));
-  RecParams p{};
-  p.B = B; p.T = T; p.H = H;
-  p.xT = xT; p.table0b = table0b; p.Pb = Pb; p.hb = hb; p.gates_b = gates_b; p.c = c; p.h_last = h_last;
-  p.err_flag = err_flag;
-  return launch_rec(false, tmW, tmX, p, st);
+  return lstm_cluster_forward2(B, T, H, Whb, xT, table0b, Pb, hb, gates_b, c, h_last, err_flag, st);
 }
 
 size_t lstm_cluster_xch_bytes(int B) { return (size_t)2 * cdiv(B, RC_ROWS) * RC_CL * RC_CL * 8 * 4 * 32 * sizeof(uint4); }
@@ -1213,23 +831,10 @@ int lstm_cluster_backward2(int B, int T, int H, const bf16* Whb, const bf16* gat
   cfg.attrs = at;
   cfg.numAttrs = 1;
   TimeScope ts(TIME_RECURRENCE, st);
+  count_flops(TIME_RECURRENCE, 2.0 * 4 * H * H * (double)cdiv(B, RC_ROWS) * RC_ROWS * T);
   ARCVAE_CUDA(cudaLaunchKernelEx(&cfg, lstm_bwd2_kernel, tmW, tmD, p));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
-}
-
-int lstm_cluster_backward(int B, int T, int H, const bf16* WhTb, const bf16* gates_b, const float* c,
-                          const float* dh_ext, const float* dh_last, int dh_last_ld, bf16* dAb, int* err_flag,
-                          cudaStream_t st) {
-  ARCVAE_REQUIRE(lstm_cluster_supported(H), "cluster recurrence kernel is built for hidden_dim 256");
-  CUtensorMap tmW, tmX;
-  ARCVAE_TRY(make_tmap_bf16(&tmW, WhTb, H, 4L * H, 4L * H, 64, 64));
-  ARCVAE_TRY(make_tmap_bf16(&tmX, dAb, (long)T * B, 4L * H, 4L * H, 64, RC_ROWS));
-  RecParams p{};
-  p.B = B; p.T = T; p.H = H;
-  p.gates_b = const_cast<bf16*>(gates_b); p.c = const_cast<float*>(c);
-  p.dh_ext = dh_ext; p.dh_last = dh_last; p.dh_last_ld = dh_last_ld; p.dAb = dAb; p.err_flag = err_flag;
-  return launch_rec(true, tmW, tmX, p, st);
 }
 
 }  // namespace arcvae

@@ -92,3 +92,42 @@ class MoleculeDataset:
         for i in range(0, len(self), batch_size):
             sel = idx_dev[i:i + batch_size]                              # ragged last batch kept (:96-97)
             yield tok.index_select(0, sel), props.index_select(0, sel)
+
+
+# ---- the dataset file of train.py (``mlx_data/chembl_cns_selfies.json``) ------------------------------------------------
+def make_chembl_standin(n_molecules: int = 4096, max_length: int = 128, vocab_size: int = 80, seed: int = 67,
+                        end_token: int = 2) -> dict:
+    """A SCHEMA-COMPATIBLE synthetic stand-in for the reference's bundled ``chembl_cns_selfies.json``, which is absent
+    from the reference mount (``.MISSING_LARGE_BLOBS:1``).  Schema as read by ``train.py:79-83, :102``:
+    ``{"molecules": [{"tpsa": float}, ...], "tokenized_sequences": [[int, ...], ...], "max_length": int}``.
+    Content is synthetic (SELFIES-shaped: body tokens 3..V-1, end token 2; CNS-drug-like lengths ~ 20..70 tokens,
+    TPSA ~ 20..120 A^2), NOT chemistry: it exercises the data path and the throughput, not model quality."""
+    rng = np.random.default_rng(seed)
+    lens = np.clip(rng.normal(42.0, 12.0, size=n_molecules).round().astype(np.int64), 8, max_length)
+    seqs = [[int(t) for t in rng.integers(3, vocab_size, size=int(n) - 1)] + [end_token] for n in lens]
+    tpsa = np.clip(rng.gamma(6.0, 10.0, size=n_molecules), 3.0, 200.0)
+    return {"molecules": [{"tpsa": float(v)} for v in tpsa], "tokenized_sequences": seqs, "max_length": int(max_length),
+            "note": "synthetic stand-in, schema of mlx_data/chembl_cns_selfies.json (train.py:79-124)"}
+
+
+def load_splits(data, *, device=None, train_split: float = 0.8, val_split: float = 0.1):
+    """``train.py:79-124``: read the dataset dict (or a path to the JSON), shuffle the indices with the GLOBAL NumPy RNG
+    (the caller seeds it: ``np.random.seed(67)``, train.py:75), split 80/10/10 and build three ``MoleculeDataset`` objects,
+    the validation and test sets normalised with the TRAINING set's statistics (:113-114, :122-123)."""
+    if isinstance(data, (str, bytes)) or hasattr(data, "__fspath__"):
+        import json
+        with open(data, "r") as f:
+            data = json.load(f)
+    properties = np.array([[mol["tpsa"]] for mol in data["molecules"]], dtype=np.float32)
+    sequences = data["tokenized_sequences"]
+    indices = np.arange(len(sequences))
+    np.random.shuffle(indices)
+    n_total = len(sequences)
+    n_train, n_val = int(train_split * n_total), int(val_split * n_total)
+    parts = (indices[:n_train], indices[n_train:n_train + n_val], indices[n_train + n_val:])
+    train = MoleculeDataset([sequences[i] for i in parts[0]], properties[parts[0]], max_length=data["max_length"],
+                            pad_token=0, device=device)
+    rest = [MoleculeDataset([sequences[i] for i in idx], properties[idx], max_length=data["max_length"], pad_token=0,
+                            properties_mean=train.properties_mean, properties_std=train.properties_std, device=device)
+            for idx in parts[1:]]
+    return train, rest[0], rest[1]

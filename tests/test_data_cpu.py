@@ -50,3 +50,24 @@ def test_empty_and_one_dimensional_properties():
     ds = MoleculeDataset([[3, 4, 2]], np.array([[50.0]]), max_length=5, device="cpu")
     m, p = next(ds.to_batches(4, shuffle=False))
     assert m.tolist() == [[3, 4, 2, 0, 0]] and p.shape == (1, 1) and float(p[0, 0]) == 0.0   # std 0 -> 1
+
+
+def test_load_splits_follows_train_py():
+    """train.py:75-124: seed 67, one shuffle of arange(N) from the global NumPy RNG, 80/10/10, train statistics reused."""
+    from mlx_vae_b200 import data
+    js = data.make_chembl_standin(333, max_length=40, seed=5)
+    assert set(js) >= {"molecules", "tokenized_sequences", "max_length"} and len(js["molecules"]) == 333
+    assert all(s[-1] == 2 and 0 not in s and len(s) <= 40 for s in js["tokenized_sequences"])
+    np.random.seed(67)
+    train, val, test = data.load_splits(js, device="cpu")
+    np.random.seed(67)
+    idx = np.arange(333); np.random.shuffle(idx)
+    n_train, n_val = int(0.8 * 333), int(0.1 * 333)
+    assert (len(train), len(val), len(test)) == (n_train, n_val, 333 - n_train - n_val)
+    assert train.molecules[0] == js["tokenized_sequences"][idx[0]] and test.molecules[-1] == js["tokenized_sequences"][idx[-1]]
+    props = np.array([[m["tpsa"]] for m in js["molecules"]], dtype=np.float32)
+    sel = idx[n_train:n_train + n_val]
+    ref = DO.MoleculeDatasetOracle([js["tokenized_sequences"][i] for i in sel], props[sel], max_length=40,
+                                   properties_mean=train.properties_mean, properties_std=train.properties_std)
+    assert np.array_equal(val.properties_normalized, ref.properties_normalized)
+    assert np.array_equal(val.properties_mean, train.properties_mean)
