@@ -21,7 +21,8 @@ def main():
         sys.exit("/root/reference is not mounted here: the fixtures can only be regenerated in the authoring container")
     out_dir = os.path.join(os.path.dirname(HERE), "tests", "golden")
     for name in R.CASES:
-        res = R.run_reference(name)
+        ck = os.path.join(out_dir, "ref_checkpoint_tiny.npz") if name == "tiny" else None
+        res = R.run_reference(name, checkpoint_to=ck)
         path = os.path.join(out_dir, f"ref_{name}.npz")
         np.savez_compressed(path, **res)
         print(f"{path}: {len(res)} entries, {os.path.getsize(path) / 1024:.0f} KiB")

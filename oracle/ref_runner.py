@@ -117,7 +117,7 @@ def summarize(a: np.ndarray, seed: int = 0):
     return np.concatenate([[f.sum(), (f * f).sum(), (f * w).sum()], f[idx]])
 
 
-def run_reference(name):
+def run_reference(name, checkpoint_to=None):
     """Everything the reference computes for case `name`, keyed like the fixture file."""
     ci = case_inputs(name)
     cfg, B, T, tf, seed = ci["cfg"], ci["B"], ci["T"], ci["tf"], ci["seed"]
@@ -225,6 +225,12 @@ def run_reference(name):
             mx.random.inject(q)
             ep = tr._train_epoch_batches(beta=HYPER["beta"], teacher_forcing_ratio=tf)   # trainer.py:242
             assert mx.random.pending() == 0
+            if checkpoint_to is not None:
+                # trainer.py:577-603: np.savez of nested dicts of mx.array (pickled object arrays)
+                tr.history["epoch"].append(3); tr.history["train_loss"].append(float(ep["loss"]))
+                tr.save_checkpoint(3)
+                import shutil
+                shutil.copyfile(os.path.join(tmp, "ck", "checkpoint_epoch_003.npz"), checkpoint_to)
         for k, v in ep.items():
             out["epoch/" + k] = np.array(v)
         for tag, mod, opt in (("penc", vae.encoder, tr.encoder_optimizer), ("pdec", vae.decoder, tr.decoder_optimizer)):

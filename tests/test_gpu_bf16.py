@@ -1,10 +1,14 @@
 """GPU tests of precision='bf16' (tcgen05 tensor-core contractions with bf16 operands, fp32 accumulation; all
 pointwise math, the loss and Adam stay fp32).
 
-STATED bf16 TOLERANCE (north_star: "a stated bf16 tolerance applies to the tensor-core projections"):
-  logits, mu/logvar, loss scalars : 2e-2 relative to the largest magnitude of the tensor (measured ~3e-3)
-  gradients                       : 5e-2 relative to the largest magnitude of the tensor (measured ~1e-2)
-Operands are rounded to bf16 (2^-9 relative) before each contraction; accumulation is fp32."""
+STATED bf16 TOLERANCE (north_star: "a stated bf16 tolerance applies to the tensor-core projections"), relative to the
+largest magnitude of the tensor, set to about twice the worst value measured on B200 (round 2):
+  logits, mu/logvar, loss scalars : 8e-3   (measured <= 4.1e-3 here, 3.5e-3 at the benched B=4096 x T=128)
+  gradients                       : 2e-2   (measured <= 4.1e-3 vs the fp64 fixtures, 9.7e-3 for the cluster recurrence
+                                            at B=4096 x T=128, 7.4e-3 for the full benched step)
+Operands are rounded to bf16 (2^-9 relative) before each contraction, the recurrence tapes are bf16 and the gates use
+MUFU.TANH (abs error 2^-11); accumulation, cell state, loss and Adam are fp32.  The benched configuration itself is
+checked in tests/test_gpu_benched_config.py (6e-3 / 2e-2)."""
 import numpy as np
 import pytest
 import torch
@@ -13,7 +17,7 @@ import arcvae_oracle as O
 from _util import golden_cfg, golden_hyper, golden_params, load_golden, model_kwargs, rel_err
 
 pytestmark = pytest.mark.gpu
-TOL_FWD, TOL_GRAD = 2e-2, 5e-2
+TOL_FWD, TOL_GRAD = 8e-3, 2e-2
 
 
 @pytest.fixture(scope="module")

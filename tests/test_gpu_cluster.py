@@ -56,7 +56,7 @@ def test_cluster_matches_per_step_paths(M, B, T):
     muC, lvC, gC = run_encoder(M, p, x, cond, "bf16", True, dmu, dlv)
     e_fwd = max(rel_err(muC.cpu(), mu32.cpu()), rel_err(lvC.cpu(), lv32.cpu()))
     e_fwd_step = max(rel_err(muS.cpu(), mu32.cpu()), rel_err(lvS.cpu(), lv32.cpu()))
-    assert e_fwd < 2e-2, (e_fwd, e_fwd_step)
+    assert e_fwd < 8e-3, (e_fwd, e_fwd_step)
     worst, worst_step, name = 0.0, 0.0, None
     for n in g32:
         s = float(g32[n].abs().max())
@@ -69,7 +69,7 @@ def test_cluster_matches_per_step_paths(M, B, T):
         worst_step = max(worst_step, float((gS[n] - g32[n]).abs().max()) / s)
     print(f"B={B} T={T}: fwd err cluster {e_fwd:.2e} / per-step {e_fwd_step:.2e}; grad err cluster {worst:.2e} ({name}) "
           f"/ per-step {worst_step:.2e}")
-    assert worst < 5e-2, (worst, name)
+    assert worst < 2e-2, (worst, name)
 
 
 def test_cluster_path_against_fp64_fixture(M):
@@ -78,4 +78,4 @@ def test_cluster_path_against_fp64_fixture(M):
     enc = M.MLXEncoder(**kw, precision="bf16").load_parameters(p["encoder"])
     mu, lv = enc(cuda(g["x"]), cuda(g["cond"]))
     enc.check()
-    assert rel_err(mu.cpu(), g["mu"]) < 2e-2 and rel_err(lv.cpu(), g["logvar"]) < 2e-2
+    assert rel_err(mu.cpu(), g["mu"]) < 8e-3 and rel_err(lv.cpu(), g["logvar"]) < 8e-3

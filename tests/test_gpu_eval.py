@@ -91,3 +91,36 @@ def test_checkpoint_roundtrip(M, tmp_path):
     a = tr.train_step(x, c, 0.05, 0.9, tf_mask=np.ones(7, dtype=bool), seed=5)
     b = tr2.train_step(x, c, 0.05, 0.9, tf_mask=np.ones(7, dtype=bool), seed=5)
     assert float(a["total_loss"]) == float(b["total_loss"]) and torch.equal(enc2.params.flat, enc.params.flat)
+
+
+def test_reference_checkpoint_loads_after_conversion(M, tmp_path):
+    """A checkpoint written by the reference's own save_checkpoint (under the mlx stand-in) -> converter -> load_checkpoint:
+    the module mirrors then hold the reference's post-epoch weights and Adam moments."""
+    import importlib.util
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "oracle", "mlx_stub"))          # unpickling needs the array class
+    try:
+        spec = importlib.util.spec_from_file_location("conv", os.path.join(root, "tools", "convert_mlx_checkpoint.py"))
+        conv = importlib.util.module_from_spec(spec); spec.loader.exec_module(conv)
+        dst = str(tmp_path / "flat.npz")
+        conv.main(os.path.join(root, "tests", "golden", "ref_checkpoint_tiny.npz"), dst)
+    finally:
+        sys.path.remove(os.path.join(root, "oracle", "mlx_stub"))
+    ref = dict(np.load(os.path.join(root, "tests", "golden", "ref_tiny.npz")))
+    kw = dict(vocab_size=11, embedding_dim=8, hidden_dim=16, latent_dim=8, num_conditions=1, num_layers=2)
+    enc = M.MLXEncoder(**kw, seed=1); dec = M.MLXAutoregressiveDecoder(**kw, seed=2)
+    tr = M.ARCVAETrainerWithLoss(enc, dec, None, None, learning_rate=1e-3, batch_size=5)
+    assert tr.load_checkpoint(dst) == 3
+    for k, v in ref.items():
+        if k.startswith("penc/"):
+            assert np.allclose(enc.params.views[k[5:]].cpu().numpy(), v, rtol=1e-6, atol=1e-7), k
+        if k.startswith("pdec/"):
+            assert np.allclose(dec.params.views[k[5:]].cpu().numpy(), v, rtol=1e-6, atol=1e-7), k
+    k = "penc_opt/fc_mu.weight.v"
+    view = enc.params.views["fc_mu.weight"]
+    beg = (view.data_ptr() - enc.params.flat.data_ptr()) // 4
+    got = tr.encoder_optimizer.v[beg:beg + view.numel()].reshape(view.shape).cpu().numpy()
+    assert np.allclose(got, ref[k], rtol=1e-6, atol=1e-14)
+    assert tr.history["epoch"] == [3.0]

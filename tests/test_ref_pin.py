@@ -120,3 +120,30 @@ def test_stub_adam_has_no_bias_correction_and_modules_are_dicts(mlx):
     assert type(grads[0]) is dict and type(grads[0]["fc"]) is dict and grads[0]["fc"]["weight"].shape == (2, 3)
     # every array sits one level below the top of the gradient dict: what makes trainer.py:502-507 sum nothing (F4)
     assert not any(isinstance(v, mx.array) for v in grads[0].values())
+
+
+def test_reference_checkpoint_converts_to_the_flat_format(tmp_path, mlx):
+    """tests/golden/ref_checkpoint_tiny.npz was written by the REFERENCE's save_checkpoint (trainer.py:577-603: pickled
+    nested dicts of mx.array) at the end of the fixture epoch; tools/convert_mlx_checkpoint.py must turn it into the flat
+    arcvae-flat-v1 file whose entries equal the post-epoch weights / Adam moments recorded in ref_tiny.npz."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("conv", os.path.join(ROOT, "tools", "convert_mlx_checkpoint.py"))
+    conv = importlib.util.module_from_spec(spec); spec.loader.exec_module(conv)
+    dst = str(tmp_path / "flat.npz")
+    conv.main(os.path.join(GOLDEN, "ref_checkpoint_tiny.npz"), dst)
+    flat = np.load(dst, allow_pickle=False)
+    ref = _fixture("tiny")
+    assert int(flat["epoch"]) == 3 and str(flat["format"]) == "arcvae-flat-v1"
+    n = 0
+    for tag, short in (("encoder", "penc"), ("decoder", "pdec")):
+        for k in [k for k in ref if k.startswith(short + "/")]:
+            name = k[len(short) + 1:]
+            assert np.allclose(flat[f"{tag}/{name}"], ref[k], rtol=1e-6, atol=1e-7), (tag, name)
+            n += 1
+        for k in [k for k in ref if k.startswith(short + "_opt/")]:
+            name, mom = k[len(short) + 5:].rsplit(".", 1)
+            assert np.allclose(flat[f"{tag}_opt/{mom}/{name}"], ref[k], rtol=1e-6, atol=1e-12), (tag, name, mom)
+            n += 1
+    assert n > 80
+    import json
+    assert json.loads(str(flat["history_json"]))["epoch"] == [3.0]

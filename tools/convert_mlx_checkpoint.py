@@ -8,8 +8,10 @@
 
 Key mapping: checkpoint['encoder_weights'][module][leaf] -> 'encoder/<module>.<leaf>' (same for the
 decoder).  MLX Adam state is keyed like the parameter tree with leaves {'m', 'v'} -> '<tag>_opt/m|v/<module>.<leaf>'.
-This script cannot be exercised in the B200 image (no MLX wheel, no network); it only uses np.load/np.savez and
-np.array() on mx.array values."""
+It only uses np.load / np.savez and np.array() on mx.array values.  Exercised in this repository on a checkpoint
+written by the reference's own ``save_checkpoint`` running under the ``mlx`` stand-in (tests/golden/ref_checkpoint_tiny.npz,
+tests/test_ref_pin.py::test_reference_checkpoint_converts_to_the_flat_format); real MLX arrays convert through the same
+``np.array(v)`` call."""
 import sys
 
 import numpy as np
@@ -38,6 +40,10 @@ def main(src, dst):
             for name, arr in flatten(state).items():     # e.g. 'fc_mu.weight.m' / 'fc_mu.weight.v' ; 'step', 'learning_rate' are skipped
                 if name.endswith(".m") or name.endswith(".v"):
                     out[f"{tag}_opt/{name[-1]}/{name[:-2]}"] = arr.astype(np.float32)
+    if "history" in ck.files:                        # trainer.py:585 — the 15-list history dict
+        import json
+        hist = ck["history"].item()
+        out["history_json"] = np.array(json.dumps({k: [float(x) for x in v] for k, v in hist.items()}))
     np.savez(dst, **out)
     print(f"wrote {dst}: {len(out)} arrays")
 
