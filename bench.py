@@ -425,9 +425,9 @@ def main():
         n = max(1.0, launches_cat["recurrence"])
         ach = flop / (t_ms * 1e-3) / 1e12
         tape = NL * R * (4 * H * 2 * 2 + H * 4 * 2 + H * 2 + 4 * H * 2 + H * 4)   # gates w+r, c w+r, h w, dA w, P/dX r (bf16/fp32 mix)
-        cluster = M._lib.load().arcvae_recurrence_is_persistent(H) != 0
         roofs["recurrence"] = {"kernel": "lstm_fwd2_kernel+lstm_bwd2_kernel" if H == 256 else
-                                         ("lstm_wide_fwd_kernel+lstm_wide_bwd_kernel" if cluster else "per-step gemm_tc_kernel + k_lstm_cell_*"),
+                                         ("gemm_tc_kernel<LSTM-step epilogue> per timestep + k_lstm_cell_bwd_b / split-K gemm_tc_kernel (W_hh L2-resident)"
+                                          if H % 64 == 0 else "per-step gemm_tc_kernel + k_lstm_cell_*"),
                                "bound": "tensor", "achieved": ach,
                                "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"],
                                "traffic": traffic.get("recurrence"), "peak_source": pk["src"] + " (sustained bf16)",

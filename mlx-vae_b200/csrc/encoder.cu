@@ -5,11 +5,15 @@
 //   layer l>0 input projection = H_{l-1} @ Wx_l^T + b_l               (time-parallel GEMM over all T*B rows)
 //   recurrence                 = MLX nn.LSTM semantics: zero initial state, gate order i,f,g,o, c_0 = i*g
 //   head                       = [h_T ; Linear(cond)] -> fc_mu / fc_logvar(_hidden) -> tanh bounds
-// Three execution paths, same math:
-//   ARCVAE_PREC_FP32            per-step fp32 FFMA GEMM + cell kernels (reference precision)
-//   ARCVAE_PREC_BF16, H != 256  per-step tcgen05 GEMM + cell kernels
-//   ARCVAE_PREC_BF16, H == 256  persistent cluster kernel per layer and direction (lstm_cluster.cu): W_hh resident in
-//                               shared memory for all T steps, bf16 tape (gates, h, dA), fp32 cell state
+// Execution paths, same math:
+//   ARCVAE_PREC_FP32              per-step fp32 FFMA GEMM + cell kernels (reference precision)
+//   ARCVAE_PREC_BF16, H == 256    persistent cluster kernel per layer and direction (lstm_cluster.cu): W_hh resident in
+//                                 shared memory for all T steps, bf16 tape (gates, h, dA), fp32 cell state
+//   ARCVAE_PREC_BF16, H % 64 == 0 (e.g. the scaled config, H = 1024: W_hh = 8 MB bf16 does not fit any cluster's shared
+//                                 memory) ONE launch per timestep: tcgen05 GEMM h_{t-1} @ Wh^T with the whole LSTM cell in
+//                                 its epilogue (gemm_tc.cu TC_EPI_LSTM_FWD); W_hh split over the N tiles of the grid
+//                                 and L2-resident across steps; bf16 tapes; reverse = cell kernel + split-K GEMM per step
+//   ARCVAE_PREC_BF16, otherwise   per-step tcgen05 GEMM + fp32 cell kernels
 #include <cstdlib>
 
 #include "kernels.cuh"
@@ -18,12 +22,13 @@ namespace arcvae {
 
 using bf16 = __nv_bfloat16;
 
-enum { PATH_STEP_F32 = 0, PATH_STEP_BF16 = 1, PATH_CLUSTER = 2 };
+enum { PATH_STEP_F32 = 0, PATH_STEP_BF16 = 1, PATH_CLUSTER = 2, PATH_STEP_FUSED = 3, PATH_COUNT = 4 };
 
 static int pick_path(const arcvae_dims& d, int precision) {
   if (precision != ARCVAE_PREC_BF16) return PATH_STEP_F32;
   const bool no_cluster = std::getenv("ARCVAE_NO_CLUSTER") != nullptr;   // read per call: tests flip it
   if (lstm_cluster_supported(d.H) && !no_cluster) return PATH_CLUSTER;
+  if ((d.H % 64) == 0 && std::getenv("ARCVAE_NO_FUSED_STEP") == nullptr) return PATH_STEP_FUSED;
   return PATH_STEP_BF16;
 }
 
@@ -55,6 +60,9 @@ struct EncTape {
   bf16* Wlvb;        // [L,2H]
   bf16* Pb;                         // [T*B,4H] input projection of the layer being run (reused)
   bf16* table0b;                    // [V,4H] bf16 copy of table0
+  // fused per-step path
+  bf16* Whp[ARCVAE_MAX_LAYERS];     // [4H,H] tile-permuted Wh (B operand of the fused LSTM-step GEMM)
+  bf16* hzero;                      // [B,H] zeros: h_{-1}
 };
 
 static size_t enc_tape_layout(const arcvae_dims& d, int B, int T, int path, void* base, size_t cap, EncTape* t) {
@@ -80,7 +88,11 @@ static size_t enc_tape_layout(const arcvae_dims& d, int B, int T, int path, void
   const size_t Rpad = (size_t)T * (((size_t)B + 127) / 128 * 128);   // cluster path: tile-padded, thread-friendly tape
   for (int l = 0; l < d.NL; l++) {
     tt.c[l] = a.take<float>((path == PATH_CLUSTER ? Rpad : R) * H);
-    if (path != PATH_CLUSTER) {
+    if (path == PATH_STEP_FUSED) {
+      tt.gates_b[l] = a.take<bf16>(R * 4 * H);
+      tt.Whp[l] = a.take<bf16>(4 * H * H);
+    }
+    if (path != PATH_CLUSTER && path != PATH_STEP_FUSED) {
       tt.gates[l] = a.take<float>(R * 4 * H);
       tt.h[l] = a.take<float>(R * H);
     }
@@ -93,10 +105,11 @@ static size_t enc_tape_layout(const arcvae_dims& d, int B, int T, int path, void
       tt.gates_b[l] = a.take<bf16>(Rpad * 4 * H);
     }
   }
-  if (path == PATH_CLUSTER) {
+  if (path == PATH_CLUSTER || path == PATH_STEP_FUSED) {
     tt.Pb = a.take<bf16>(R * 4 * H);
     tt.table0b = a.take<bf16>((size_t)d.V * 4 * H);
   }
+  if (path == PATH_STEP_FUSED) tt.hzero = a.take<bf16>((size_t)B * H);
   if (t) *t = tt;
   return align_up(a.off, 256);
 }
@@ -231,7 +244,7 @@ using namespace arcvae;
 extern "C" size_t arcvae_encoder_tape_bytes(const arcvae_dims* d, int B, int T) {
   if (!d) return 0;
   size_t m = 0;
-  for (int path = 0; path < 3; path++) {
+  for (int path = 0; path < PATH_COUNT; path++) {
     size_t s = enc_tape_layout(*d, B, T, path, nullptr, 0, nullptr);
     if (s > m) m = s;
   }
@@ -289,6 +302,44 @@ extern "C" int arcvae_encoder_forward(const arcvae_dims* d, const arcvae_encoder
     return head_forward(*d, p, tp, tp.h_last, cond, B, mu, logvar, precision, st);
   }
 
+  if (path == PATH_STEP_FUSED) {
+    ARCVAE_TRY(f32_to_bf16(tp.table0, tp.table0b, (long)d->V * G4, st));
+    ARCVAE_CUDA(cudaMemsetAsync(tp.hzero, 0, (size_t)B * H * sizeof(bf16), st));
+    for (int l = 0; l < d->NL; l++) {
+      ARCVAE_TRY(perm4_rows_to_bf16(p->Wh[l], H, H, tp.Whp[l], st));
+      if (l == 0) {
+        ARCVAE_TRY(gather_rows_bf16(tp.table0b, tp.xT, R, G4, tp.Pb, st));        // P0 = table0[x] (bias folded in)
+      } else {
+        TcGemm g{};                                                               // P_l = h_{l-1} @ Wx_l^T + b_l, all T*B rows
+        g.M = (int)R; g.N = G4; g.K = H;
+        g.A = tp.hb[l - 1]; g.lda = H; g.a_mn = false;
+        g.B = tp.Wxb[l]; g.ldb = H; g.b_mn = false;
+        g.C = nullptr; g.ldc = 0; g.Cb = tp.Pb; g.ldcb = G4; g.bias = p->bias[l]; g.accumulate = false; g.splitk = 1;
+        g.rm = id; g.a_rows_total = R;
+        ARCVAE_TRY(gemm_tc(g, st));
+      }
+      TimeScope ts(TIME_RECURRENCE, st);
+      for (int t = 0; t < T; t++) {
+        // one launch per step: gates = P_t + h_{t-1} @ Wh^T, cell, h_t — nn.LSTM's loop body in the GEMM epilogue
+        const long r0 = (long)t * B;
+        TcGemm g{};
+        g.M = B; g.N = G4; g.K = H;
+        g.A = t > 0 ? tp.hb[l] + (r0 - B) * H : tp.hzero; g.lda = H; g.a_mn = false;
+        g.B = tp.Whp[l]; g.ldb = H; g.b_mn = false;
+        g.accumulate = false; g.splitk = 1; g.rm = id; g.a_rows_total = B;
+        g.epi = TC_EPI_LSTM_FWD; g.Hh = H;
+        g.pre_b = tp.Pb + r0 * G4;
+        g.c_prev = t > 0 ? tp.c[l] + (r0 - B) * H : nullptr;
+        g.c_out = tp.c[l] + r0 * H;
+        g.gates_b = tp.gates_b[l] + r0 * G4;
+        g.hb_out = tp.hb[l] + r0 * H;
+        g.hf_out = (l == d->NL - 1 && t == T - 1) ? tp.h_last : nullptr;
+        ARCVAE_TRY(gemm_tc(g, st));
+      }
+    }
+    return head_forward(*d, p, tp, tp.h_last, cond, B, mu, logvar, precision, st);
+  }
+
   for (int l = 0; l < d->NL; l++) {
     if (l == 0) {
       ARCVAE_TRY(gather_rows(tp.table0, tp.xT, (int)R, G4, tp.gates[0], st));
@@ -337,18 +388,46 @@ extern "C" int arcvae_encoder_backward(const arcvae_dims* d, const arcvae_encode
 
   ARCVAE_TRY(head_backward(*d, p, g, tp, sc, cond, B, dmu, dlogvar, precision, st));
 
-  if (path == PATH_CLUSTER) {
+  if (path == PATH_CLUSTER || path == PATH_STEP_FUSED) {
     // weight gradients that share dA^T (dWh, dWx, bias / table scatter) run as ONE multi-segment GEMM per layer: dA is read
     // from HBM once.  The one-hot token operand serves the layer-0 table scatter AND, through its row sums, the bias
     // gradients of the upper layers.
     int* const errf = device_error_flag();
     ARCVAE_REQUIRE(errf != nullptr, "device error flag allocation failed");
-    const bool fuse_dw = scatter_onehot_supported(G4, d->V, 0) && (H % 64) == 0 && H <= 256;
+    const bool fuse_dw = path == PATH_CLUSTER && scatter_onehot_supported(G4, d->V, 0) && (H % 64) == 0 && H <= 256;
     if (fuse_dw) ARCVAE_TRY(build_onehot(tp.xT, R, d->V, nullptr, B, 0, sc.onehot, st));
     for (int l = d->NL - 1; l >= 0; l--) {
       const bool top = (l == d->NL - 1);
-      ARCVAE_TRY(lstm_cluster_backward2(B, T, H, tp.Whb[l], tp.gates_b[l], tp.c[l], top ? nullptr : sc.dX,
-                                        top ? sc.du : nullptr, H2, sc.dAb, sc.xch, errf, st));
+      if (path == PATH_CLUSTER) {
+        ARCVAE_TRY(lstm_cluster_backward2(B, T, H, tp.Whb[l], tp.gates_b[l], tp.c[l], top ? nullptr : sc.dX,
+                                          top ? sc.du : nullptr, H2, sc.dAb, sc.xch, errf, st));
+      } else {
+        // BPTT one step per launch pair: cell reverse from the bf16 tape, then d h_{t-1} = dA_t @ Wh (split-K, fp32 atomics)
+        ARCVAE_CUDA(cudaMemsetAsync(sc.dc, 0, (size_t)B * H * sizeof(float), st));
+        timing_begin(TIME_RECURRENCE, st);
+        for (int t = T - 1; t >= 0; t--) {
+          const long r0 = (long)t * B;
+          const float* dh_ext = top ? nullptr : sc.dX + r0 * H;
+          if (top && t == T - 1) {                              // d h_T = du[:, 0:H] (row pitch 2H) -> dense
+            ARCVAE_CUDA(cudaMemcpy2DAsync(sc.dh_rec[1], (size_t)H * sizeof(float), sc.du, (size_t)H2 * sizeof(float),
+                                          (size_t)H * sizeof(float), B, cudaMemcpyDeviceToDevice, st));
+            dh_ext = sc.dh_rec[1];
+          }
+          ARCVAE_TRY(lstm_cell_bwd_b(tp.gates_b[l] + r0 * G4, tp.c[l] + r0 * H, t > 0 ? tp.c[l] + (r0 - B) * H : nullptr,
+                                     dh_ext, t == T - 1 ? nullptr : sc.dh_rec[0], sc.dc, sc.dAb + r0 * G4, B, H, st));
+          if (t > 0) {
+            ARCVAE_CUDA(cudaMemsetAsync(sc.dh_rec[0], 0, (size_t)B * H * sizeof(float), st));
+            TcGemm q{};
+            q.M = B; q.N = H; q.K = G4;
+            q.A = sc.dAb + r0 * G4; q.lda = G4; q.a_mn = false;
+            q.B = tp.Whb[l]; q.ldb = H; q.b_mn = true;
+            q.C = sc.dh_rec[0]; q.ldc = H; q.accumulate = true; q.splitk = 0;      // auto split-K: K = 4H is long, few tiles
+            q.rm = id; q.a_rows_total = B;
+            ARCVAE_TRY(gemm_tc(q, st));
+          }
+        }
+        timing_end(TIME_RECURRENCE, st);
+      }
       if (fuse_dw) {
         ARCVAE_CUDA(cudaMemsetAsync(sc.segtmp, 0, (size_t)G4 * SCATTER_NW * sizeof(float), st));
         TcGemm q{};

@@ -43,6 +43,7 @@ struct TcParams {
   int epi;
   bf16* gates_b; bf16* hb_out; bf16* dg_out;
   int Hh;
+  const bf16* pre_b; const float* c_prev; float* c_out; float* hf_out;     // TC_EPI_LSTM_FWD
   // multi-segment B (weight gradients that share the A operand): column tile ni multiplies A with its own B matrix
   // (rows shifted by seg_shift[ni]; negative TMA coordinates zero-fill) into its own C
   int nseg; int segN[3]; int seg_shift[3]; float* segC[3]; int seg_ldc[3];
@@ -126,6 +127,17 @@ __device__ __forceinline__ void scr_put16(uint8_t* dst, const float (&v)[16]) {
   *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   *reinterpret_cast<uint4*>(dst + 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
 }
+// 16 floats -> 16 bf16 in two 16-byte registers, stored to a (thread-private) global row segment
+__device__ __forceinline__ void st_bf16x16(bf16* dst, const float (&v)[16]) {
+  uint32_t pk[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    pk[j] = *reinterpret_cast<uint32_t*>(&t);
+  }
+  reinterpret_cast<uint4*>(dst)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  reinterpret_cast<uint4*>(dst)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+}
 __device__ __forceinline__ void scr_get16(const uint8_t* src, float (&v)[16]) {
   const uint4 a = *reinterpret_cast<const uint4*>(src);
   const uint4 b = *reinterpret_cast<const uint4*>(src + 16);
@@ -148,6 +160,9 @@ struct __align__(8) TcShared {
   uint32_t tmem_base;
 };
 
+// LSTM = true: the instantiation whose epilogue is the fused encoder LSTM step (TC_EPI_LSTM_FWD); kept apart so that its
+// register footprint does not touch the code generation of the other epilogues
+template <bool LSTM>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2, const TcParams p) {
@@ -304,7 +319,77 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint8_t* srow = scr + lane * TC_SCR_PITCH;
       const int rows_here = min(32, p.M - (m0 + q * 32));          // rows of this warp's quarter inside the matrix
       const long grow0 = rows_here > 0 ? p.rm(m0 + q * 32) : 0;     // first global row (a row tile never straddles timesteps)
-      if (p.epi == TC_EPI_DEC_CELL_FWD) {
+      if (LSTM) {
+        // one encoder LSTM step (MLX nn.LSTM loop body, models/encoder.py:98-101).  Accumulator columns of this 256-wide
+        // tile: [0,64) = i, [64,128) = f, [128,192) = g, [192,256) = o of hidden units 64*ni .. 64*ni+63 (tile-permuted
+        // Wh); this warp: units half*32 .. +32 in two chunks of 16.  Thread = batch row: P_t, c_{t-1} in, gates / c_t / h_t
+        // out, all in natural column order.
+        const int H = p.Hh;
+#pragma unroll 1
+        for (int cc = 0; cc < 2; cc++) {
+          const int cu = half * 32 + cc * 16;                    // unit offset inside the 64-unit block
+          const int u0 = ni * 64 + cu;                           // natural hidden-unit index of the chunk
+          uint32_t ra[4][16];
+#pragma unroll
+          for (int gi = 0; gi < 4; gi++) tc::tmem_ld16(taddr + gi * 64 + cu, ra[gi]);
+          uint4 pv[4][2];
+          float4 cv[4];
+#pragma unroll
+          for (int k4 = 0; k4 < 4; k4++) cv[k4] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row_ok) {
+            const bf16* prow = p.pre_b + grow * 4L * H + u0;
+#pragma unroll
+            for (int gi = 0; gi < 4; gi++) {
+              pv[gi][0] = __ldg(reinterpret_cast<const uint4*>(prow + (long)gi * H));
+              pv[gi][1] = __ldg(reinterpret_cast<const uint4*>(prow + (long)gi * H) + 1);
+            }
+            if (p.c_prev != nullptr) {
+#pragma unroll
+              for (int k4 = 0; k4 < 4; k4++) cv[k4] = __ldg(reinterpret_cast<const float4*>(p.c_prev + grow * H + u0) + k4);
+            }
+          }
+          tc::tmem_ld_wait();
+          if (row_ok) {
+            float gi_[16], gf_[16], gg_[16], go_[16], cn[16], hv[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+              // bf16 element k of the 16-wide segment: 32-bit word k/2 of the two 16-byte registers, low / high half
+              const uint4 w0 = pv[0][k >> 3], w1 = pv[1][k >> 3], w2 = pv[2][k >> 3], w3 = pv[3][k >> 3];
+              const int wi = (k >> 1) & 3;
+              const uint32_t x0 = wi == 0 ? w0.x : wi == 1 ? w0.y : wi == 2 ? w0.z : w0.w;
+              const uint32_t x1 = wi == 0 ? w1.x : wi == 1 ? w1.y : wi == 2 ? w1.z : w1.w;
+              const uint32_t x2 = wi == 0 ? w2.x : wi == 1 ? w2.y : wi == 2 ? w2.z : w2.w;
+              const uint32_t x3 = wi == 0 ? w3.x : wi == 1 ? w3.y : wi == 2 ? w3.z : w3.w;
+              const float p0 = __uint_as_float((k & 1) ? (x0 & 0xffff0000u) : (x0 << 16));
+              const float p1 = __uint_as_float((k & 1) ? (x1 & 0xffff0000u) : (x1 << 16));
+              const float p2 = __uint_as_float((k & 1) ? (x2 & 0xffff0000u) : (x2 << 16));
+              const float p3 = __uint_as_float((k & 1) ? (x3 & 0xffff0000u) : (x3 << 16));
+              const float4 c4 = cv[k >> 2];
+              const float cp = (k & 3) == 0 ? c4.x : (k & 3) == 1 ? c4.y : (k & 3) == 2 ? c4.z : c4.w;
+              gi_[k] = sigmoid_fast_(__uint_as_float(ra[0][k]) + p0);
+              gf_[k] = sigmoid_fast_(__uint_as_float(ra[1][k]) + p1);
+              gg_[k] = tanh_fast_(__uint_as_float(ra[2][k]) + p2);
+              go_[k] = sigmoid_fast_(__uint_as_float(ra[3][k]) + p3);
+              cn[k] = fmaf(gf_[k], cp, gi_[k] * gg_[k]);
+              hv[k] = go_[k] * tanh_fast_(cn[k]);
+            }
+            bf16* grow_g = p.gates_b + grow * 4L * H + u0;
+            st_bf16x16(grow_g, gi_);
+            st_bf16x16(grow_g + (long)H, gf_);
+            st_bf16x16(grow_g + 2L * H, gg_);
+            st_bf16x16(grow_g + 3L * H, go_);
+            st_bf16x16(p.hb_out + grow * H + u0, hv);
+            float4* cdst = reinterpret_cast<float4*>(p.c_out + grow * H + u0);
+#pragma unroll
+            for (int k4 = 0; k4 < 4; k4++) cdst[k4] = make_float4(cn[4 * k4], cn[4 * k4 + 1], cn[4 * k4 + 2], cn[4 * k4 + 3]);
+            if (p.hf_out != nullptr) {
+              float4* hdst = reinterpret_cast<float4*>(p.hf_out + grow * H + u0);
+#pragma unroll
+              for (int k4 = 0; k4 < 4; k4++) hdst[k4] = make_float4(hv[4 * k4], hv[4 * k4 + 1], hv[4 * k4 + 2], hv[4 * k4 + 3]);
+            }
+          }
+        }
+      } else if (p.epi == TC_EPI_DEC_CELL_FWD) {
         // accumulator columns of this 192-wide tile: [0,64) = i, [64,128) = g, [128,192) = o of units 64*ni .. 64*ni+63;
         // this warp: units half*32 .. +32.  scratch row = [h 64 B | i 64 B | g 64 B | o 64 B]
         const int H = p.Hh;
@@ -544,6 +629,7 @@ int pick_splitk_tc(int M, int N, int K);
 int gemm_tc(const TcGemm& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return 0;
   ARCVAE_REQUIRE(g.C != nullptr || g.Cb != nullptr || g.epi != TC_EPI_PLAIN || g.nseg > 1, "gemm_tc needs an output");
+  ARCVAE_REQUIRE(g.epi != TC_EPI_LSTM_FWD || g.splitk <= 1, "fused LSTM step: no split-K");
   ARCVAE_REQUIRE(!(g.a_mn && g.rm.tlist != nullptr), "row map needs a K-major A");
   ARCVAE_REQUIRE(g.rm.tlist == nullptr || (g.rm.Bt % TC_BM) == 0, "row-mapped tiles must not straddle timesteps");
   TcParams p;
@@ -590,7 +676,16 @@ int gemm_tc(const TcGemm& g, cudaStream_t st) {
   p.rm = g.rm;
   p.epi = g.epi; p.gates_b = g.gates_b; p.hb_out = g.hb_out; p.dg_out = g.dg_out;
   p.Hh = g.Hh;
-  if (g.epi == TC_EPI_DEC_CELL_FWD) {
+  p.pre_b = g.pre_b; p.c_prev = g.c_prev; p.c_out = g.c_out; p.hf_out = g.hf_out;
+  if (g.epi == TC_EPI_LSTM_FWD) {
+    ARCVAE_REQUIRE(g.N == 4 * g.Hh && g.Hh % 64 == 0 && !g.a_mn && !g.b_mn && p.splitk == 1 && g.nseg <= 1 &&
+                   g.rm.tlist == nullptr, "fused LSTM step: N = 4H tile-permuted, K-major operands, no split-K");
+    ARCVAE_REQUIRE(g.pre_b != nullptr && g.c_out != nullptr && g.gates_b != nullptr && g.hb_out != nullptr, "fused LSTM step: outputs");
+    ARCVAE_REQUIRE(((reinterpret_cast<uintptr_t>(g.pre_b) | reinterpret_cast<uintptr_t>(g.c_out) | reinterpret_cast<uintptr_t>(g.gates_b) |
+                     reinterpret_cast<uintptr_t>(g.hb_out) | reinterpret_cast<uintptr_t>(g.c_prev) | reinterpret_cast<uintptr_t>(g.hf_out)) & 15) == 0,
+                   "fused LSTM step: 16-byte aligned tensors");
+    p.BN = 256; p.nt = g.N / 256;
+  } else if (g.epi == TC_EPI_DEC_CELL_FWD) {
     ARCVAE_REQUIRE(g.N % 192 == 0 && g.Hh * 3 == g.N && !g.b_mn && g.bias != nullptr && g.gates_b && g.hb_out,
                    "fused decoder cell (forward): N = 3H tile-permuted, K-major B, bias");
     p.BN = 192; p.nt = g.N / 192;
@@ -637,8 +732,10 @@ int gemm_tc(const TcGemm& g, cudaStream_t st) {
   }
 
   const int num_sms = device_sm_count();
-  if (first_use_on_device(ONCE_GEMM_TC))
-    ARCVAE_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  if (first_use_on_device(ONCE_GEMM_TC)) {
+    ARCVAE_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    ARCVAE_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  }
   ARCVAE_REQUIRE(smem <= 227 * 1024, "gemm_tc shared memory budget");
   const int total = p.mt * p.nt * p.splitk;
   const int grid = total < num_sms ? total : num_sms;
@@ -649,7 +746,8 @@ int gemm_tc(const TcGemm& g, cudaStream_t st) {
     else ncols = g.N;
     count_flops(TIME_GEMM_TC, 2.0 * g.M * ncols * g.K);
   }
-  gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmB1, tmB2, p);
+  if (g.epi == TC_EPI_LSTM_FWD) gemm_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmB1, tmB2, p);
+  else gemm_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmB1, tmB2, p);
   ARCVAE_LAUNCHED();
   return 0;
 }

@@ -20,6 +20,12 @@ int lstm_cell_fwd(float* gates, const float* c_prev, float* c, float* h, __nv_bf
 int lstm_cell_bwd(float* gates, const float* c, const float* c_prev, const float* dh_ext, const float* dh_rec,
                   float* dc, __nv_bfloat16* dAb, int Bn, int H, cudaStream_t st);
 
+// fused per-step encoder path: bf16 gate tape -> bf16 dA (natural column order), see encoder.cu PATH_STEP_FUSED
+int lstm_cell_bwd_b(const __nv_bfloat16* gates_b, const float* c, const float* c_prev, const float* dh_ext,
+                    const float* dh_rec, float* dc, __nv_bfloat16* dAb, int Bn, int H, cudaStream_t st);
+int perm4_rows_to_bf16(const float* W, int H, int D, __nv_bfloat16* out, cudaStream_t st);
+int gather_rows_bf16(const __nv_bfloat16* table, const int32_t* tok, long R, int N, __nv_bfloat16* out, cudaStream_t st);
+
 // decoder cells (zero state: c = i*g, h = o*tanh(c); forget gate unused) on COMPACT gate layout [.., 3H] = (i,g,o)
 // layer 0: a = table[tok[r]] + cond[r % B] @ wc^T   (table [V,3H], wc [3H,C]); rows r = rm(i), i < R
 // gates_b (optional, fused bf16 path): activated (i,g,o) in the tile-permuted layout of the fused GEMM epilogues
@@ -90,13 +96,20 @@ struct TcGemm {
   __nv_bfloat16* hb_out = nullptr;              // [rows,H]  CELL_FWD: h
   __nv_bfloat16* dg_out = nullptr;              // [rows,3H] CELL_BWD: pre-activation gradients (same layout as gates_b)
   int Hh = 0;
+  // fused encoder LSTM step (TC_EPI_LSTM_FWD): one launch = h_{t-1} @ Wh^T + P_t -> gates -> (c_t, h_t).  B is the
+  // TILE-PERMUTED Wh (row j*256 + gi*64 + u <- Wh row gi*H + j*64 + u: a 256-wide N tile = the 4 gates of 64 units);
+  // every tensor below keeps the NATURAL column order (i | f | g | o, each H wide)
+  const __nv_bfloat16* pre_b = nullptr;         // [rows,4H] input projection of this step incl. bias
+  const float* c_prev = nullptr;                // [rows,H] cell state of the previous step (null: zero)
+  float* c_out = nullptr;                       // [rows,H]
+  float* hf_out = nullptr;                      // [rows,H] fp32 copy of h (nullable; the encoder head reads h_{T-1})
   // multi-segment B (nseg = 2 or 3): weight gradients that share the MN-major A operand (dA^T) run as ONE GEMM whose
   // column tile i multiplies with seg[i].B (row k of A pairs with row k - k_shift of B; rows before 0 count as zero)
   // and accumulates into seg[i].C — A is read from HBM once.  Requires a_mn, b_mn, accumulate.
   int nseg = 1;
   struct Seg { const __nv_bfloat16* B; int ldb; int N; int k_shift; float* C; int ldc; } seg[3] = {};
 };
-enum { TC_EPI_PLAIN = 0, TC_EPI_DEC_CELL_FWD = 1, TC_EPI_DEC_CELL_BWD = 2 };
+enum { TC_EPI_PLAIN = 0, TC_EPI_DEC_CELL_FWD = 1, TC_EPI_DEC_CELL_BWD = 2, TC_EPI_LSTM_FWD = 3 };
 int gemm_tc(const TcGemm& g, cudaStream_t st);
 int pick_splitk_tc(int M, int N, int K);
 int f32_to_bf16(const float* src, __nv_bfloat16* dst, long n, cudaStream_t st);

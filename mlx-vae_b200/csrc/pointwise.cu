@@ -113,6 +113,91 @@ int lstm_cell_bwd(float* gates, const float* c, const float* c_prev, const float
   return 0;
 }
 
+// ---- fused per-step encoder path (hidden sizes without a cluster kernel): bf16 tapes in natural column order ----------
+// reverse of one step from the bf16 gate tape: dA (bf16, [Bn,4H]) out; dc carries dL/dc_t in and dL/dc_{t-1} out
+__global__ void k_lstm_cell_bwd_b(const __nv_bfloat16* __restrict__ gates, const float* __restrict__ c,
+                                  const float* __restrict__ c_prev, const float* __restrict__ dh_ext,
+                                  const float* __restrict__ dh_rec, float* __restrict__ dc,
+                                  __nv_bfloat16* __restrict__ dAb, int Bn, int H) {
+  const long total = (long)Bn * (H >> 1);               // two adjacent hidden units per thread (bf16x2 accesses)
+  const int H2 = H >> 1;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const long b = idx / H2;
+    const int j = (int)(idx - b * H2) * 2;
+    const __nv_bfloat16* g = gates + b * 4L * H + j;
+    const float2 i_ = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(g));
+    const float2 f_ = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(g + H));
+    const float2 g_ = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(g + 2L * H));
+    const float2 o_ = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(g + 3L * H));
+    const long e = b * H + j;
+    float2 dh = make_float2(0.f, 0.f);
+    if (dh_ext != nullptr) { const float2 t = *reinterpret_cast<const float2*>(dh_ext + e); dh.x += t.x; dh.y += t.y; }
+    if (dh_rec != nullptr) { const float2 t = *reinterpret_cast<const float2*>(dh_rec + e); dh.x += t.x; dh.y += t.y; }
+    const float2 cc = *reinterpret_cast<const float2*>(c + e);
+    const float2 cp = c_prev != nullptr ? *reinterpret_cast<const float2*>(c_prev + e) : make_float2(0.f, 0.f);
+    const float2 dcin = *reinterpret_cast<const float2*>(dc + e);
+    float ai[2], af[2], ag[2], ao[2], dco[2];
+    const float iv[2] = {i_.x, i_.y}, fv[2] = {f_.x, f_.y}, gv[2] = {g_.x, g_.y}, ov[2] = {o_.x, o_.y};
+    const float dhv[2] = {dh.x, dh.y}, cv[2] = {cc.x, cc.y}, cpv[2] = {cp.x, cp.y}, dcv[2] = {dcin.x, dcin.y};
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      const float tcv = tanh_approx_(cv[k]);
+      const float dct = dcv[k] + dhv[k] * ov[k] * (1.f - tcv * tcv);
+      ao[k] = dhv[k] * tcv * ov[k] * (1.f - ov[k]);
+      ai[k] = dct * gv[k] * iv[k] * (1.f - iv[k]);
+      ag[k] = dct * iv[k] * (1.f - gv[k] * gv[k]);
+      af[k] = dct * cpv[k] * fv[k] * (1.f - fv[k]);
+      dco[k] = dct * fv[k];
+    }
+    __nv_bfloat16* d = dAb + b * 4L * H + j;
+    *reinterpret_cast<__nv_bfloat162*>(d) = __floats2bfloat162_rn(ai[0], ai[1]);
+    *reinterpret_cast<__nv_bfloat162*>(d + H) = __floats2bfloat162_rn(af[0], af[1]);
+    *reinterpret_cast<__nv_bfloat162*>(d + 2L * H) = __floats2bfloat162_rn(ag[0], ag[1]);
+    *reinterpret_cast<__nv_bfloat162*>(d + 3L * H) = __floats2bfloat162_rn(ao[0], ao[1]);
+    *reinterpret_cast<float2*>(dc + e) = make_float2(dco[0], dco[1]);
+  }
+}
+int lstm_cell_bwd_b(const __nv_bfloat16* gates_b, const float* c, const float* c_prev, const float* dh_ext,
+                    const float* dh_rec, float* dc, __nv_bfloat16* dAb, int Bn, int H, cudaStream_t st) {
+  ARCVAE_REQUIRE((H & 1) == 0, "even hidden size");
+  k_lstm_cell_bwd_b<<<grid_for((long)Bn * (H >> 1), 256), 256, 0, st>>>(gates_b, c, c_prev, dh_ext, dh_rec, dc, dAb, Bn, H);
+  ARCVAE_LAUNCHED();
+  return 0;
+}
+// tile-permuted bf16 copy of a [4H, D] gate matrix: out row j*256 + gi*64 + u <- W row gi*H + j*64 + u
+__global__ void k_perm4_rows_to_bf16(const float* __restrict__ W, int H, int D, __nv_bfloat16* __restrict__ out) {
+  const long total = 4L * H * D;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long prow = i / D;
+    const int col = (int)(i - prow * D);
+    const int j = (int)(prow >> 8), rem = (int)(prow & 255), gi = rem >> 6, u = rem & 63;
+    out[i] = __float2bfloat16(W[((long)gi * H + j * 64 + u) * D + col]);
+  }
+}
+int perm4_rows_to_bf16(const float* W, int H, int D, __nv_bfloat16* out, cudaStream_t st) {
+  ARCVAE_REQUIRE(H % 64 == 0, "tile-permuted gates need hidden_dim % 64 == 0");
+  k_perm4_rows_to_bf16<<<grid_for(4L * H * D, 256), 256, 0, st>>>(W, H, D, out);
+  ARCVAE_LAUNCHED();
+  return 0;
+}
+// out[r, :] = table[tok[r], :] for bf16 rows of N elements (N % 8 == 0): 16-byte vectors
+__global__ void k_gather_rows_bf16(const __nv_bfloat16* __restrict__ table, const int32_t* __restrict__ tok, long R, int N8,
+                                   __nv_bfloat16* __restrict__ out) {
+  const long total = R * N8;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / N8;
+    const int c = (int)(i - r * N8);
+    reinterpret_cast<uint4*>(out)[i] = __ldg(reinterpret_cast<const uint4*>(table) + (long)tok[r] * N8 + c);
+  }
+}
+int gather_rows_bf16(const __nv_bfloat16* table, const int32_t* tok, long R, int N, __nv_bfloat16* out, cudaStream_t st) {
+  ARCVAE_REQUIRE((N & 7) == 0, "bf16 row gather needs N % 8 == 0");
+  TimeScope ts(TIME_POINTWISE, st);
+  k_gather_rows_bf16<<<grid_for(R * (N >> 3), 256, 16), 256, 0, st>>>(table, tok, R, N >> 3, out);
+  ARCVAE_LAUNCHED();
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // decoder cells (compact gates i,g,o)
 __device__ __forceinline__ void dec0_preact(const float* __restrict__ table, const float* __restrict__ wc,

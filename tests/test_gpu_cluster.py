@@ -79,3 +79,56 @@ def test_cluster_path_against_fp64_fixture(M):
     mu, lv = enc(cuda(g["x"]), cuda(g["cond"]))
     enc.check()
     assert rel_err(mu.cpu(), g["mu"]) < 8e-3 and rel_err(lv.cpu(), g["logvar"]) < 8e-3
+
+
+@pytest.mark.parametrize("H,NL,B,T", [(128, 2, 200, 7), (1024, 3, 256, 12), (64, 1, 77, 5)])
+def test_fused_step_path_matches_oracle_and_unfused_path(M, H, NL, B, T):
+    """Hidden sizes without a cluster kernel (BASELINE configs[3]: H = 1024) run ONE launch per timestep: the tcgen05 GEMM
+    h_{t-1} @ Wh^T (tile-permuted Wh, L2-resident across steps) with the LSTM cell in its epilogue.  Encoder forward and
+    BPTT against the fp64 oracle (stated bf16 tolerance) and against the older unfused per-step path
+    (ARCVAE_NO_FUSED_STEP=1), which must agree closely since both round the same operands to bf16."""
+    cfg = O.Config(80, 128, H, 128, 1, NL)
+    p = O.init_params(cfg, seed=13, dtype=torch.float32)
+    x, cond, _, _ = O.synthetic_batch(B, T, cfg, seed=B + T)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    dmu = torch.randn(B, cfg.latent_dim, device="cuda", generator=g) / B
+    dlv = torch.randn(B, cfg.latent_dim, device="cuda", generator=g) / B
+
+    def run(env):
+        if env:
+            os.environ["ARCVAE_NO_FUSED_STEP"] = "1"
+        try:
+            enc = M.MLXEncoder(**model_kwargs(cfg), precision="bf16").load_parameters(p["encoder"])
+            l0 = M._lib.launch_count()
+            mu, lv = enc(cuda(x), cuda(cond))
+            fwd_launches = M._lib.launch_count() - l0
+            enc.zero_grad()
+            enc.backward(dmu, dlv)
+            torch.cuda.synchronize()
+            M._lib.check_device_error()
+            return mu.clone(), lv.clone(), {k: v.clone() for k, v in O.tree_flatten(enc.gradients()).items()}, fwd_launches
+        finally:
+            os.environ.pop("ARCVAE_NO_FUSED_STEP", None)
+
+    muF, lvF, gF, nF = run(False)
+    muU, lvU, gU, nU = run(True)
+    assert nF < nU - (T - 1) * NL + 1, (nF, nU)            # one launch per step instead of two
+    # fp64 oracle: forward values and the encoder gradients of  sum(mu * dmu) + sum(logvar * dlv)
+    p64 = O.tree_map(lambda t: t.double().requires_grad_(True), p["encoder"])
+    mu_o, lv_o = O.encoder_forward(p64, torch.as_tensor(x), torch.as_tensor(cond).double(), NL)
+    ((mu_o * dmu.cpu().double()).sum() + (lv_o * dlv.cpu().double()).sum()).backward()
+    e_fwd = max(rel_err(muF.cpu(), mu_o.detach()), rel_err(lvF.cpu(), lv_o.detach()))
+    worst, name, worst_u = 0.0, None, 0.0
+    for n, leaf in O.tree_flatten(p64).items():
+        ref = leaf.grad if leaf.grad is not None else torch.zeros_like(leaf)
+        s = float(ref.abs().max())
+        if s == 0.0:
+            continue
+        e = float((gF[n].double().cpu() - ref).abs().max()) / s
+        if e > worst:
+            worst, name = e, n
+        worst_u = max(worst_u, float((gF[n] - gU[n]).abs().max()) / s)
+    print(f"H={H} NL={NL} B={B} T={T}: fused-step fwd err vs fp64 oracle {e_fwd:.2e}, worst grad {worst:.2e} ({name}); "
+          f"vs unfused per-step path {worst_u:.2e}; forward launches {nF} vs {nU}")
+    assert e_fwd < 8e-3 and worst < 2e-2, (e_fwd, worst, name)
+    assert rel_err(muF.cpu(), muU.cpu()) < 5e-3 and worst_u < 1e-2
