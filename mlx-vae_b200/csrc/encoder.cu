@@ -130,6 +130,7 @@ struct EncScratch {
   bf16* onehot;     // [T*B,SCATTER_NW] one-hot tokens (tensor-core scatter)
   void* xch;        // cluster backward: exchange buffers of the partial d h
   float* segtmp;    // [4H,SCATTER_NW] one-hot segment of the fused weight-gradient GEMM (dtable0^T / bias row sums)
+  float* dh_part;   // [4][B,H] split-K partials of d h_{t-1} (fused per-step path)
 };
 
 static size_t enc_scratch_layout(const arcvae_dims& d, int B, int T, int path, void* base, size_t cap, EncScratch* s) {
@@ -153,6 +154,7 @@ static size_t enc_scratch_layout(const arcvae_dims& d, int B, int T, int path, v
   ss.onehot = (path != PATH_STEP_F32) ? a.take<bf16>((size_t)T * B * SCATTER_NW) : nullptr;
   ss.xch = (path != PATH_STEP_F32) ? a.take<char>(lstm_cluster_xch_bytes(B)) : nullptr;
   ss.segtmp = (path != PATH_STEP_F32) ? a.take<float>((size_t)4 * d.H * SCATTER_NW) : nullptr;
+  ss.dh_part = (path != PATH_STEP_F32) ? a.take<float>((size_t)4 * B * d.H) : nullptr;
   if (s) *s = ss;
   return align_up(a.off, 256);
 }
@@ -404,6 +406,11 @@ extern "C" int arcvae_encoder_backward(const arcvae_dims* d, const arcvae_encode
       } else {
         // BPTT one step per launch pair: cell reverse from the bf16 tape, then d h_{t-1} = dA_t @ Wh (split-K, fp32 atomics)
         ARCVAE_CUDA(cudaMemsetAsync(sc.dc, 0, (size_t)B * H * sizeof(float), st));
+        // split-K factor of the d h GEMM (few output tiles, K = 4H): partials are STORED, the cell kernel adds them
+        const long tiles = (long)cdiv(B, 128) * cdiv(H, 256), kblocks = G4 / 64;
+        int S = 1;
+        while (S < 4 && tiles * S * 2 <= 148 && kblocks / (S * 2) >= 8) S *= 2;
+        const long pstride = (long)B * H;
         timing_begin(TIME_RECURRENCE, st);
         for (int t = T - 1; t >= 0; t--) {
           const long r0 = (long)t * B;
@@ -414,14 +421,13 @@ extern "C" int arcvae_encoder_backward(const arcvae_dims* d, const arcvae_encode
             dh_ext = sc.dh_rec[1];
           }
           ARCVAE_TRY(lstm_cell_bwd_b(tp.gates_b[l] + r0 * G4, tp.c[l] + r0 * H, t > 0 ? tp.c[l] + (r0 - B) * H : nullptr,
-                                     dh_ext, t == T - 1 ? nullptr : sc.dh_rec[0], sc.dc, sc.dAb + r0 * G4, B, H, st));
+                                     dh_ext, t == T - 1 ? nullptr : sc.dh_part, S, pstride, sc.dc, sc.dAb + r0 * G4, B, H, st));
           if (t > 0) {
-            ARCVAE_CUDA(cudaMemsetAsync(sc.dh_rec[0], 0, (size_t)B * H * sizeof(float), st));
             TcGemm q{};
             q.M = B; q.N = H; q.K = G4;
             q.A = sc.dAb + r0 * G4; q.lda = G4; q.a_mn = false;
             q.B = tp.Whb[l]; q.ldb = H; q.b_mn = true;
-            q.C = sc.dh_rec[0]; q.ldc = H; q.accumulate = true; q.splitk = 0;      // auto split-K: K = 4H is long, few tiles
+            q.C = sc.dh_part; q.ldc = H; q.accumulate = false; q.splitk = S; q.split_stride = S > 1 ? pstride : 0;
             q.rm = id; q.a_rows_total = B;
             ARCVAE_TRY(gemm_tc(q, st));
           }

@@ -34,6 +34,7 @@ struct TcParams {
   int stages;
   int a_mn, b_mn;    // operand major-ness
   int mt, nt, splitk, kb_per;
+  long split_stride;
   float* C; int ldc;
   bf16* Cb; int ldcb;
   const float* bias;
@@ -227,6 +228,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int k0 = kb * TC_BK;
           if (!p.a_mn) {
             tc::tma_load_2d(sa, &tmA, &sh->full[stage], k0, gm0);                       // box {64 k, 128 rows}
+            if (p.bm2) tc::tma_load_2d(sa + 16384, &tmA, &sh->full[stage], k0, gm0 + TC_BM);   // rows 128..255 of the tile
           } else {
             for (int j = 0; j < BMt / 64; j++)                                          // box {64 m, 64 k} x 2 (x 4)
               tc::tma_load_2d(sa + j * 8192, &tmA, &sh->full[stage], m0 + j * 64, k0);
@@ -276,8 +278,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                        : tc::make_smem_desc(sb + k * 32, 16, 1024);
             tc::mma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             if (p.bm2)                                            // rows 128..255 of the tile against the same B
-              tc::mma_bf16(tmem_base + 256, tc::make_smem_desc(sa + 16384 + k * 2048, 8192, 1024), db, idesc,
-                           (kb > kb0 || k > 0) ? 1u : 0u);
+              tc::mma_bf16(tmem_base + 256,
+                           p.a_mn ? tc::make_smem_desc(sa + 16384 + k * 2048, 8192, 1024)
+                                  : tc::make_smem_desc(sa + 16384 + k * 32, 16, 1024),
+                           db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           tc::mma_commit(&sh->empty[stage]);                  // smem stage free once these MMAs have read it
           if (kb == kb1 - 1) tc::mma_commit(&sh->tmem_full[acc]);
@@ -299,7 +303,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int ch_lo = half == 0 ? 0 : (nchunks + 1) >> 1;
       const int ch_hi = half == 0 ? (nchunks + 1) >> 1 : nchunks;
       const int n0 = mseg ? 0 : ni * p.BN;
-      float* const Ct = mseg ? p.segC[ni] : p.C;           // output of this column tile
+      float* const Ct = mseg ? p.segC[ni] : (p.split_stride > 0 ? p.C + (long)(tile / (p.mt * p.nt)) * p.split_stride : p.C);
       const int ldct = mseg ? p.seg_ldc[ni] : p.ldc;
       const int Nt = mseg ? p.segN[ni] : p.N;
       const int acc = p.bm2 ? 0 : (it & 1);
@@ -312,7 +316,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool row_ok = row_local < p.M;
       const long grow = row_ok ? p.rm(row_local) : 0;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.bm2 ? sub * 256 : acc * p.BN);
-      const bool atomic = p.splitk > 1;
+      const bool atomic = p.splitk > 1 && p.split_stride == 0;
       const bool add_bias = p.bias != nullptr && (tile / (p.mt * p.nt)) == 0;
       const int TC_SCR_PITCH = p.scr_pitch;
       uint8_t* scr = scratch + (warp - 2) * 32 * TC_SCR_PITCH;
@@ -664,14 +668,16 @@ int gemm_tc(const TcGemm& g, cudaStream_t st) {
     const long maxs = kblocks / 8;
     if (sk > maxs) sk = maxs;
     splitk = sk < 1 ? 1 : (int)sk;
-  } else if (p.bm2) {
+  } else if (p.bm2 && g.a_mn && splitk > 1) {
     splitk *= 2;                            // the caller sized the split for 128-row tiles
   }
   if (splitk > kblocks) splitk = kblocks;
   p.kb_per = cdiv(kblocks, splitk);
   p.splitk = cdiv(kblocks, p.kb_per);
-  ARCVAE_REQUIRE(p.splitk == 1 || (g.accumulate && (g.C != nullptr || g.nseg > 1) && g.Cb == nullptr),
-                 "split-K accumulates with fp32 atomics into C");
+  ARCVAE_REQUIRE(p.splitk == 1 || (g.accumulate && (g.C != nullptr || g.nseg > 1) && g.Cb == nullptr) ||
+                     (g.split_stride > 0 && !g.accumulate && g.C != nullptr && g.Cb == nullptr && g.nseg <= 1 && g.bias == nullptr),
+                 "split-K accumulates with fp32 atomics into C, or stores partials (split_stride)");
+  p.split_stride = p.splitk > 1 ? g.split_stride : 0;
   p.C = g.C; p.ldc = g.ldc; p.Cb = g.Cb; p.ldcb = g.ldcb; p.bias = g.bias; p.accumulate = g.accumulate ? 1 : 0;
   p.rm = g.rm;
   p.epi = g.epi; p.gates_b = g.gates_b; p.hb_out = g.hb_out; p.dg_out = g.dg_out;

@@ -21,8 +21,10 @@ int lstm_cell_bwd(float* gates, const float* c, const float* c_prev, const float
                   float* dc, __nv_bfloat16* dAb, int Bn, int H, cudaStream_t st);
 
 // fused per-step encoder path: bf16 gate tape -> bf16 dA (natural column order), see encoder.cu PATH_STEP_FUSED
+// dh_rec: nsplit partial [Bn,H] buffers, split_stride floats apart (split-K GEMM with TcGemm::split_stride)
 int lstm_cell_bwd_b(const __nv_bfloat16* gates_b, const float* c, const float* c_prev, const float* dh_ext,
-                    const float* dh_rec, float* dc, __nv_bfloat16* dAb, int Bn, int H, cudaStream_t st);
+                    const float* dh_rec, int nsplit, long split_stride, float* dc, __nv_bfloat16* dAb, int Bn, int H,
+                    cudaStream_t st);
 int perm4_rows_to_bf16(const float* W, int H, int D, __nv_bfloat16* out, cudaStream_t st);
 int gather_rows_bf16(const __nv_bfloat16* table, const int32_t* tok, long R, int N, __nv_bfloat16* out, cudaStream_t st);
 
@@ -88,6 +90,8 @@ struct TcGemm {
   const float* bias;                            // [N] or null
   bool accumulate;                              // C += ...   (mandatory with splitk > 1: fp32 atomics)
   int splitk;
+  long split_stride = 0;                        // > 0 with splitk > 1: split ks STORES its partial to C + ks*split_stride
+                                                // (no atomics, no pre-zeroed C; the consumer adds the partials)
   RowMap rm;                                    // rows of A (K-major) and C; rm.Bt must be a multiple of 128
   long a_rows_total;                            // rows of the allocation behind A when rm is used
   // fused decoder epilogues (zero-state LSTM cell on compact, tile-permuted gates; see decoder.cu)

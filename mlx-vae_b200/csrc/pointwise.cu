@@ -117,8 +117,8 @@ int lstm_cell_bwd(float* gates, const float* c, const float* c_prev, const float
 // reverse of one step from the bf16 gate tape: dA (bf16, [Bn,4H]) out; dc carries dL/dc_t in and dL/dc_{t-1} out
 __global__ void k_lstm_cell_bwd_b(const __nv_bfloat16* __restrict__ gates, const float* __restrict__ c,
                                   const float* __restrict__ c_prev, const float* __restrict__ dh_ext,
-                                  const float* __restrict__ dh_rec, float* __restrict__ dc,
-                                  __nv_bfloat16* __restrict__ dAb, int Bn, int H) {
+                                  const float* __restrict__ dh_rec, int nsplit, long split_stride,
+                                  float* __restrict__ dc, __nv_bfloat16* __restrict__ dAb, int Bn, int H) {
   const long total = (long)Bn * (H >> 1);               // two adjacent hidden units per thread (bf16x2 accesses)
   const int H2 = H >> 1;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -132,7 +132,12 @@ __global__ void k_lstm_cell_bwd_b(const __nv_bfloat16* __restrict__ gates, const
     const long e = b * H + j;
     float2 dh = make_float2(0.f, 0.f);
     if (dh_ext != nullptr) { const float2 t = *reinterpret_cast<const float2*>(dh_ext + e); dh.x += t.x; dh.y += t.y; }
-    if (dh_rec != nullptr) { const float2 t = *reinterpret_cast<const float2*>(dh_rec + e); dh.x += t.x; dh.y += t.y; }
+    if (dh_rec != nullptr) {
+      for (int s = 0; s < nsplit; s++) {                    // split-K partials of d h_t = dA_{t+1} @ Wh
+        const float2 t = *reinterpret_cast<const float2*>(dh_rec + s * split_stride + e);
+        dh.x += t.x; dh.y += t.y;
+      }
+    }
     const float2 cc = *reinterpret_cast<const float2*>(c + e);
     const float2 cp = c_prev != nullptr ? *reinterpret_cast<const float2*>(c_prev + e) : make_float2(0.f, 0.f);
     const float2 dcin = *reinterpret_cast<const float2*>(dc + e);
@@ -158,9 +163,11 @@ __global__ void k_lstm_cell_bwd_b(const __nv_bfloat16* __restrict__ gates, const
   }
 }
 int lstm_cell_bwd_b(const __nv_bfloat16* gates_b, const float* c, const float* c_prev, const float* dh_ext,
-                    const float* dh_rec, float* dc, __nv_bfloat16* dAb, int Bn, int H, cudaStream_t st) {
+                    const float* dh_rec, int nsplit, long split_stride, float* dc, __nv_bfloat16* dAb, int Bn, int H,
+                    cudaStream_t st) {
   ARCVAE_REQUIRE((H & 1) == 0, "even hidden size");
-  k_lstm_cell_bwd_b<<<grid_for((long)Bn * (H >> 1), 256), 256, 0, st>>>(gates_b, c, c_prev, dh_ext, dh_rec, dc, dAb, Bn, H);
+  k_lstm_cell_bwd_b<<<grid_for((long)Bn * (H >> 1), 256), 256, 0, st>>>(gates_b, c, c_prev, dh_ext, dh_rec, nsplit, split_stride,
+                                                                         dc, dAb, Bn, H);
   ARCVAE_LAUNCHED();
   return 0;
 }
