@@ -160,6 +160,24 @@ int arcvae_decoder_backward(const arcvae_dims* d, const arcvae_decoder_params* p
                             float* dlogits_tm, void* tape, size_t tape_bytes, const arcvae_decoder_params* g,
                             void* scratch, size_t scratch_bytes, int precision, void* stream);
 
+/* ---- decoder with carry_state=True — an EXTENSION, not the reference's behaviour: the state built by
+ * initialize_hidden_state (models/decoder.py:76-111) is consumed and carried from position to position (the reference
+ * computes it at :143 and never passes it to the LSTM layers, :165-168).  Same tensors and conventions as
+ * arcvae_decoder_forward / _backward plus z [B,L]; the reverse pass also returns dz [B,L] (d total / d z), which
+ * arcvae_reparam_backward folds into d mu / d logvar (z = mu + eps*exp(logvar/2), models/encoder.py:147-153). */
+size_t arcvae_decoder_cs_tape_bytes(const arcvae_dims* d, int B, int T);
+size_t arcvae_decoder_cs_scratch_bytes(const arcvae_dims* d, int B, int T);
+int arcvae_decoder_cs_forward(const arcvae_dims* d, const arcvae_decoder_params* p, const float* z, const float* cond,
+                              const int32_t* target, const uint8_t* tf_mask_host, int B, int T, float* logits_tm,
+                              int32_t* dec_inputs_tm, void* tape, size_t tape_bytes, int precision, void* stream);
+int arcvae_decoder_cs_backward(const arcvae_dims* d, const arcvae_decoder_params* p, const float* z, const float* cond,
+                               int B, int T, float* dlogits_tm, void* tape, size_t tape_bytes,
+                               const arcvae_decoder_params* g, float* dz, void* scratch, size_t scratch_bytes,
+                               int precision, void* stream);
+/* dmu += dz ; dlogvar += dz * (z - mu) / 2 */
+int arcvae_reparam_backward(const float* dz, const float* z, const float* mu, int B, int L, float* dmu, float* dlogvar,
+                            void* stream);
+
 /* ---- losses: losses/recon.py:29-64, losses/kl.py:35-66, losses/info.py:23-78,
  *      complete_vae_loss.py:45-99 — one fused kernel, forward values and gradients --------------- */
 /* logits element (b,t,v) at logits[b*ls_b + t*ls_t + v]; targets (b,t) at targets[b*ts_b + t*ts_t].

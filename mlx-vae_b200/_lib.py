@@ -83,6 +83,16 @@ SIGNATURES = {
     "arcvae_decoder_backward": (C.c_int, [C.POINTER(Dims), C.POINTER(DecoderParams), C.c_void_p, C.c_int, C.c_int,
                                           C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(DecoderParams), C.c_void_p,
                                           C.c_size_t, C.c_int, C.c_void_p]),
+    "arcvae_decoder_cs_tape_bytes": (C.c_size_t, [C.POINTER(Dims), C.c_int, C.c_int]),
+    "arcvae_decoder_cs_scratch_bytes": (C.c_size_t, [C.POINTER(Dims), C.c_int, C.c_int]),
+    "arcvae_decoder_cs_forward": (C.c_int, [C.POINTER(Dims), C.POINTER(DecoderParams), C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                            C.c_int, C.c_void_p]),
+    "arcvae_decoder_cs_backward": (C.c_int, [C.POINTER(Dims), C.POINTER(DecoderParams), C.c_void_p, C.c_void_p, C.c_int,
+                                             C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(DecoderParams),
+                                             C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "arcvae_reparam_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                          C.c_void_p]),
     "arcvae_loss_fwd_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int,
                                       C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                       C.POINTER(LossHyper), C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p,

@@ -17,7 +17,11 @@ def _run(encoder, decoder, property_predictor, x, conditions, beta, lambda_prop,
         # the reference would raise TypeError here (complete_vae_loss.py:63-67 vs losses/prop.py:5-11, F10)
         raise NotImplementedError("property_predictor must be None, as in train.py:186")
     mu, logvar = encoder(x, conditions)                                                         # :38
-    logits = decoder(None, conditions, target_seq=x, teacher_forcing_ratio=teacher_forcing_ratio,
+    z_in = None
+    if getattr(decoder, "carry_state", False):
+        # extension mode: the decoder consumes z (reference mode: z is dead, F1); same Philox stream as the loss kernel
+        z_in = encoder.reparameterize(mu, logvar, eps, seed=seed, offset=eps_offset)            # :39
+    logits = decoder(z_in, conditions, target_seq=x, teacher_forcing_ratio=teacher_forcing_ratio,
                      tf_mask=tf_mask)                                                           # :42
     hp = make_hyper(beta, lambda_prop, lambda_collapse, free_bits, lambda_mi, target_mi, 4.85, pad_mask)
     targets = encoder._tokens(x)
@@ -35,7 +39,11 @@ def _run(encoder, decoder, property_predictor, x, conditions, beta, lambda_prop,
         d["recon_loss"] = recon
         d["total_loss"] = recon + d["weighted_kl"] + d["collapse_penalty"] + d["weighted_prop_loss"] + d["mi_penalty"]
     if backward:
-        decoder.backward(out.dlogits)
+        dz = decoder.backward(out.dlogits)
+        if dz is not None:                      # carry_state: the reconstruction loss reaches the encoder through z
+            B_, L_ = mu.shape
+            _lib.check(_lib.load().arcvae_reparam_backward(dz.data_ptr(), z_in.data_ptr(), mu.data_ptr(), B_, L_,
+                                                           out.dmu.data_ptr(), out.dlogvar.data_ptr(), _lib.stream_ptr()))
         if backward_hooks is not None:
             backward_hooks.after_decoder_backward(decoder, d)
         encoder.backward(out.dmu, out.dlogvar)

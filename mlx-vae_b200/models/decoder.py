@@ -26,7 +26,7 @@ class MLXAutoregressiveDecoder(Module):
 
     def __init__(self, vocab_size: int, embedding_dim: int = 256, hidden_dim: int = 512, latent_dim: int = 200,
                  num_conditions: int = 6, num_layers: int = 3, pad_token: int = 0, end_token: int = 2, *,
-                 device=None, seed: Optional[int] = None, precision="fp32"):
+                 device=None, seed: Optional[int] = None, precision="fp32", carry_state: bool = False):
         self.vocab_size, self.embedding_dim, self.hidden_dim = vocab_size, embedding_dim, hidden_dim
         self.latent_dim, self.num_conditions, self.num_layers = latent_dim, num_conditions, num_layers
         self.pad_token, self.end_token = pad_token, end_token
@@ -35,6 +35,10 @@ class MLXAutoregressiveDecoder(Module):
                          pad_token=pad_token, end_token=end_token), device, seed, precision)
         self._ctx = None
         self.last_inputs = None   # [B,T] tokens fed at each position by the last call (diagnostic)
+        # carry_state=True is an EXTENSION, not the reference: the state of initialize_hidden_state is
+        # consumed and carried across positions, z reaches the logits and backward() returns d total / d z
+        self.carry_state = bool(carry_state)
+        self.last_dz = None
 
     def initialize_hidden_state(self, z: torch.Tensor, conditions: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """decoder.py:76-111.  The reference computes this and never uses it (F1); provided for API parity.
@@ -77,29 +81,53 @@ class MLXAutoregressiveDecoder(Module):
             mask = np.ascontiguousarray(np.asarray(tf_mask).astype(np.uint8))
             if mask.shape != (T,):
                 raise ValueError(f"tf_mask must have shape ({T},)")
-        nbytes = lib.arcvae_decoder_tape_bytes(self._dims, B, T)
-        tape = self.ws.get("tape", nbytes)
         logits_tm = torch.empty((T, B, self.vocab_size), dtype=torch.float32, device=self.device)
         inputs_tm = torch.empty((T, B), dtype=torch.int32, device=self.device)
-        _lib.check(lib.arcvae_decoder_forward(self._dims, self._cparams, cond.data_ptr(), _lib.ptr(target),
-                                              mask.ctypes.data, B, T, logits_tm.data_ptr(), inputs_tm.data_ptr(),
-                                              tape.data_ptr(), tape.numel(), self.precision, _lib.stream_ptr()))
-        self._ctx = (B, T, cond, tape)
+        if self.carry_state:
+            if z is None:
+                raise ValueError("carry_state=True: the decoder state is initialised from z, which must be given")
+            zz = self._f32(z)
+            if zz.shape != (B, self.latent_dim):
+                raise ValueError(f"z must be [{B},{self.latent_dim}], got {tuple(zz.shape)}")
+            tape = self.ws.get("tape_cs", lib.arcvae_decoder_cs_tape_bytes(self._dims, B, T))
+            _lib.check(lib.arcvae_decoder_cs_forward(self._dims, self._cparams, zz.data_ptr(), cond.data_ptr(),
+                                                     _lib.ptr(target), mask.ctypes.data, B, T, logits_tm.data_ptr(),
+                                                     inputs_tm.data_ptr(), tape.data_ptr(), tape.numel(), self.precision,
+                                                     _lib.stream_ptr()))
+            self._ctx = (B, T, cond, tape, zz)
+        else:
+            tape = self.ws.get("tape", lib.arcvae_decoder_tape_bytes(self._dims, B, T))
+            _lib.check(lib.arcvae_decoder_forward(self._dims, self._cparams, cond.data_ptr(), _lib.ptr(target),
+                                                  mask.ctypes.data, B, T, logits_tm.data_ptr(), inputs_tm.data_ptr(),
+                                                  tape.data_ptr(), tape.numel(), self.precision, _lib.stream_ptr()))
+            self._ctx = (B, T, cond, tape)
         self.last_inputs = inputs_tm.transpose(0, 1)
         self.last_tf_mask = mask.astype(bool)
         return logits_tm.transpose(0, 1)   # [B,T,V] view of the time-major buffer
 
     def backward(self, dlogits: torch.Tensor):
         """Reverse pass of the last call.  ``dlogits`` is [B,T,V]; the transposed view of a time-major [T,B,V]
-        buffer (what the fused loss writes) is consumed in place, anything else is copied."""
+        buffer (what the fused loss writes) is consumed in place, anything else is copied.  Returns None in the
+        reference mode (z does not reach the logits) and d total / d z [B,L] with ``carry_state=True``."""
         if self._ctx is None:
             raise _lib.ArcvaeError("decoder.backward() without a forward")
         lib = _lib.load()
-        B, T, cond, tape = self._ctx
         _lib.require_cuda(dlogits)
         d_tm = dlogits.transpose(0, 1)
         if not d_tm.is_contiguous() or d_tm.dtype != torch.float32:
             d_tm = d_tm.contiguous().float()
+        if self.carry_state:
+            B, T, cond, tape, zz = self._ctx
+            scratch = self.ws.get("scratch_cs", lib.arcvae_decoder_cs_scratch_bytes(self._dims, B, T))
+            dz = torch.empty_like(zz)
+            _lib.check(lib.arcvae_decoder_cs_backward(self._dims, self._cparams, zz.data_ptr(), cond.data_ptr(), B, T,
+                                                      d_tm.data_ptr(), tape.data_ptr(), tape.numel(), self._cgrads,
+                                                      dz.data_ptr(), scratch.data_ptr(), scratch.numel(), self.precision,
+                                                      _lib.stream_ptr()))
+            self._ctx = None
+            self.last_dz = dz
+            return dz
+        B, T, cond, tape = self._ctx
         sbytes = lib.arcvae_decoder_scratch_bytes(self._dims, B, T)
         scratch = self.ws.get("scratch", sbytes)
         _lib.check(lib.arcvae_decoder_backward(self._dims, self._cparams, cond.data_ptr(), B, T, d_tm.data_ptr(),

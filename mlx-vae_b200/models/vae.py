@@ -15,15 +15,17 @@ class ARCVAE:
 
     def __init__(self, vocab_size: int, embedding_dim: int = 256, hidden_dim: int = 512, latent_dim: int = 200,
                  num_conditions: int = 6, num_layers: int = 3, dropout: float = 0.2, *, device=None,
-                 seed: Optional[int] = None, precision="fp32"):
+                 seed: Optional[int] = None, precision="fp32", carry_state: bool = False):
         s = (lambda k: None if seed is None else seed + k)
         self.encoder = MLXEncoder(vocab_size, embedding_dim, hidden_dim, latent_dim, num_conditions, num_layers,
                                   dropout, device=device, seed=s(0), precision=precision)
         self.decoder = MLXAutoregressiveDecoder(vocab_size, embedding_dim, hidden_dim, latent_dim, num_conditions,
-                                                num_layers, device=device, seed=s(1), precision=precision)
+                                                num_layers, device=device, seed=s(1), precision=precision,
+                                                carry_state=carry_state)
         self.decoder_sampling = MLXAutoregressiveDecoderSampling(vocab_size, embedding_dim, hidden_dim, latent_dim,
                                                                  num_conditions, num_layers, device=device, seed=s(2),
-                                                                 precision=precision)
+                                                                 precision=precision, carry_state=carry_state)
+        self.carry_state = bool(carry_state)
         self.latent_dim = latent_dim
 
     def __call__(self, x: torch.Tensor, conditions: torch.Tensor, target_seq: Optional[torch.Tensor] = None,
@@ -47,5 +49,9 @@ class ARCVAE:
                 decoder=self.decoder)
         else:
             sampler = self.decoder_sampling
-        return sampler.generate_with_temperature(None, conditions, max_length=max_length, temperature=temperature,
+        z = None
+        if self.carry_state:                     # vae.py:121: z ~ N(0, I) from the prior (Philox(seed) on the device)
+            zero = torch.zeros((batch_size, self.latent_dim), dtype=torch.float32, device=self.encoder.device)
+            z = MLXEncoder.reparameterize(zero, zero, None, seed=seed)
+        return sampler.generate_with_temperature(z, conditions, max_length=max_length, temperature=temperature,
                                                  multinomial=multinomial, seed=seed)

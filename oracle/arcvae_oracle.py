@@ -215,32 +215,42 @@ def initialize_hidden_state(p: Tree, z, conditions, num_layers: int):
     return hidden, torch.zeros_like(hidden)
 
 
-def _decoder_step(p: Tree, current_token, conditions, num_layers: int):
-    """models/decoder.py:154-175 — one position; LSTM layers called WITHOUT state."""
+def _decoder_step(p: Tree, current_token, conditions, num_layers: int, state=None):
+    """models/decoder.py:154-175 — one position.  ``state is None``: LSTM layers called WITHOUT state, as the reference
+    does (F1).  ``state = (h, c)`` (lists of [B,H] per layer): the ``carry_state=True`` extension (the
+    evidently intended semantics of decoder.py:95-99, :143): every layer is called with its own (hidden, cell) and the
+    state is updated in place."""
     embedded = p["embedding"]["weight"][current_token.long()]          # :154
     lstm_input = torch.cat([embedded, conditions], dim=1).unsqueeze(1)  # :157-160
     output = lstm_input
     for i in range(num_layers):                                        # :165-168
-        output, _hidden = lstm_layer(p[f"lstm_layer_{i}"], output)
+        if state is None:
+            output, _hidden = lstm_layer(p[f"lstm_layer_{i}"], output)
+        else:
+            output, cells = lstm_layer(p[f"lstm_layer_{i}"], output, hidden=state[0][i], cell=state[1][i])
+            state[0][i], state[1][i] = output[:, -1, :], cells[:, -1, :]
     return linear(p["fc_out"], output[:, 0, :])                        # :172-175
 
 
 def decoder_forward(p: Tree, z, conditions, num_layers: int, target_seq=None, max_length: int = 80,
-                    tf_mask: Optional[Sequence[bool]] = None, return_inputs: bool = False):
+                    tf_mask: Optional[Sequence[bool]] = None, return_inputs: bool = False, carry_state: bool = False):
     """models/decoder.py:113-190.
 
     ``tf_mask[t]`` replaces the host coin ``np.random.rand() < teacher_forcing_ratio``
     of ``decoder.py:180`` (one coin per position for the whole batch, F7).  With
     ``target_seq is None`` every coin is false, as in the reference.
+    ``carry_state=True`` (NOT the reference's behaviour): the state built by ``initialize_hidden_state`` is consumed and
+    carried from position to position.
     """
     B = z.shape[0]
     T = target_seq.shape[1] if target_seq is not None else max_length   # :137-140
-    _ = initialize_hidden_state(p, z, conditions, num_layers)          # :143 dead value
+    hidden, cell = initialize_hidden_state(p, z, conditions, num_layers)   # :143 dead value unless carry_state
+    state = ([hidden[i] for i in range(num_layers)], [cell[i] for i in range(num_layers)]) if carry_state else None
     current = torch.zeros((B,), dtype=torch.long)                      # :146 start token 0
     outs, inputs = [], []
     for t in range(T):
         inputs.append(current)
-        logits = _decoder_step(p, current, conditions, num_layers)
+        logits = _decoder_step(p, current, conditions, num_layers, state)
         outs.append(logits)
         use_tf = target_seq is not None and tf_mask is not None and bool(tf_mask[t])
         if use_tf:
@@ -255,7 +265,7 @@ def decoder_forward(p: Tree, z, conditions, num_layers: int, target_seq=None, ma
 
 def generate_with_temperature(p: Tree, z, conditions, num_layers: int, max_length: int = 80,
                               temperature: float = 1.0, early_stopping: bool = True, end_token: int = 2,
-                              return_margin: bool = False):
+                              return_margin: bool = False, carry_state: bool = False):
     """models/decoder_sampling.py:48-128.  Returns tokens [B, t_stop<=max_length] (int64).
 
     "Sampling" is argmax(softmax(logits/temperature)) (:110-117, F8).  With
@@ -263,14 +273,15 @@ def generate_with_temperature(p: Tree, z, conditions, num_layers: int, max_lengt
     classify near-tie disagreements instead of hiding them.
     """
     B = z.shape[0]
-    _ = initialize_hidden_state(p, z, conditions, num_layers)          # :75 dead value
+    hidden, cell = initialize_hidden_state(p, z, conditions, num_layers)   # :75 dead value unless carry_state
+    state = ([hidden[i] for i in range(num_layers)], [cell[i] for i in range(num_layers)]) if carry_state else None
     current = torch.zeros((B,), dtype=torch.long)                      # :78
     ended = torch.zeros((B,), dtype=torch.bool)                        # :81
     toks, margins = [], []
     for _t in range(max_length):
         if early_stopping and bool(ended.all()):                       # :87-88
             break
-        logits = _decoder_step(p, current, conditions, num_layers)
+        logits = _decoder_step(p, current, conditions, num_layers, state)
         probs = torch.softmax(logits / temperature, dim=1)             # :110-113
         current = torch.argmax(probs, dim=1)                           # :117
         toks.append(current)
@@ -371,11 +382,13 @@ def property_prediction_loss(z, predicted_properties, target_properties, propert
 
 
 def complete_vae_loss(params, x, conditions, num_layers, eps, tf_mask, beta=0.4, lambda_prop=0.1,
-                      lambda_collapse=0.01, free_bits=0.5, lambda_mi=0.0, target_mi=4.85, return_logits=False):
+                      lambda_collapse=0.01, free_bits=0.5, lambda_mi=0.0, target_mi=4.85, return_logits=False,
+                      carry_state=False):
     """complete_vae_loss.py:37-99 with ``property_predictor=None`` (train.py:186)."""
     mu, logvar = encoder_forward(params["encoder"], x, conditions, num_layers)       # :38
     z = reparameterize(mu, logvar, eps)                                              # :39
-    logits = decoder_forward(params["decoder"], z, conditions, num_layers, target_seq=x, tf_mask=tf_mask)  # :42
+    logits = decoder_forward(params["decoder"], z, conditions, num_layers, target_seq=x, tf_mask=tf_mask,
+                             carry_state=carry_state)                                # :42
     recon = reconstruction_loss(logits, x)                                           # :45
     kl = kl_divergence(mu, logvar, free_bits=free_bits)                              # :48
     collapse = posterior_collapse(mu, logvar, weight=lambda_collapse)                # :51 (target 4.85 default)

@@ -170,3 +170,44 @@ def test_philox_known_answer():
     assert philox_ref.philox4x32(0, 0, 0) == (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)
     full = 0xffffffffffffffff
     assert philox_ref.philox4x32(full, full, full) == (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)
+
+
+def test_carry_state_decoder_is_a_stacked_lstm_with_initial_state():
+    """carry_state=True (NOT the reference's behaviour): with teacher forcing everywhere the decoder is a
+    standard stacked LSTM over [Emb[tok_{t-1}]; cond] with h0 = (z_to_hidden(z) + condition_to_hidden(cond)) / 2 in every
+    layer and c0 = 0 (decoder.py:95-111) — cross-checked against torch.nn.LSTM; z now reaches the logits and
+    z_to_hidden / Wh receive gradients (they are exactly zero in the reference mode, F1)."""
+    cfg = O.Config(13, 8, 12, 6, 2, 3)
+    p = O.init_params(cfg, seed=21, dtype=torch.float64)
+    B, T = 5, 7
+    x, cond, eps, _ = O.synthetic_batch(B, T, cfg, seed=22)
+    xt, ct, z = torch.as_tensor(x).long(), torch.as_tensor(cond).double(), torch.as_tensor(eps).double()
+    mask = np.ones(T, dtype=bool)
+    lg = O.decoder_forward(p["decoder"], z, ct, cfg.num_layers, target_seq=xt, tf_mask=mask, carry_state=True)
+    d = p["decoder"]
+    ref = torch.nn.LSTM(cfg.embedding_dim + cfg.num_conditions, cfg.hidden_dim, num_layers=cfg.num_layers, batch_first=True).double()
+    with torch.no_grad():
+        for l in range(cfg.num_layers):
+            getattr(ref, f"weight_ih_l{l}").copy_(d[f"lstm_layer_{l}"]["Wx"]); getattr(ref, f"weight_hh_l{l}").copy_(d[f"lstm_layer_{l}"]["Wh"])
+            getattr(ref, f"bias_ih_l{l}").copy_(d[f"lstm_layer_{l}"]["bias"]); getattr(ref, f"bias_hh_l{l}").zero_()
+    tok_in = torch.cat([torch.zeros(B, 1, dtype=torch.long), xt[:, :-1]], dim=1)
+    inp = torch.cat([d["embedding"]["weight"][tok_in], ct.unsqueeze(1).expand(B, T, -1)], dim=2)
+    h0, c0 = O.initialize_hidden_state(d, z, ct, cfg.num_layers)
+    out, _ = ref(inp, (h0.contiguous(), c0.contiguous()))
+    assert torch.allclose(lg, O.linear(d["fc_out"], out), atol=1e-12)
+    # different z -> different logits; reference mode ignores z
+    lg2 = O.decoder_forward(d, z + 1.0, ct, cfg.num_layers, target_seq=xt, tf_mask=mask, carry_state=True)
+    assert float((lg2 - lg).abs().max()) > 1e-3
+    a = O.decoder_forward(d, z, ct, cfg.num_layers, target_seq=xt, tf_mask=mask)
+    b = O.decoder_forward(d, z + 1.0, ct, cfg.num_layers, target_seq=xt, tf_mask=mask)
+    assert torch.equal(a, b)
+    hyper = dict(beta=0.05, lambda_prop=0.1, lambda_collapse=0.001, free_bits=1.0, lambda_mi=0.01, target_mi=4.85)
+    _, (ge, gd) = O.loss_and_grads(p, xt, ct, cfg.num_layers, z, mask, carry_state=True, **hyper)
+    assert float(gd["z_to_hidden"]["weight"].abs().max()) > 0 and float(gd["lstm_layer_1"]["Wh"].abs().max()) > 0
+    assert float(gd["condition_to_hidden"]["bias"].abs().max()) > 0
+    _, (ge0, _) = O.loss_and_grads(p, xt, ct, cfg.num_layers, z, mask, **hyper)
+    # the reconstruction loss now reaches the encoder through z
+    assert float((ge["fc_mu"]["weight"] - ge0["fc_mu"]["weight"]).abs().max()) > 1e-6
+    # greedy sampling with state: first token equals the argmax of the first teacher-forced position
+    toks = O.generate_with_temperature(d, z, ct, cfg.num_layers, max_length=4, early_stopping=False, carry_state=True)
+    assert torch.equal(toks[:, 0], lg[:, 0].argmax(dim=1))
