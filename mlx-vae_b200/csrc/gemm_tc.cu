@@ -634,6 +634,7 @@ int gemm_tc(const TcGemm& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return 0;
   ARCVAE_REQUIRE(g.C != nullptr || g.Cb != nullptr || g.epi != TC_EPI_PLAIN || g.nseg > 1, "gemm_tc needs an output");
   ARCVAE_REQUIRE(g.epi != TC_EPI_LSTM_FWD || g.splitk <= 1, "fused LSTM step: no split-K");
+  if (gemm_ws_supported(g) && std::getenv("ARCVAE_NO_WS") == nullptr) return gemm_ws(g, st);
   ARCVAE_REQUIRE(!(g.a_mn && g.rm.tlist != nullptr), "row map needs a K-major A");
   ARCVAE_REQUIRE(g.rm.tlist == nullptr || (g.rm.Bt % TC_BM) == 0, "row-mapped tiles must not straddle timesteps");
   TcParams p;

@@ -115,6 +115,9 @@ struct TcGemm {
 };
 enum { TC_EPI_PLAIN = 0, TC_EPI_DEC_CELL_FWD = 1, TC_EPI_DEC_CELL_BWD = 2, TC_EPI_LSTM_FWD = 3 };
 int gemm_tc(const TcGemm& g, cudaStream_t st);
+// weight-stationary variant (gemm_ws.cu) for K <= 256, bf16 output / fused decoder cell; gemm_tc dispatches to it
+bool gemm_ws_supported(const TcGemm& g);
+int gemm_ws(const TcGemm& g, cudaStream_t st);
 int pick_splitk_tc(int M, int N, int K);
 int f32_to_bf16(const float* src, __nv_bfloat16* dst, long n, cudaStream_t st);
 int f32_to_bf16_pitched(const float* src, long R, int V, __nv_bfloat16* dst, int Vp, cudaStream_t st);   // pad columns zero

@@ -64,3 +64,32 @@ def test_splitk_large_k(M):
 
 def test_many_tiles_persistent(M):
     run(M, False, False, 128 * 300 + 5, 1024, 256, bias=True)
+
+
+@pytest.mark.parametrize("m,n,k,bias", [(4096, 1024, 256, True), (128 * 9 + 37, 256, 64, False), (5000, 512, 128, True),
+                                        (128 * 300, 1024, 256, True), (1024, 768, 192, True)])
+def test_weight_stationary_bf16_out(M, m, n, k, bias):
+    """K <= 256 with a bf16-only output dispatches to gemm_ws_kernel (csrc/gemm_ws.cu): weight panel resident in shared
+    memory, TMA-store epilogue.  Must equal the generic kernel (ARCVAE_NO_WS=1) bit for bit — same MMA order, same
+    rounding — and torch fp64 within bf16 output rounding."""
+    import os
+    lib = M._lib.load()
+    g = torch.Generator(device="cuda").manual_seed(m + n + k)
+    A = torch.randn(m, k, device="cuda", generator=g).to(torch.bfloat16)
+    B = torch.randn(n, k, device="cuda", generator=g).to(torch.bfloat16)
+    bvec = torch.randn(n, device="cuda", generator=g) if bias else None
+    outs = []
+    for env in (False, True):
+        if env:
+            os.environ["ARCVAE_NO_WS"] = "1"
+        try:
+            Cb = torch.full((m, n), 7.0, device="cuda", dtype=torch.bfloat16)
+            M._lib.check(lib.arcvae_gemm_bf16(0, 0, m, n, k, A.data_ptr(), k, B.data_ptr(), k, None, 0, Cb.data_ptr(), n,
+                                              bvec.data_ptr() if bias else None, 0, 1, 0))
+            torch.cuda.synchronize()
+            outs.append(Cb)
+        finally:
+            os.environ.pop("ARCVAE_NO_WS", None)
+    ref = A.double() @ B.double().T + (bvec.double() if bias else 0.0)
+    assert rel_err(outs[0].float().cpu(), ref.cpu()) < 1e-2
+    assert torch.equal(outs[0], outs[1]), float((outs[0].float() - outs[1].float()).abs().max())
