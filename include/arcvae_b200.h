@@ -155,7 +155,17 @@ size_t arcvae_decoder_scratch_bytes(const arcvae_dims* d, int B, int T);
 int arcvae_decoder_forward(const arcvae_dims* d, const arcvae_decoder_params* p, const float* cond,
                            const int32_t* target, const uint8_t* tf_mask_host, int B, int T, float* logits_tm,
                            int32_t* dec_inputs_tm, void* tape, size_t tape_bytes, int precision, void* stream);
-/* dlogits_tm [T,B,V] (destroyed); accumulates into `g`. */
+/* fc_out with the cross-entropy in its epilogue (bf16 fused path only: arcvae_decoder_ce_supported): the fp32 logits are
+ * never written.  Per row: CE into *ce_sum (device double, accumulated: pass &stats[2L+2] of arcvae_loss_fwd_bwd),
+ * d logits = (softmax - onehot(target)) * ce_scale as bf16 into the tape, and the greedy feedback token where the host
+ * coin of the position is false (decoder.py:185).  ce_scale = 1 / (GLOBAL number of positions): unmasked mean of
+ * losses/recon.py:59-60.  Follow with arcvae_decoder_backward(dlogits_tm = NULL). */
+int arcvae_decoder_ce_supported(const arcvae_dims* d, int B, int precision);
+int arcvae_decoder_forward_ce(const arcvae_dims* d, const arcvae_decoder_params* p, const float* cond,
+                              const int32_t* target, const uint8_t* tf_mask_host, int B, int T, float ce_scale,
+                              double* ce_sum, int32_t* dec_inputs_tm, void* tape, size_t tape_bytes, int precision,
+                              void* stream);
+/* dlogits_tm [T,B,V] (destroyed), or NULL after arcvae_decoder_forward_ce; accumulates into `g`. */
 int arcvae_decoder_backward(const arcvae_dims* d, const arcvae_decoder_params* p, const float* cond, int B, int T,
                             float* dlogits_tm, void* tape, size_t tape_bytes, const arcvae_decoder_params* g,
                             void* scratch, size_t scratch_bytes, int precision, void* stream);
@@ -184,7 +194,10 @@ int arcvae_reparam_backward(const float* dz, const float* z, const float* mu, in
  * phases: bit0 = batch statistics into `stats` (zeroed by the caller), bit1 = finish (losses[], dlogits,
  * dmu, dlogvar, z).  Single GPU: phases=3 (one cooperative launch).  Data parallel: phases=1,
  * all-reduce(sum) `stats`, phases=2.  Any of logits / mu may be NULL to skip that half.
- * dlogits may alias logits.  eps==NULL -> Philox(seed, offset). */
+ * dlogits may alias logits.  eps==NULL -> Philox(seed, offset).
+ * phases bit2 (value 4, with logits == NULL and T given): the cross-entropy sum of this shard already sits in
+ * stats[2L+2] (arcvae_decoder_forward_ce accumulated it there, scaled d logits are in the decoder tape); the kernel adds
+ * the token count B*T and reports recon / total from it. */
 int arcvae_loss_fwd_bwd(const float* logits, int64_t ls_b, int64_t ls_t, const int32_t* targets, int64_t ts_b,
                         int64_t ts_t, int B, int T, int V, int pad_token, const float* mu, const float* logvar,
                         const float* eps, int L, const arcvae_loss_hyper* hyper, uint64_t seed, uint64_t offset,

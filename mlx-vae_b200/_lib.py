@@ -80,6 +80,10 @@ SIGNATURES = {
     "arcvae_decoder_forward": (C.c_int, [C.POINTER(Dims), C.POINTER(DecoderParams), C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
                                          C.c_void_p]),
+    "arcvae_decoder_ce_supported": (C.c_int, [C.POINTER(Dims), C.c_int, C.c_int]),
+    "arcvae_decoder_forward_ce": (C.c_int, [C.POINTER(Dims), C.POINTER(DecoderParams), C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                            C.c_int, C.c_void_p]),
     "arcvae_decoder_backward": (C.c_int, [C.POINTER(Dims), C.POINTER(DecoderParams), C.c_void_p, C.c_int, C.c_int,
                                           C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(DecoderParams), C.c_void_p,
                                           C.c_size_t, C.c_int, C.c_void_p]),

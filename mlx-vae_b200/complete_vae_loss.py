@@ -4,6 +4,8 @@ from __future__ import annotations
 
 from typing import Optional
 
+import os
+
 import torch
 
 from . import _lib
@@ -12,24 +14,44 @@ from .losses._fused import fused_loss, make_hyper
 
 def _run(encoder, decoder, property_predictor, x, conditions, beta, lambda_prop, lambda_collapse,
          teacher_forcing_ratio, free_bits, lambda_mi, target_mi, eps, tf_mask, seed, pad_mask, backward, allreduce,
-         return_logits=False, backward_hooks=None, eps_offset=0):
+         return_logits=False, backward_hooks=None, eps_offset=0, ce_world=1, info=None):
     if property_predictor is not None:
         # the reference would raise TypeError here (complete_vae_loss.py:63-67 vs losses/prop.py:5-11, F10)
         raise NotImplementedError("property_predictor must be None, as in train.py:186")
     mu, logvar = encoder(x, conditions)                                                         # :38
+    hp = make_hyper(beta, lambda_prop, lambda_collapse, free_bits, lambda_mi, target_mi, 4.85, pad_mask)
+    targets = encoder._tokens(x)
+    B_, T_ = targets.shape
     z_in = None
     if getattr(decoder, "carry_state", False):
         # extension mode: the decoder consumes z (reference mode: z is dead, F1); same Philox stream as the loss kernel
         z_in = encoder.reparameterize(mu, logvar, eps, seed=seed, offset=eps_offset)            # :39
-    logits = decoder(z_in, conditions, target_seq=x, teacher_forcing_ratio=teacher_forcing_ratio,
-                     tf_mask=tf_mask)                                                           # :42
-    hp = make_hyper(beta, lambda_prop, lambda_collapse, free_bits, lambda_mi, target_mi, 4.85, pad_mask)
-    targets = encoder._tokens(x)
-    out = fused_loss(logits, targets, mu, logvar, hp, eps=eps, seed=seed, offset=eps_offset, pad_token=decoder.pad_token,
-                     want_grads=backward, want_z=True, inplace_dlogits=backward and not return_logits,
-                     allreduce=allreduce)                                                       # :39, :45-82
+    fuse_ce = (backward and not return_logits and not pad_mask and os.environ.get("ARCVAE_NO_FUSED_CE") is None
+               and decoder.ce_supported(B_))
+    if fuse_ce:
+        # training step on the fused bf16 path: fc_out + cross-entropy + d logits + greedy feedback in ONE GEMM epilogue;
+        # the fp32 logits never reach HBM.  Unmasked mean over the GLOBAL batch (losses/recon.py:59-60): under data
+        # parallelism the shards are equal (trainer contract), so the global position count is world x B x T.
+        L_ = mu.shape[1]
+        stats = torch.zeros(2 * L_ + 6, dtype=torch.float64, device=mu.device)
+        decoder.forward_ce(conditions, targets, stats[2 * L_ + 2:2 * L_ + 3], 1.0 / (float(ce_world) * B_ * T_),
+                           teacher_forcing_ratio, tf_mask=tf_mask)                              # :42, :45
+        out = fused_loss(None, None, mu, logvar, hp, eps=eps, seed=seed, offset=eps_offset, pad_token=decoder.pad_token,
+                         want_grads=True, want_z=True, allreduce=allreduce, stats=stats, ce_T=T_)   # :39, :48-82
+        logits = None
+    else:
+        logits = decoder(z_in, conditions, target_seq=x, teacher_forcing_ratio=teacher_forcing_ratio,
+                         tf_mask=tf_mask)                                                       # :42
+        out = fused_loss(logits, targets, mu, logvar, hp, eps=eps, seed=seed, offset=eps_offset, pad_token=decoder.pad_token,
+                         want_grads=backward, want_z=True, inplace_dlogits=backward and not return_logits,
+                         allreduce=allreduce)                                                   # :39, :45-82
     d = {k: out.losses[i] for i, k in enumerate(_lib.LOSS_KEYS)}                                # :86-99
     d.update(mu=mu, logvar=logvar, z=out.z)
+    # under data parallelism the unfused path reports recon = local CE / global tokens (a partial the trainer sums through
+    # the gradient all-reduce); on the fused-CE path the CE sum is part of the all-reduced statistics: already global
+    if info is not None:
+        info["recon_is_global"] = bool(fuse_ce and allreduce is not None)
+        info["fused_ce"] = bool(fuse_ce)
     if return_logits:
         d["logits"] = logits
     if allreduce is not None and not backward:
@@ -45,7 +67,7 @@ def _run(encoder, decoder, property_predictor, x, conditions, beta, lambda_prop,
             _lib.check(_lib.load().arcvae_reparam_backward(dz.data_ptr(), z_in.data_ptr(), mu.data_ptr(), B_, L_,
                                                            out.dmu.data_ptr(), out.dlogvar.data_ptr(), _lib.stream_ptr()))
         if backward_hooks is not None:
-            backward_hooks.after_decoder_backward(decoder, d)
+            backward_hooks.after_decoder_backward(decoder, d, bool(fuse_ce and allreduce is not None))
         encoder.backward(out.dmu, out.dlogvar)
     return d
 

@@ -93,6 +93,10 @@ struct DecTape {
   uint8_t* mask;                     // [T]
   __nv_bfloat16* hdb[ARCVAE_MAX_LAYERS];   // bf16 [R,H] copies (tensor-core operands)
   __nv_bfloat16* gates_b[ARCVAE_MAX_LAYERS];   // fused path: bf16 [R,3H] activated gates, tile-permuted
+  // fc_out with the cross-entropy in its epilogue (arcvae_decoder_forward_ce)
+  __nv_bfloat16* dlb;                // bf16 [R,Vp] d logits
+  int32_t* xT;                       // [T,B] targets, time-major
+  uint8_t* fb;                       // [T] position t feeds argmax(logits_t) to t+1
 };
 
 static size_t dec_tape_layout(const arcvae_dims& d, int B, int T, void* base, size_t cap, DecTape* t) {
@@ -109,6 +113,9 @@ static size_t dec_tape_layout(const arcvae_dims& d, int B, int T, void* base, si
   tt.mask = a.take<uint8_t>((size_t)T + 16);
   for (int l = 0; l < d.NL; l++) tt.hdb[l] = a.take<__nv_bfloat16>(R * d.H);
   for (int l = 0; l < d.NL; l++) tt.gates_b[l] = a.take<__nv_bfloat16>(R * 3 * d.H);   // layer 0 too: no recompute in backward
+  tt.dlb = a.take<__nv_bfloat16>(R * (size_t)((d.V + 7) / 8 * 8));
+  tt.xT = a.take<int32_t>(R);
+  tt.fb = a.take<uint8_t>((size_t)T + 16);
   if (t) *t = tt;
   return align_up(a.off, 256);
 }
@@ -180,11 +187,15 @@ static int upload_ints(int* dst, const int* src, int n, cudaStream_t st) {
   return 0;
 }
 
+struct CeArgs {                        // fc_out + cross-entropy + d logits + greedy feedback in one GEMM epilogue
+  const int32_t* xT; const uint8_t* fb; int32_t* in_tok; __nv_bfloat16* dlb; int Vp; double* ce_sum; float scale;
+};
+
 // one batched pass of the decoder stack over the rows selected by `rm`
 static int dec_stack_forward(const arcvae_dims& d, const arcvae_decoder_params* p, const DecPrep& pr, const float* cond,
                              const int32_t* in_tok, int B, int nrows, RowMap rm, long rows_total, float* const* hd,
                              __nv_bfloat16* const* hdb, float* const* G, __nv_bfloat16* const* gates_b, float* logits,
-                             int precision, bool fused, cudaStream_t st) {
+                             int precision, bool fused, cudaStream_t st, const CeArgs* ce = nullptr) {
   const int H = d.H, H3 = 3 * d.H;
   const bool bf = precision == ARCVAE_PREC_BF16;
   ARCVAE_TRY(dec_cell0_fwd(pr.table, pr.wc, in_tok, cond, B, d.C, H, d.V, nrows, rm, fused ? nullptr : hd[0],
@@ -204,6 +215,17 @@ static int dec_stack_forward(const arcvae_dims& d, const arcvae_decoder_params* 
                           Mat{pr.Wxc[l], pr.Wxcb[l], H}, G[l], H3, pr.bc[l], false, rm, rows_total, st));
       ARCVAE_TRY(dec_cell_fwd(G[l], hd[l], bf ? hdb[l] : nullptr, H, nrows, rm, st));
     }
+  }
+  if (ce != nullptr) {
+    TcGemm g{};
+    g.M = nrows; g.N = d.V; g.K = H;
+    g.A = hdb[d.NL - 1]; g.lda = H; g.a_mn = false;
+    g.B = pr.Woutb; g.ldb = H; g.b_mn = false;
+    g.bias = p->fc_out_b; g.accumulate = false; g.splitk = 1; g.rm = rm; g.a_rows_total = rows_total;
+    g.epi = TC_EPI_CE;
+    g.ce_target = ce->xT; g.ce_fb = ce->fb; g.ce_tok = ce->in_tok; g.ce_B = B; g.ce_dl = ce->dlb; g.ce_ldl = ce->Vp;
+    g.ce_sum = ce->ce_sum; g.ce_scale = ce->scale;
+    return gemm_tc(g, st);
   }
   ARCVAE_TRY(gemm_any(precision, 0, 1, nrows, d.V, H, Mat{fused ? nullptr : hd[d.NL - 1], bf ? hdb[d.NL - 1] : nullptr, H},
                       Mat{p->fc_out_w, pr.Woutb, H}, logits, d.V, p->fc_out_b, false, rm, rows_total, st));
@@ -228,14 +250,15 @@ extern "C" size_t arcvae_decoder_scratch_bytes(const arcvae_dims* d, int B, int 
   return d ? dec_scratch_layout(*d, B, T, nullptr, 0, nullptr) : 0;
 }
 
-extern "C" int arcvae_decoder_forward(const arcvae_dims* d, const arcvae_decoder_params* p, const float* cond,
-                                      const int32_t* target, const uint8_t* tf_mask_host, int B, int T,
-                                      float* logits_tm, int32_t* dec_inputs_tm, void* tape, size_t tape_bytes,
-                                      int precision, void* stream) {
+// ce_sum != nullptr: fc_out runs with the cross-entropy in its epilogue (no logits tensor); see arcvae_decoder_forward_ce
+static int decoder_forward_impl(const arcvae_dims* d, const arcvae_decoder_params* p, const float* cond,
+                                const int32_t* target, const uint8_t* tf_mask_host, int B, int T, float* logits_tm,
+                                int32_t* dec_inputs_tm, void* tape, size_t tape_bytes, int precision, float ce_scale,
+                                double* ce_sum, void* stream) {
   ARCVAE_TRY(check_dims_dec(d));
   ARCVAE_REQUIRE(B > 0 && T > 0, "empty batch / sequence");
   ARCVAE_REQUIRE(precision == ARCVAE_PREC_FP32 || precision == ARCVAE_PREC_BF16, "precision");
-  ARCVAE_REQUIRE(logits_tm != nullptr, "logits output");
+  ARCVAE_REQUIRE(logits_tm != nullptr || ce_sum != nullptr, "logits output");
   cudaStream_t st = (cudaStream_t)stream;
   DecTape tp;
   size_t need = dec_tape_layout(*d, B, T, tape, tape_bytes, &tp);
@@ -281,16 +304,50 @@ extern "C" int arcvae_decoder_forward(const arcvae_dims* d, const arcvae_decoder
     k_init_dec_inputs<<<grid, 256, 0, st>>>(target, tp.mask, B, T, tp.in_tok);
     ARCVAE_LAUNCHED();
   }
+  CeArgs ce{};
+  if (ce_sum != nullptr) {
+    ARCVAE_REQUIRE(target != nullptr && dec_fused_ok(*d, precision, B, true) && d->V <= 128,
+                   "fused cross-entropy needs targets, the fused bf16 decoder path (H % 64 == 0, B % 128 == 0) and V <= 128");
+    std::vector<int> packed((T + 3) / 4, 0);                  // fb[t]: position t feeds argmax(logits_t) to position t+1
+    for (int t = 0; t + 1 < T; t++)
+      if (!coin[t]) packed[t >> 2] |= 1 << (8 * (t & 3));
+    ARCVAE_TRY(upload_ints(reinterpret_cast<int*>(tp.fb), packed.data(), (int)packed.size(), st));
+    ARCVAE_TRY(transpose_tokens(target, B, T, tp.xT, st));
+    ce = CeArgs{tp.xT, tp.fb, tp.in_tok, tp.dlb, (d->V + 7) / 8 * 8, ce_sum, ce_scale};
+  }
   for (int lv = 0; lv <= maxlevel; lv++) {
     RowMap rm{tp.tlists + off_t[lv], B};
     int nrows = n_t[lv] * B;
     ARCVAE_TRY(dec_stack_forward(*d, p, tp.prep, cond, tp.in_tok, B, nrows, rm, (long)T * B, tp.hd, tp.hdb, tp.G,
-                                 tp.gates_b, logits_tm, precision, dec_fused_ok(*d, precision, B, true), st));
-    ARCVAE_TRY(argmax_feedback(logits_tm, tp.tlists + off_f[lv], n_f[lv], B, d->V, tp.in_tok, st));
+                                 tp.gates_b, logits_tm, precision, dec_fused_ok(*d, precision, B, true), st,
+                                 ce_sum != nullptr ? &ce : nullptr));
+    if (ce_sum == nullptr) ARCVAE_TRY(argmax_feedback(logits_tm, tp.tlists + off_f[lv], n_f[lv], B, d->V, tp.in_tok, st));
   }
   if (dec_inputs_tm != nullptr)
     ARCVAE_CUDA(cudaMemcpyAsync(dec_inputs_tm, tp.in_tok, (size_t)T * B * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
   return 0;
+}
+
+extern "C" int arcvae_decoder_forward(const arcvae_dims* d, const arcvae_decoder_params* p, const float* cond,
+                                      const int32_t* target, const uint8_t* tf_mask_host, int B, int T,
+                                      float* logits_tm, int32_t* dec_inputs_tm, void* tape, size_t tape_bytes,
+                                      int precision, void* stream) {
+  ARCVAE_REQUIRE(logits_tm != nullptr, "logits output");
+  return decoder_forward_impl(d, p, cond, target, tf_mask_host, B, T, logits_tm, dec_inputs_tm, tape, tape_bytes, precision,
+                              0.f, nullptr, stream);
+}
+
+extern "C" int arcvae_decoder_ce_supported(const arcvae_dims* d, int B, int precision) {
+  return (d != nullptr && dec_fused_ok(*d, precision, B, true) && d->V <= 128) ? 1 : 0;
+}
+
+extern "C" int arcvae_decoder_forward_ce(const arcvae_dims* d, const arcvae_decoder_params* p, const float* cond,
+                                         const int32_t* target, const uint8_t* tf_mask_host, int B, int T, float ce_scale,
+                                         double* ce_sum, int32_t* dec_inputs_tm, void* tape, size_t tape_bytes,
+                                         int precision, void* stream) {
+  ARCVAE_REQUIRE(ce_sum != nullptr && ce_scale > 0.f, "ce_sum / ce_scale");
+  return decoder_forward_impl(d, p, cond, target, tf_mask_host, B, T, nullptr, dec_inputs_tm, tape, tape_bytes, precision,
+                              ce_scale, ce_sum, stream);
 }
 
 extern "C" int arcvae_decoder_backward(const arcvae_dims* d, const arcvae_decoder_params* p, const float* cond, int B,
@@ -299,7 +356,7 @@ extern "C" int arcvae_decoder_backward(const arcvae_dims* d, const arcvae_decode
                                        int precision, void* stream) {
   ARCVAE_TRY(check_dims_dec(d));
   ARCVAE_REQUIRE(precision == ARCVAE_PREC_FP32 || precision == ARCVAE_PREC_BF16, "precision");
-  ARCVAE_REQUIRE(g != nullptr && dlogits_tm != nullptr, "grad pointers");
+  ARCVAE_REQUIRE(g != nullptr, "grad pointers");
   cudaStream_t st = (cudaStream_t)stream;
   DecTape tp;
   size_t need = dec_tape_layout(*d, B, T, tape, tape_bytes, &tp);
@@ -315,11 +372,36 @@ extern "C" int arcvae_decoder_backward(const arcvae_dims* d, const arcvae_decode
   const bool bf = precision == ARCVAE_PREC_BF16;
   const bool fused = dec_fused_ok(*d, precision, B, true);
   const int Vp = (V + 7) / 8 * 8;            // row pitch of the bf16 copy of dlogits
-  if (bf) ARCVAE_TRY(f32_to_bf16_pitched(dlogits_tm, R, V, sc.dlb, Vp, st));
+  // dlogits_tm == NULL: the forward was arcvae_decoder_forward_ce and the bf16 d logits already sit in the tape
+  ARCVAE_REQUIRE(dlogits_tm != nullptr || (bf && fused), "dlogits (or a preceding arcvae_decoder_forward_ce)");
+  if (dlogits_tm == nullptr) sc.dlb = tp.dlb;
+  else if (bf) ARCVAE_TRY(f32_to_bf16_pitched(dlogits_tm, R, V, sc.dlb, Vp, st));
   // fc_out: logits = h_top @ Wout^T + b
-  ARCVAE_TRY(gemm_any(precision, 1, 0, V, H, (int)R, Mat{dlogits_tm, bf ? sc.dlb : nullptr, bf && fused ? Vp : V},
-                      Mat{fused ? nullptr : tp.hd[top], bf ? tp.hdb[top] : nullptr, H}, g->fc_out_w, H, nullptr, true, id, R, st));
-  ARCVAE_TRY(colsum(dlogits_tm, R, V, V, g->fc_out_b, st));
+  const bool fuse_out = fused && H <= 256 && (H % 64) == 0 && V <= 128 && std::getenv("ARCVAE_NO_FUSED_DWOUT") == nullptr;
+  if (fuse_out) {
+    // dWout = dlogits^T h_top and the bias gradient (row sums of dlogits^T onehot: every one-hot row sums to 1) in ONE
+    // pass over the bf16 d logits
+    ARCVAE_TRY(build_onehot(tp.in_tok, R, V, cond, B, C, sc.onehot, st));
+    ARCVAE_CUDA(cudaMemsetAsync(sc.segtmp, 0, (size_t)128 * SCATTER_NW * sizeof(float), st));
+    TcGemm q{};
+    q.M = V; q.N = H; q.K = (int)R;
+    q.A = sc.dlb; q.lda = Vp; q.a_mn = true; q.b_mn = true;
+    q.accumulate = true; q.rm = id; q.a_rows_total = R;
+    q.nseg = 2;
+    q.seg[0] = {tp.hdb[top], H, H, 0, g->fc_out_w, H};
+    q.seg[1] = {sc.onehot, SCATTER_NW, SCATTER_NW, 0, sc.segtmp, SCATTER_NW};
+    long sk = (2 * 148) / 2;
+    const long maxs = cdiv(R, 64) / 8;
+    if (sk > maxs) sk = maxs;
+    q.splitk = sk < 1 ? 1 : (int)sk;
+    ARCVAE_TRY(gemm_tc(q, st));
+    ARCVAE_TRY(rowsum_add(sc.segtmp, V, SCATTER_NW, V, g->fc_out_b, st));
+  } else {
+    ARCVAE_TRY(gemm_any(precision, 1, 0, V, H, (int)R, Mat{dlogits_tm, bf ? sc.dlb : nullptr, bf && fused ? Vp : V},
+                        Mat{fused ? nullptr : tp.hd[top], bf ? tp.hdb[top] : nullptr, H}, g->fc_out_w, H, nullptr, true, id, R, st));
+    if (dlogits_tm != nullptr) ARCVAE_TRY(colsum(dlogits_tm, R, V, V, g->fc_out_b, st));
+    else ARCVAE_TRY(colsum_bf16(sc.dlb, R, V, Vp, g->fc_out_b, st));
+  }
   float* dh = sc.dh[0];
   float* dh_next = sc.dh[1];
 
@@ -337,7 +419,7 @@ extern "C" int arcvae_decoder_backward(const arcvae_dims* d, const arcvae_decode
     };
     // one-hot of the fed tokens (+ cond hi/lo columns): operand of the layer-0 table scatter and, through its row sums,
     // of the bias gradients of the upper layers
-    ARCVAE_TRY(build_onehot(tp.in_tok, R, V, cond, B, C, sc.onehot, st));
+    if (!fuse_out) ARCVAE_TRY(build_onehot(tp.in_tok, R, V, cond, B, C, sc.onehot, st));
     const bool fuse_dw = H <= 256;
     __nv_bfloat16* cur = sc.dGb;
     __nv_bfloat16* nxt = sc.dGb2;

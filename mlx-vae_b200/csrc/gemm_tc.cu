@@ -45,6 +45,8 @@ struct TcParams {
   bf16* gates_b; bf16* hb_out; bf16* dg_out;
   int Hh;
   const bf16* pre_b; const float* c_prev; float* c_out; float* hf_out;     // TC_EPI_LSTM_FWD
+  const int32_t* ce_target; const uint8_t* ce_fb; int32_t* ce_tok; int ce_B; bf16* ce_dl; int ce_ldl; double* ce_sum;
+  float ce_scale;                                                          // TC_EPI_CE
   // multi-segment B (weight gradients that share the A operand): column tile ni multiplies A with its own B matrix
   // (rows shifted by seg_shift[ni]; negative TMA coordinates zero-fill) into its own C
   int nseg; int segN[3]; int seg_shift[3]; float* segC[3]; int seg_ldc[3];
@@ -161,9 +163,121 @@ struct __align__(8) TcShared {
   uint32_t tmem_base;
 };
 
-// LSTM = true: the instantiation whose epilogue is the fused encoder LSTM step (TC_EPI_LSTM_FWD); kept apart so that its
+// ---- fc_out epilogue with the cross-entropy (TC_EPI_CE) ---------------------------------------------------------------
+// NCH = number of 16-column chunks of the row (0: run-time, up to 8).  Called by ALL lanes of the warp (tcgen05.ld is
+// .sync.aligned); rows outside the matrix compute on garbage and store nothing.
+template <int NCH>
+__device__ __forceinline__ void ce_epilogue(const TcParams& p, uint32_t taddr, int half, int q, int lane, bool row_ok, long grow,
+                                            float4 (*ce_x)[32], float& ce_acc) {
+  constexpr int MAXC = NCH > 0 ? (NCH + 1) / 2 : 4;            // chunks per warp (first warp takes the larger share)
+  const int nch = NCH > 0 ? NCH : ((p.N + 15) >> 4);
+  const int c_lo = half == 0 ? 0 : (nch + 1) >> 1;
+  const int c_hi = half == 0 ? (nch + 1) >> 1 : nch;
+  const int V = p.N;
+  float v[MAXC * 16];
+#pragma unroll
+  for (int i = 0; i < MAXC; i++) {
+    const int ch = c_lo + i;
+    if (ch < c_hi) {                                           // warp-uniform
+      uint32_t r[16];
+      tc::tmem_ld16(taddr + ch * 16, r);
+      float4 bv[4];
+#pragma unroll
+      for (int k4 = 0; k4 < 4; k4++)
+      {
+        const int c4 = ch * 16 + k4 * 4;
+        if (c4 + 3 < V) bv[k4] = __ldg(reinterpret_cast<const float4*>(p.bias + ch * 16) + k4);
+        else bv[k4] = make_float4(c4 < V ? __ldg(p.bias + c4) : 0.f, c4 + 1 < V ? __ldg(p.bias + c4 + 1) : 0.f,
+                                  c4 + 2 < V ? __ldg(p.bias + c4 + 2) : 0.f, 0.f);
+      }
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int k4 = 0; k4 < 4; k4++) {
+        const float b4[4] = {bv[k4].x, bv[k4].y, bv[k4].z, bv[k4].w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int col = ch * 16 + k4 * 4 + j;
+          v[i * 16 + k4 * 4 + j] = col < V ? __uint_as_float(r[k4 * 4 + j]) + b4[j] : -INFINITY;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; j++) v[i * 16 + j] = -INFINITY;
+    }
+  }
+  // local max / argmax (four independent chains, merged lowest-index-first)
+  float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  int b4i[4] = {0, 1, 2, 3};
+#pragma unroll
+  for (int j = 0; j < MAXC * 16; j += 4)
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      if (v[j + k] > m4[k]) { m4[k] = v[j + k]; b4i[k] = j + k; }
+  float mloc = m4[0];
+  int bloc = b4i[0];
+#pragma unroll
+  for (int k = 1; k < 4; k++)
+    if (m4[k] > mloc || (m4[k] == mloc && b4i[k] < bloc)) { mloc = m4[k]; bloc = b4i[k]; }
+  bloc += c_lo * 16;
+  const int tgt = row_ok ? p.ce_target[grow] : 0;
+  const int tl = (tgt >= c_lo * 16 && tgt < c_hi * 16) ? tgt - c_lo * 16 : -1;   // target index inside this warp's slice
+  float s4[4] = {0.f, 0.f, 0.f, 0.f};
+  float lt = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXC * 16; j += 4)
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (j + k == tl) lt = v[j + k];
+      v[j + k] = __expf(v[j + k] - mloc);                      // exp(-inf) = 0 for padding columns
+      s4[k] += v[j + k];
+    }
+  const float sloc = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+  // exchange with the other warp of this lane quarter
+  ce_x[q * 2 + half][lane] = make_float4(mloc, sloc, lt, __int_as_float(bloc));
+  asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+  const float4 o = ce_x[q * 2 + (half ^ 1)][lane];
+  asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");    // slot reusable for the next tile
+  const float m = fmaxf(mloc, o.x);
+  const float fl = __expf(mloc - m), fo = __expf(o.x - m);
+  const float ssum = sloc * fl + o.y * fo;
+  if (!row_ok) return;
+  if (half == 0) {
+    ce_acc += (m + __logf(ssum)) - (lt + o.z);
+    const int t = (int)(grow / p.ce_B);
+    if (p.ce_fb[t]) {                                          // decoder.py:185: next input = argmax(logits_t), lowest index on ties
+      const int bo = __float_as_int(o.w);
+      p.ce_tok[grow + p.ce_B] = (o.x > mloc) ? bo : bloc;
+    }
+  }
+  const float inv = p.ce_scale * fl / ssum;
+  bf16* drow = p.ce_dl + grow * p.ce_ldl + c_lo * 16;
+#pragma unroll
+  for (int i = 0; i < MAXC; i++) {
+    const int ch = c_lo + i;
+    if (ch < c_hi) {
+#pragma unroll
+      for (int h8 = 0; h8 < 2; h8++) {
+        if (ch * 16 + h8 * 8 < p.ce_ldl) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const int e0 = i * 16 + h8 * 8 + 2 * j;
+            const float g0 = v[e0] * inv - (e0 == tl ? p.ce_scale : 0.f);
+            const float g1 = v[e0 + 1] * inv - (e0 + 1 == tl ? p.ce_scale : 0.f);
+            __nv_bfloat162 tt = __floats2bfloat162_rn(g0, g1);
+            pk[j] = *reinterpret_cast<uint32_t*>(&tt);
+          }
+          *reinterpret_cast<uint4*>(drow + i * 16 + h8 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+    }
+  }
+}
+
+// MODE 1: the instantiation whose epilogue is the fused encoder LSTM step (TC_EPI_LSTM_FWD); kept apart so that its
 // register footprint does not touch the code generation of the other epilogues
-template <bool LSTM>
+// MODE 2: fc_out with the cross-entropy / d logits / greedy feedback in the epilogue (TC_EPI_CE)
+template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2, const TcParams p) {
@@ -292,9 +406,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ===================================================== epilogue (warps 2..9 -> TMEM lane quarters 2,3,0,1,2,3,0,1)
+    constexpr bool LSTM = (MODE == 1);
+    __shared__ float4 ce_x_storage[MODE == 2 ? 8 : 1][32];
+    float4 (*ce_x)[32] = ce_x_storage;
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;          // which half of the tile's 16-column chunks this warp handles
     int it = 0;
+    float ce_acc = 0.f;                        // MODE 2: this thread's cross-entropy sum
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
       const int ni = tile % p.nt;
       const int mi = (tile / p.nt) % p.mt;
@@ -323,7 +441,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint8_t* srow = scr + lane * TC_SCR_PITCH;
       const int rows_here = min(32, p.M - (m0 + q * 32));          // rows of this warp's quarter inside the matrix
       const long grow0 = rows_here > 0 ? p.rm(m0 + q * 32) : 0;     // first global row (a row tile never straddles timesteps)
-      if (LSTM) {
+      if (MODE == 2) {
+        // a row of V <= 128 logits sits in one TMEM lane: the two warps of a lane quarter split its 16-column chunks
+        // (warp `half` 0 takes the first ceil(n/2) chunks), reduce max / sum-exp / target logit / argmax locally and
+        // combine through 16 bytes of shared memory per row
+        const int nchv = (p.N + 15) >> 4;
+        switch (nchv) {
+          case 5: ce_epilogue<5>(p, taddr, half, q, lane, row_ok, grow, ce_x, ce_acc); break;      // V = 80 (default vocabulary)
+          default: ce_epilogue<0>(p, taddr, half, q, lane, row_ok, grow, ce_x, ce_acc); break;
+        }
+      } else if (LSTM) {
         // one encoder LSTM step (MLX nn.LSTM loop body, models/encoder.py:98-101).  Accumulator columns of this 256-wide
         // tile: [0,64) = i, [64,128) = f, [128,192) = g, [192,256) = o of hidden units 64*ni .. 64*ni+63 (tile-permuted
         // Wh); this warp: units half*32 .. +32 in two chunks of 16.  Thread = batch row: P_t, c_{t-1} in, gates / c_t / h_t
@@ -552,6 +679,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&sh->tmem_empty[acc]);
     }
+    if (MODE == 2) {
+      const float w = warp_sum(ce_acc);
+      if (lane == 0 && half == 0 && w != 0.f) atomicAdd(p.ce_sum, (double)w);
+    }
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -684,6 +815,15 @@ int gemm_tc(const TcGemm& g, cudaStream_t st) {
   p.epi = g.epi; p.gates_b = g.gates_b; p.hb_out = g.hb_out; p.dg_out = g.dg_out;
   p.Hh = g.Hh;
   p.pre_b = g.pre_b; p.c_prev = g.c_prev; p.c_out = g.c_out; p.hf_out = g.hf_out;
+  p.ce_target = g.ce_target; p.ce_fb = g.ce_fb; p.ce_tok = g.ce_tok; p.ce_B = g.ce_B; p.ce_dl = g.ce_dl; p.ce_ldl = g.ce_ldl;
+  p.ce_sum = g.ce_sum; p.ce_scale = g.ce_scale;
+  if (g.epi == TC_EPI_CE) {
+    ARCVAE_REQUIRE(g.N <= 128 && !g.a_mn && !g.b_mn && p.splitk == 1 && g.nseg <= 1 && g.bias != nullptr,
+                   "fused cross-entropy: one N tile (V <= 128), K-major operands, bias, no split-K");
+    ARCVAE_REQUIRE(g.ce_target && g.ce_fb && g.ce_tok && g.ce_dl && g.ce_sum && g.ce_B > 0 && (g.ce_ldl % 8) == 0 &&
+                   g.ce_ldl >= g.N && g.ce_ldl <= 128 && (reinterpret_cast<uintptr_t>(g.ce_dl) & 15) == 0,
+                   "fused cross-entropy: outputs");
+  }
   if (g.epi == TC_EPI_LSTM_FWD) {
     ARCVAE_REQUIRE(g.N == 4 * g.Hh && g.Hh % 64 == 0 && !g.a_mn && !g.b_mn && p.splitk == 1 && g.nseg <= 1 &&
                    g.rm.tlist == nullptr, "fused LSTM step: N = 4H tile-permuted, K-major operands, no split-K");
@@ -709,7 +849,7 @@ int gemm_tc(const TcGemm& g, cudaStream_t st) {
   p.use_scratch = (g.epi == TC_EPI_DEC_CELL_FWD || g.epi == TC_EPI_DEC_CELL_BWD || plain_fast) ? 1 : 0;
   p.scr_pitch = g.epi == TC_EPI_DEC_CELL_BWD ? TC_SCR_PITCH_BWD : TC_SCR_PITCH_FWD;
   const size_t scratch_bytes = p.use_scratch ? (size_t)TC_EPI_WARPS * 32 * p.scr_pitch : 0;
-  int stages = (int)((225 * 1024 - 2048 - scratch_bytes) / stage_bytes);
+  int stages = (int)(((g.epi == TC_EPI_CE ? 220 : 225) * 1024 - 2048 - scratch_bytes) / stage_bytes);
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   if (stages > p.kb_per + 1 && p.kb_per + 1 >= 2) stages = p.kb_per + 1 > 2 ? p.kb_per + 1 : 2;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
@@ -740,10 +880,11 @@ int gemm_tc(const TcGemm& g, cudaStream_t st) {
 
   const int num_sms = device_sm_count();
   if (first_use_on_device(ONCE_GEMM_TC)) {
-    ARCVAE_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    ARCVAE_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    ARCVAE_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    ARCVAE_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    ARCVAE_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));   // + 4 KB static
   }
-  ARCVAE_REQUIRE(smem <= 227 * 1024, "gemm_tc shared memory budget");
+  ARCVAE_REQUIRE(smem <= (size_t)(g.epi == TC_EPI_CE ? 222 : 227) * 1024, "gemm_tc shared memory budget");
   const int total = p.mt * p.nt * p.splitk;
   const int grid = total < num_sms ? total : num_sms;
   TimeScope ts(TIME_GEMM_TC, st);
@@ -753,8 +894,9 @@ int gemm_tc(const TcGemm& g, cudaStream_t st) {
     else ncols = g.N;
     count_flops(TIME_GEMM_TC, 2.0 * g.M * ncols * g.K);
   }
-  if (g.epi == TC_EPI_LSTM_FWD) gemm_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmB1, tmB2, p);
-  else gemm_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmB1, tmB2, p);
+  if (g.epi == TC_EPI_LSTM_FWD) gemm_tc_kernel<1><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmB1, tmB2, p);
+  else if (g.epi == TC_EPI_CE) gemm_tc_kernel<2><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmB1, tmB2, p);
+  else gemm_tc_kernel<0><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmB1, tmB2, p);
   ARCVAE_LAUNCHED();
   return 0;
 }

@@ -107,13 +107,24 @@ struct TcGemm {
   const float* c_prev = nullptr;                // [rows,H] cell state of the previous step (null: zero)
   float* c_out = nullptr;                       // [rows,H]
   float* hf_out = nullptr;                      // [rows,H] fp32 copy of h (nullable; the encoder head reads h_{T-1})
+  // fc_out with the cross-entropy in its epilogue (TC_EPI_CE; N = V <= 128, one N tile holds a whole row of logits):
+  // CE sum, d logits (bf16, scaled by ce_scale = 1 / global token count) and the greedy feedback token — the fp32 logits
+  // never reach HBM (losses/recon.py:29-64 + models/decoder.py:175-185 in one pass)
+  const int32_t* ce_target = nullptr;           // [T*B] time-major targets
+  const uint8_t* ce_fb = nullptr;               // [T] != 0: position t feeds argmax(logits_t) to position t+1
+  int32_t* ce_tok = nullptr;                    // [T*B] decoder inputs (time-major), written at (t+1, b)
+  int ce_B = 0;                                 // rows per timestep
+  __nv_bfloat16* ce_dl = nullptr;               // [rows, ce_ldl] d logits
+  int ce_ldl = 0;
+  double* ce_sum = nullptr;                     // += sum of CE over the rows of this launch
+  float ce_scale = 0.f;
   // multi-segment B (nseg = 2 or 3): weight gradients that share the MN-major A operand (dA^T) run as ONE GEMM whose
   // column tile i multiplies with seg[i].B (row k of A pairs with row k - k_shift of B; rows before 0 count as zero)
   // and accumulates into seg[i].C — A is read from HBM once.  Requires a_mn, b_mn, accumulate.
   int nseg = 1;
   struct Seg { const __nv_bfloat16* B; int ldb; int N; int k_shift; float* C; int ldc; } seg[3] = {};
 };
-enum { TC_EPI_PLAIN = 0, TC_EPI_DEC_CELL_FWD = 1, TC_EPI_DEC_CELL_BWD = 2, TC_EPI_LSTM_FWD = 3 };
+enum { TC_EPI_PLAIN = 0, TC_EPI_DEC_CELL_FWD = 1, TC_EPI_DEC_CELL_BWD = 2, TC_EPI_LSTM_FWD = 3, TC_EPI_CE = 4 };
 int gemm_tc(const TcGemm& g, cudaStream_t st);
 // weight-stationary variant (gemm_ws.cu) for K <= 256, bf16 output / fused decoder cell; gemm_tc dispatches to it
 bool gemm_ws_supported(const TcGemm& g);

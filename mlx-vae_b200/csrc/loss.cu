@@ -207,6 +207,11 @@ __global__ void __launch_bounds__(256, 4) k_loss_fused(LossArgs a) {
         if (blockIdx.x == 0) atomicAdd(st_sc + 4, (double)a.B);
       }
     }
+    if (a.logits == nullptr && (a.phases & 4)) {
+      // the cross-entropy sum was accumulated into st_sc[2] by the fc_out epilogue (gemm_tc.cu TC_EPI_CE): only the
+      // token count of this shard is missing (unmasked mean, losses/recon.py:59-60)
+      if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(st_sc + 3, (double)a.B * (double)a.T);
+    }
     if (a.logits != nullptr) {
       double cnt = 0.0;
       if (a.hp.pad_mask) {
@@ -222,7 +227,7 @@ __global__ void __launch_bounds__(256, 4) k_loss_fused(LossArgs a) {
       if (threadIdx.x == 0 && cnt != 0.0) atomicAdd(st_sc + 3, cnt);
     }
   }
-  if (a.phases == 3) {
+  if ((a.phases & 3) == 3) {
     __threadfence();
     cg::this_grid().sync();
   }
@@ -305,7 +310,7 @@ __global__ void __launch_bounds__(256, 4) k_loss_fused(LossArgs a) {
   if (is_last && threadIdx.x == 0 && a.losses != nullptr) {
     __threadfence();
     float recon = 0.f, kl = 0.f, collapse = 0.f, mi = 0.f, mi_pen = 0.f;
-    if (a.logits != nullptr && ntok > 0.0) recon = (float)(vst[2 * L + 2] / ntok);
+    if ((a.logits != nullptr || (a.phases & 4)) && ntok > 0.0) recon = (float)(vst[2 * L + 2] / ntok);
     if (a.mu != nullptr) {
       kl = (float)(vst[2 * L + 1] / Bg);
       mi = (float)fmax(mi_raw, 0.0);
@@ -335,7 +340,9 @@ extern "C" int arcvae_loss_fwd_bwd(const float* logits, int64_t ls_b, int64_t ls
                                    float* dlogits, float* dmu, float* dlogvar, float* z, void* stream) {
   using namespace arcvae;
   ARCVAE_REQUIRE(hyper != nullptr && stats != nullptr, "hyper and stats are mandatory");
-  ARCVAE_REQUIRE(phases >= 1 && phases <= 3, "phases must be 1, 2 or 3");
+  ARCVAE_REQUIRE((phases & 3) >= 1 && (phases & ~7) == 0, "phases: bit0 statistics, bit1 finish, bit2 cross-entropy precomputed");
+  ARCVAE_REQUIRE(!(phases & 4) || (logits == nullptr && T > 0 && !hyper->pad_mask),
+                 "precomputed cross-entropy: no logits, T given, unmasked mean");
   ARCVAE_REQUIRE(logits == nullptr || targets != nullptr, "logits need targets");
   ARCVAE_REQUIRE(mu == nullptr || logvar != nullptr, "mu needs logvar");
   ARCVAE_REQUIRE(B > 0, "empty batch");
@@ -366,7 +373,7 @@ extern "C" int arcvae_loss_fwd_bwd(const float* logits, int64_t ls_b, int64_t ls
   int grid = (int)(want < max_blocks ? want : max_blocks);
   if (grid < 1) grid = 1;
   TimeScope ts(TIME_LOSS, st);
-  if (phases == 3) {
+  if ((phases & 3) == 3) {
     void* args[] = {&a};
     ARCVAE_CUDA(cudaLaunchCooperativeKernel((void*)k_loss_fused, dim3(grid), dim3(256), args, 0, st));
     g_launches.fetch_add(1, std::memory_order_relaxed);

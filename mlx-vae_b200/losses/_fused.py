@@ -24,11 +24,14 @@ def make_hyper(beta=0.0, lambda_prop=0.0, lambda_collapse=0.0, free_bits=0.0, la
 def fused_loss(logits: Optional[torch.Tensor], targets: Optional[torch.Tensor], mu: Optional[torch.Tensor],
                logvar: Optional[torch.Tensor], hyper: _lib.LossHyper, *, eps: Optional[torch.Tensor] = None,
                seed: int = 0, offset: int = 0, pad_token: int = 0, want_grads: bool = True, want_z: bool = True,
-               inplace_dlogits: bool = False, allreduce=None) -> FusedLossOut:
+               inplace_dlogits: bool = False, allreduce=None, stats: Optional[torch.Tensor] = None,
+               ce_T: int = 0) -> FusedLossOut:
     """One launch (two around ``allreduce`` under data parallelism) computing every scalar of complete_vae_loss and,
     if ``want_grads``, d total / d logits, d mu, d logvar.  ``logits`` is [B,T,V] with unit stride on V and arbitrary
     (b,t) strides; ``targets`` [B,T] int32 with arbitrary strides.  ``allreduce(stats)`` (optional) must sum the first
-    2L+5 doubles of ``stats`` across ranks in place on the current stream."""
+    2L+5 doubles of ``stats`` across ranks in place on the current stream.
+    ``stats`` + ``ce_T`` (with ``logits=None``): the cross-entropy sum was already accumulated into ``stats[2L+2]`` by
+    ``decoder.forward_ce`` (fc_out epilogue); the kernel only adds the token count B*ce_T and reports recon / total."""
     lib = _lib.load()
     _lib.require_cuda(logits, targets, mu, logvar, eps)
     out = FusedLossOut()
@@ -51,7 +54,10 @@ def fused_loss(logits: Optional[torch.Tensor], targets: Optional[torch.Tensor], 
         L = mu.shape[1]
         if eps is not None:
             eps = eps.float().contiguous()
-    out.stats = torch.zeros(2 * L + 6, dtype=torch.float64, device=dev)
+    ce_pre = 4 if (logits is None and ce_T > 0) else 0
+    if ce_pre:
+        T = int(ce_T)
+    out.stats = stats if stats is not None else torch.zeros(2 * L + 6, dtype=torch.float64, device=dev)
     out.losses = torch.empty(len(_lib.LOSS_KEYS), dtype=torch.float32, device=dev)
     out.dlogits = out.dmu = out.dlogvar = out.z = None
     if logits is not None and want_grads:
@@ -66,7 +72,7 @@ def fused_loss(logits: Optional[torch.Tensor], targets: Optional[torch.Tensor], 
     def call(phases):
         _lib.check(lib.arcvae_loss_fwd_bwd(_lib.ptr(logits), ls_b, ls_t, _lib.ptr(targets), ts_b, ts_t, B, T, V,
                                            pad_token, _lib.ptr(mu), _lib.ptr(logvar), _lib.ptr(eps), L, hyper,
-                                           seed, offset, phases, out.stats.data_ptr(), out.losses.data_ptr(),
+                                           seed, offset, phases | ce_pre, out.stats.data_ptr(), out.losses.data_ptr(),
                                            _lib.ptr(out.dlogits), _lib.ptr(out.dmu), _lib.ptr(out.dlogvar),
                                            _lib.ptr(out.z), _lib.stream_ptr()))
 

@@ -105,13 +105,52 @@ class MLXAutoregressiveDecoder(Module):
         self.last_tf_mask = mask.astype(bool)
         return logits_tm.transpose(0, 1)   # [B,T,V] view of the time-major buffer
 
-    def backward(self, dlogits: torch.Tensor):
+    def ce_supported(self, B: int) -> bool:
+        return (not self.carry_state) and bool(_lib.load().arcvae_decoder_ce_supported(self._dims, int(B), self.precision))
+
+    def forward_ce(self, conditions: torch.Tensor, target_seq: torch.Tensor, ce_sum: torch.Tensor, ce_scale: float,
+                   teacher_forcing_ratio: float = 0.5, *, tf_mask: Optional[Sequence[bool]] = None) -> None:
+        """Training-step variant of ``__call__`` for the fused bf16 path: fc_out runs with the cross-entropy in its GEMM
+        epilogue, so the fp32 logits [B,T,V] are never written.  ``ce_sum`` (a float64 device scalar view, e.g.
+        ``stats[2L+2:2L+3]``) accumulates the CE sum; d logits (scaled by ``ce_scale`` = 1 / global positions) stay in the
+        tape as bf16 for ``backward(None)``.  Same coins / feedback semantics as ``__call__`` (decoder.py:180-185)."""
+        lib = _lib.load()
+        cond = self._f32(conditions)
+        target = self._tokens(target_seq)
+        B, T = target.shape
+        if tf_mask is None:
+            mask = np.zeros(T, dtype=np.uint8)
+            for t in range(T):
+                mask[t] = 1 if np.random.rand() < teacher_forcing_ratio else 0
+        else:
+            mask = np.ascontiguousarray(np.asarray(tf_mask).astype(np.uint8))
+            if mask.shape != (T,):
+                raise ValueError(f"tf_mask must have shape ({T},)")
+        tape = self.ws.get("tape", lib.arcvae_decoder_tape_bytes(self._dims, B, T))
+        inputs_tm = torch.empty((T, B), dtype=torch.int32, device=self.device)
+        _lib.check(lib.arcvae_decoder_forward_ce(self._dims, self._cparams, cond.data_ptr(), target.data_ptr(),
+                                                 mask.ctypes.data, B, T, float(ce_scale), ce_sum.data_ptr(),
+                                                 inputs_tm.data_ptr(), tape.data_ptr(), tape.numel(), self.precision,
+                                                 _lib.stream_ptr()))
+        self._ctx = (B, T, cond, tape)
+        self.last_inputs = inputs_tm.transpose(0, 1)
+        self.last_tf_mask = mask.astype(bool)
+
+    def backward(self, dlogits: Optional[torch.Tensor]):
         """Reverse pass of the last call.  ``dlogits`` is [B,T,V]; the transposed view of a time-major [T,B,V]
         buffer (what the fused loss writes) is consumed in place, anything else is copied.  Returns None in the
         reference mode (z does not reach the logits) and d total / d z [B,L] with ``carry_state=True``."""
         if self._ctx is None:
             raise _lib.ArcvaeError("decoder.backward() without a forward")
         lib = _lib.load()
+        if dlogits is None:                      # after forward_ce: the bf16 d logits are in the tape
+            B, T, cond, tape = self._ctx
+            scratch = self.ws.get("scratch", lib.arcvae_decoder_scratch_bytes(self._dims, B, T))
+            _lib.check(lib.arcvae_decoder_backward(self._dims, self._cparams, cond.data_ptr(), B, T, None,
+                                                   tape.data_ptr(), tape.numel(), self._cgrads, scratch.data_ptr(),
+                                                   scratch.numel(), self.precision, _lib.stream_ptr()))
+            self._ctx = None
+            return None
         _lib.require_cuda(dlogits)
         d_tm = dlogits.transpose(0, 1)
         if not d_tm.is_contiguous() or d_tm.dtype != torch.float32:

@@ -89,7 +89,9 @@ class ARCVAETrainerWithLoss:
         that of the GLOBAL batch (what a single device would compute on the concatenated shards):
           * KL / MI / penalties come from the all-reduced batch statistics inside the loss kernel;
           * the kernel reports recon = (this rank's CE sum) / (global token count); the partial rides in the aux tail of
-            the decoder's flat gradient buffer through the gradient all-reduce and is summed there;
+            the decoder's flat gradient buffer through the gradient all-reduce and is summed there (on the fused bf16
+            path the CE sum is part of the all-reduced statistics instead; shards must then be EQUAL in size, since the
+            d logits are scaled by 1 / (world x B x T) before the statistics are exchanged);
           * the Philox draw of eps is indexed by the GLOBAL row (``global_row_start``, default rank x local batch: even
             shards), so replicas do not repeat each other's noise and N ranks reproduce the single-device draw."""
         enc, dec, sync = self.encoder, self.decoder, self.sync
@@ -106,7 +108,7 @@ class ARCVAETrainerWithLoss:
         d = _run(enc, dec, self.property_predictor, molecules, conditions, beta, self.lambda_prop, self.lambda_collapse,
                  teacher_forcing_ratio, self.free_bits, self.lambda_mi, 4.85, eps, tf_mask, seed, self.pad_mask, True,
                  sync.allreduce_stats if dp else None, backward_hooks=hooks,
-                 eps_offset=int(global_row_start) * enc.latent_dim)
+                 eps_offset=int(global_row_start) * enc.latent_dim, ce_world=sync.world)
         if dp:
             sync.allreduce_async(enc.grads.flat)
             sync.wait()
@@ -237,7 +239,10 @@ class _DPHooks:
     def __init__(self, sync: GradSync):
         self.sync = sync
 
-    def after_decoder_backward(self, decoder, losses):
-        # this rank's partial reconstruction loss travels with the gradients (FlatParams.aux)
-        decoder.grads.aux[0:1].copy_(losses["recon_loss"].reshape(1))
+    def after_decoder_backward(self, decoder, losses, recon_is_global=False):
+        # this rank's partial reconstruction loss travels with the gradients (FlatParams.aux).  On the fused-CE path the
+        # CE sum went through the statistics all-reduce, so recon is already the global value on every rank: each rank
+        # contributes 1/world of it and the sum restores it
+        r = losses["recon_loss"].reshape(1)
+        decoder.grads.aux[0:1].copy_(r / self.sync.world if recon_is_global else r)
         self.sync.allreduce_async(decoder.grads.storage)

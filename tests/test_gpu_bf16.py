@@ -186,3 +186,49 @@ def test_bf16_training_trajectory_tracks_fp32(M):
     assert a[-1] < 0.8 * a[0] and b[-1] < 0.8 * b[0], (a[0], a[-1], b[0], b[-1])
     assert np.all(np.isfinite(b))
     assert np.max(np.abs(a - b) / np.abs(a)) < 5e-2, np.max(np.abs(a - b) / np.abs(a))
+
+
+@pytest.mark.parametrize("B,T,tf", [(256, 24, 0.7), (128, 9, 0.0), (1024, 33, 1.0)])
+def test_fused_cross_entropy_epilogue_equals_unfused_path(M, B, T, tf):
+    """Training step on the fused bf16 path: fc_out runs with cross-entropy, d logits and the greedy feedback in its GEMM
+    epilogue (csrc/gemm_tc.cu TC_EPI_CE; no fp32 logits in HBM).  Same accumulators, same formulas as the unfused path
+    (fc_out GEMM -> fused loss kernel -> bf16 copy -> argmax kernel, forced with ARCVAE_NO_FUSED_CE=1): the fed tokens must
+    be identical, the loss dict and every gradient equal up to summation order."""
+    import os
+    cfg = O.Config()
+    x, cond, eps, tf_mask = O.synthetic_batch(B, T, cfg, seed=B + T, tf_ratio=tf)
+    if tf == 1.0:
+        tf_mask = np.ones(T, dtype=bool)
+    p = O.init_params(cfg, seed=19, dtype=torch.float32)
+    p["decoder"] = O.tree_map(lambda t: t * 4.0, p["decoder"])
+    kw = model_kwargs(cfg)
+    hyper = dict(beta=0.05, lambda_prop=0.1, lambda_collapse=0.001, free_bits=1.0, lambda_mi=0.01, target_mi=4.85)
+    res = {}
+    for tag in ("fused", "unfused"):
+        if tag == "unfused":
+            os.environ["ARCVAE_NO_FUSED_CE"] = "1"
+        try:
+            enc = M.MLXEncoder(**kw, precision="bf16").load_parameters(p["encoder"])
+            dec = M.MLXAutoregressiveDecoder(**kw, precision="bf16").load_parameters(p["decoder"])
+            assert dec.ce_supported(B)
+            l0 = M._lib.launch_count()
+            d, (ge, gd) = M.loss_and_grad(enc, dec, None, cuda(x), cuda(cond), eps=cuda(eps), tf_mask=tf_mask, **hyper)
+            torch.cuda.synchronize()
+            res[tag] = ({k: float(d[k]) for k in M._lib.LOSS_KEYS}, {k: v.clone() for k, v in O.tree_flatten({"e": ge, "d": gd}).items()},
+                        dec.last_inputs.clone(), M._lib.launch_count() - l0)
+        finally:
+            os.environ.pop("ARCVAE_NO_FUSED_CE", None)
+    (la, ga, ia, na), (lb, gb, ib, nb) = res["fused"], res["unfused"]
+    assert torch.equal(ia, ib), "greedy feedback tokens differ between the fused and the unfused path"
+    assert na <= nb + 2
+    for k in la:
+        assert abs(la[k] - lb[k]) <= 2e-6 * max(1.0, abs(lb[k])), (k, la[k], lb[k])
+    worst = 0.0
+    for n in ga:
+        s = float(gb[n].abs().max())
+        if s == 0.0:
+            assert float(ga[n].abs().max()) == 0.0, n
+            continue
+        worst = max(worst, float((ga[n] - gb[n]).abs().max()) / s)
+    print(f"fused CE epilogue B={B} T={T} tf={tf}: worst gradient difference to the unfused path {worst:.2e}; launches {na} vs {nb}")
+    assert worst < 2e-3
