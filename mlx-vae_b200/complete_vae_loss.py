@@ -18,16 +18,19 @@ def _run(encoder, decoder, property_predictor, x, conditions, beta, lambda_prop,
     if property_predictor is not None:
         # the reference would raise TypeError here (complete_vae_loss.py:63-67 vs losses/prop.py:5-11, F10)
         raise NotImplementedError("property_predictor must be None, as in train.py:186")
-    mu, logvar = encoder(x, conditions)                                                         # :38
     hp = make_hyper(beta, lambda_prop, lambda_collapse, free_bits, lambda_mi, target_mi, 4.85, pad_mask)
     targets = encoder._tokens(x)
     B_, T_ = targets.shape
+    fuse_ce = (backward and not return_logits and not pad_mask and os.environ.get("ARCVAE_NO_FUSED_CE") is None
+               and decoder.ce_supported(B_))
+    if fuse_ce and os.environ.get("ARCVAE_ONE_STREAM") is None:
+        return _run_two_streams(encoder, decoder, x, conditions, targets, hp, teacher_forcing_ratio, eps, tf_mask, seed,
+                                eps_offset, info, allreduce, backward_hooks, ce_world)
+    mu, logvar = encoder(x, conditions)                                                         # :38
     z_in = None
     if getattr(decoder, "carry_state", False):
         # extension mode: the decoder consumes z (reference mode: z is dead, F1); same Philox stream as the loss kernel
         z_in = encoder.reparameterize(mu, logvar, eps, seed=seed, offset=eps_offset)            # :39
-    fuse_ce = (backward and not return_logits and not pad_mask and os.environ.get("ARCVAE_NO_FUSED_CE") is None
-               and decoder.ce_supported(B_))
     if fuse_ce:
         # training step on the fused bf16 path: fc_out + cross-entropy + d logits + greedy feedback in ONE GEMM epilogue;
         # the fp32 logits never reach HBM.  Unmasked mean over the GLOBAL batch (losses/recon.py:59-60): under data
@@ -69,6 +72,49 @@ def _run(encoder, decoder, property_predictor, x, conditions, beta, lambda_prop,
         if backward_hooks is not None:
             backward_hooks.after_decoder_backward(decoder, d, bool(fuse_ce and allreduce is not None))
         encoder.backward(out.dmu, out.dlogvar)
+    return d
+
+
+def _run_two_streams(encoder, decoder, x, conditions, targets, hp, teacher_forcing_ratio, eps, tf_mask, seed, eps_offset,
+                     info, allreduce, backward_hooks, ce_world):
+    """Training step of the fused bf16 path with the ENCODER chain on a second (high-priority) stream.
+
+    In the reference mode the decoder never sees z (F1) and, with the cross-entropy in the fc_out epilogue, its reverse
+    pass needs nothing from the loss kernel: decoder forward + backward are independent of the whole encoder chain; only
+    the loss kernel joins them (it reads the CE sum).  The persistent cluster recurrence holds 128 of the 148 SMs for
+    ~4.5 ms at low occupancy; the decoder's kernels fill the 20 SMs it leaves (measured 9.41 -> 8.94 ms per step).
+    Under data parallelism the statistics all-reduce is enqueued on the encoder stream and the decoder's gradient
+    all-reduce starts as soon as its reverse pass is enqueued, as before.  ARCVAE_ONE_STREAM=1 restores the serial order."""
+    B_, T_ = targets.shape
+    L_ = encoder.latent_dim
+    main = torch.cuda.current_stream()
+    hi = getattr(encoder, "_hi_stream", None)
+    if hi is None:
+        hi = encoder._hi_stream = torch.cuda.Stream(device=encoder.device, priority=-1)
+    stats = torch.zeros(2 * L_ + 6, dtype=torch.float64, device=decoder.device)
+    hi.wait_stream(main)
+    with torch.cuda.stream(hi):
+        mu, logvar = encoder(x, conditions)                                                     # :38
+    decoder.forward_ce(conditions, targets, stats[2 * L_ + 2:2 * L_ + 3], 1.0 / (float(ce_world) * B_ * T_),
+                       teacher_forcing_ratio, tf_mask=tf_mask)                                  # :42, :45
+    ce_done = main.record_event()
+    with torch.cuda.stream(hi):
+        hi.wait_event(ce_done)
+        out = fused_loss(None, None, mu, logvar, hp, eps=eps, seed=seed, offset=eps_offset, pad_token=decoder.pad_token,
+                         want_grads=True, want_z=True, allreduce=allreduce, stats=stats, ce_T=T_)   # :39, :48-82
+        loss_done = hi.record_event()
+        encoder.backward(out.dmu, out.dlogvar)
+    d = {k: out.losses[i] for i, k in enumerate(_lib.LOSS_KEYS)}                                # :86-99
+    d.update(mu=mu, logvar=logvar, z=out.z)
+    if info is not None:
+        info["recon_is_global"], info["fused_ce"] = allreduce is not None, True
+    decoder.backward(None)
+    if backward_hooks is not None:
+        main.wait_event(loss_done)               # the hook reads the loss scalars
+        backward_hooks.after_decoder_backward(decoder, d, allreduce is not None)
+    main.wait_stream(hi)
+    for t in (mu, logvar, out.z, out.losses, out.dmu, out.dlogvar, stats):
+        t.record_stream(main)                    # allocated on the encoder stream, consumed by the caller on `main`
     return d
 
 
