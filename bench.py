@@ -382,7 +382,9 @@ def main():
     # under the encoder's cluster recurrence); a kernel's own duration can only be read without a concurrent stream, so
     # this pass runs the SERIAL order (ARCVAE_ONE_STREAM) — `serial_ms_per_step` is its step time
     os.environ["ARCVAE_ONE_STREAM"] = "1"
-    for _ in range(2):
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()          # the serial order allocates from another stream's pool: settle the caching allocator
+    for _ in range(3):                # outside the timed steps (a cudaMalloc / cudaFree stalls the device for tens of ms)
         step_resident()
     ms_serial, _, _ = timed(step_resident, min(args.steps, 5))
     M._lib.timing_enable(True)

@@ -29,7 +29,8 @@ KEYS = [
 
 
 def traffic(reps):
-    """--traffic rec.ncu-rep gemm.ncu-rep loss.ncu-rep -> JSON {category: mean DRAM bytes (read+write) per launch}."""
+    """--traffic rec.ncu-rep gemm.ncu-rep loss.ncu-rep -> JSON {category: mean DRAM bytes (read+write) per launch}.
+    The gemm capture must hold ALL tensor-core GEMM launches of one step (capture.sh: --launch-skip 72 -c 24)."""
     import json
     out = {}
     for cat, rep in zip(("recurrence", "gemm_tc", "loss"), reps):
