@@ -91,17 +91,28 @@ def _run_two_streams(encoder, decoder, x, conditions, targets, hp, teacher_forci
     hi = getattr(encoder, "_hi_stream", None)
     if hi is None:
         hi = encoder._hi_stream = torch.cuda.Stream(device=encoder.device, priority=-1)
-    stats = torch.zeros(2 * L_ + 6, dtype=torch.float64, device=decoder.device)
+    # every tensor of the step is allocated HERE, on the caller's stream: the side stream only runs kernels on them and is
+    # bracketed by hi.wait_stream(main) / main.wait_stream(hi), so the caching allocator never sees a cross-stream block
+    # (record_stream() defers reuse and ends in sporadic cudaMalloc stalls of the whole device)
+    dev = decoder.device
+    stats = torch.zeros(2 * L_ + 6, dtype=torch.float64, device=dev)
+    cond32 = encoder._f32(conditions)
+    mu = torch.empty((B_, L_), dtype=torch.float32, device=dev)
+    logvar = torch.empty_like(mu)
+    bufs = {"losses": torch.empty(len(_lib.LOSS_KEYS), dtype=torch.float32, device=dev), "dmu": torch.empty_like(mu),
+            "dlogvar": torch.empty_like(mu), "z": torch.empty_like(mu)}
+    if eps is not None:
+        eps = eps.float().contiguous()
     hi.wait_stream(main)
     with torch.cuda.stream(hi):
-        mu, logvar = encoder(x, conditions)                                                     # :38
+        encoder(targets, cond32, out=(mu, logvar))                                              # :38
     decoder.forward_ce(conditions, targets, stats[2 * L_ + 2:2 * L_ + 3], 1.0 / (float(ce_world) * B_ * T_),
                        teacher_forcing_ratio, tf_mask=tf_mask)                                  # :42, :45
     ce_done = main.record_event()
     with torch.cuda.stream(hi):
         hi.wait_event(ce_done)
         out = fused_loss(None, None, mu, logvar, hp, eps=eps, seed=seed, offset=eps_offset, pad_token=decoder.pad_token,
-                         want_grads=True, want_z=True, allreduce=allreduce, stats=stats, ce_T=T_)   # :39, :48-82
+                         want_grads=True, want_z=True, allreduce=allreduce, stats=stats, ce_T=T_, bufs=bufs)   # :39, :48-82
         loss_done = hi.record_event()
         encoder.backward(out.dmu, out.dlogvar)
     d = {k: out.losses[i] for i, k in enumerate(_lib.LOSS_KEYS)}                                # :86-99
@@ -113,8 +124,6 @@ def _run_two_streams(encoder, decoder, x, conditions, targets, hp, teacher_forci
         main.wait_event(loss_done)               # the hook reads the loss scalars
         backward_hooks.after_decoder_backward(decoder, d, allreduce is not None)
     main.wait_stream(hi)
-    for t in (mu, logvar, out.z, out.losses, out.dmu, out.dlogvar, stats):
-        t.record_stream(main)                    # allocated on the encoder stream, consumed by the caller on `main`
     return d
 
 

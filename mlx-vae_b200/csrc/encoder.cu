@@ -52,6 +52,7 @@ struct EncTape {
   bf16* Wxb[ARCVAE_MAX_LAYERS];     // [4H,H], l >= 1
   // cluster path
   bf16* gates_b[ARCVAE_MAX_LAYERS]; // [T*B,4H] activated gates
+  void* xh;                         // forward exchange buffer of the cluster kernel (flag-in-data vectors of h_t)
   // bf16 operands of the tensor-core head products (bf16 paths)
   bf16* ub;          // [B,2H]
   bf16* lvhb;        // [B,2H]
@@ -103,6 +104,7 @@ static size_t enc_tape_layout(const arcvae_dims& d, int B, int T, int path, void
     }
     if (path == PATH_CLUSTER) {
       tt.gates_b[l] = a.take<bf16>(Rpad * 4 * H);
+      if (l == 0) tt.xh = a.take<char>(lstm_cluster_xh_bytes(B));
     }
   }
   if (path == PATH_CLUSTER || path == PATH_STEP_FUSED) {
@@ -288,18 +290,29 @@ extern "C" int arcvae_encoder_forward(const arcvae_dims* d, const arcvae_encoder
     ARCVAE_REQUIRE(errf != nullptr, "device error flag allocation failed");
     ARCVAE_TRY(f32_to_bf16(tp.table0, tp.table0b, (long)d->V * G4, st));
     for (int l = 0; l < d->NL; l++) {
+      bool p_in_tape = false;
       if (l >= 1) {
-        // time-parallel input projection, bf16 out (bias included): Pb = hb_{l-1} @ Wx_l^T + b_l
+        // time-parallel input projection, bf16 out (bias included): P = hb_{l-1} @ Wx_l^T + b_l.  Preferred: the
+        // weight-stationary GEMM writes it into THIS layer's gate tape in the tape's thread-friendly layout (the recurrence
+        // reads it with 512-byte warp accesses and overwrites it with the activated gates); else row-major into Pb.
         TcGemm g{};
         g.M = (int)R; g.N = G4; g.K = H;
         g.A = tp.hb[l - 1]; g.lda = H; g.a_mn = false;
         g.B = tp.Wxb[l]; g.ldb = H; g.b_mn = false;
-        g.C = nullptr; g.ldc = 0; g.Cb = tp.Pb; g.ldcb = G4; g.bias = p->bias[l]; g.accumulate = false; g.splitk = 1;
+        g.C = nullptr; g.ldc = 0; g.bias = p->bias[l]; g.accumulate = false; g.splitk = 1;
         g.rm = id; g.a_rows_total = R;
-        ARCVAE_TRY(gemm_tc(g, st));
+        g.Cb = tp.gates_b[l]; g.ldcb = G4; g.epi = TC_EPI_LSTM_P; g.Hh = H; g.lp_B = B;
+        p_in_tape = gemm_ws_supported(g) && std::getenv("ARCVAE_NO_WS") == nullptr && lstm_cluster_fwd_generation(l) == 3;
+        if (p_in_tape) {
+          ARCVAE_TRY(gemm_ws(g, st));
+        } else {
+          g.Cb = tp.Pb; g.epi = TC_EPI_PLAIN; g.Hh = 0; g.lp_B = 0;
+          ARCVAE_TRY(gemm_tc(g, st));
+        }
       }
-      ARCVAE_TRY(lstm_cluster_forward(B, T, H, tp.Whb[l], tp.xT, l == 0 ? tp.table0b : nullptr, l == 0 ? nullptr : tp.Pb,
-                                      tp.hb[l], tp.gates_b[l], tp.c[l], l == d->NL - 1 ? tp.h_last : nullptr, errf, st));
+      ARCVAE_TRY(lstm_cluster_forward(B, T, H, tp.Whb[l], tp.xT, l == 0 ? tp.table0b : nullptr,
+                                      (l == 0 || p_in_tape) ? nullptr : tp.Pb, tp.hb[l], tp.gates_b[l], tp.c[l],
+                                      l == d->NL - 1 ? tp.h_last : nullptr, tp.xh, errf, st));
     }
     return head_forward(*d, p, tp, tp.h_last, cond, B, mu, logvar, precision, st);
   }

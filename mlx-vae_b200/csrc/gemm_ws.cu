@@ -33,8 +33,10 @@ struct WsParams {
   RowMap rm;
   int epi;        // WS_EPI_*
   int nslab;      // staging slabs
+  int lp_B;       // WS_EPI_LSTM_P: rows per timestep
+  uint4* lp_out;  // WS_EPI_LSTM_P: thread-friendly output
 };
-enum { WS_EPI_PLAIN = 0, WS_EPI_DEC_CELL_FWD = 1 };
+enum { WS_EPI_PLAIN = 0, WS_EPI_DEC_CELL_FWD = 1, WS_EPI_LSTM_P = 2 };
 
 struct __align__(8) WsShared {
   uint64_t full[WS_STAGES];
@@ -44,6 +46,11 @@ struct __align__(8) WsShared {
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
 };
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  const __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&t);
+}
 
 namespace ws {
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
@@ -212,6 +219,42 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ws::bulk_commit();
           }
         }
+      } else if (p.epi == WS_EPI_LSTM_P) {
+        // input projection of an encoder LSTM layer for the cluster recurrence: panel ni = gate ni (BN = H = 256), 64-column
+        // block s = the units of cluster CTA s, `half` = which 32 of them.  Thread = row writes its 16-byte chunks straight
+        // to the layout that kernel reads: the 32 lanes of a warp hit 512 consecutive bytes (no staging, no TMA).
+        const long gr = (long)gm0 + r;
+        const int tt = (int)(gr / p.lp_B), bb = (int)(gr - (long)tt * p.lp_B);
+        const int ntl = (p.lp_B + 127) >> 7;
+        const long slots_per_t = (long)ntl * 32;
+        const int tile = bb >> 7, qq = (bb >> 5) & 3, ln = bb & 31;
+        const bool rvalid = gr < p.M;
+#pragma unroll 1
+        for (int s = 0; s < 4; s++) {
+          const int c0 = s * 64 + half * 32;
+          uint32_t ra[16], rb[16];
+          tc::tmem_ld16(taddr + c0, ra);
+          tc::tmem_ld16(taddr + c0 + 16, rb);
+          float4 bv[8];
+#pragma unroll
+          for (int k4 = 0; k4 < 8; k4++)
+            bv[k4] = p.bias != nullptr ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0) + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          tc::tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int k4 = 0; k4 < 4; k4++) {
+            pk[2 * k4] = pack_bf16x2(__uint_as_float(ra[4 * k4 + 0]) + bv[k4].x, __uint_as_float(ra[4 * k4 + 1]) + bv[k4].y);
+            pk[2 * k4 + 1] = pack_bf16x2(__uint_as_float(ra[4 * k4 + 2]) + bv[k4].z, __uint_as_float(ra[4 * k4 + 3]) + bv[k4].w);
+            pk[8 + 2 * k4] = pack_bf16x2(__uint_as_float(rb[4 * k4 + 0]) + bv[4 + k4].x, __uint_as_float(rb[4 * k4 + 1]) + bv[4 + k4].y);
+            pk[8 + 2 * k4 + 1] = pack_bf16x2(__uint_as_float(rb[4 * k4 + 2]) + bv[4 + k4].z, __uint_as_float(rb[4 * k4 + 3]) + bv[4 + k4].w);
+          }
+          if (rvalid) {
+            const long warp_slot = (((long)tile * 4 + s) * 4 + qq) * 2 + half;
+            uint4* dst = p.lp_out + (((long)tt * slots_per_t + warp_slot) * 16 + ni * 4) * 32 + ln;
+#pragma unroll
+            for (int cu = 0; cu < 4; cu++) dst[cu * 32] = make_uint4(pk[4 * cu], pk[4 * cu + 1], pk[4 * cu + 2], pk[4 * cu + 3]);
+          }
+        }
       } else {
         // decoder zero-state LSTM cell (models/decoder.py:165-168 with no state): accumulator columns [0,64) = i,
         // [64,128) = g, [128,192) = o of hidden units 64*ni .. 64*ni+63.  Slabs: 0 = h, 1 = i, 2 = g, 3 = o.
@@ -284,6 +327,9 @@ bool gemm_ws_supported(const TcGemm& g) {
   if (g.epi == TC_EPI_PLAIN)
     return g.Cb != nullptr && (g.N % 256) == 0 && (g.ldcb % 8) == 0 && (reinterpret_cast<uintptr_t>(g.Cb) & 15) == 0 &&
            (g.bias == nullptr || (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0);
+  if (g.epi == TC_EPI_LSTM_P)
+    return g.Cb != nullptr && g.N == 1024 && g.Hh == 256 && g.lp_B > 0 && g.rm.tlist == nullptr &&
+           (reinterpret_cast<uintptr_t>(g.Cb) & 15) == 0 && (g.bias == nullptr || (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0);
   if (g.epi == TC_EPI_DEC_CELL_FWD)
     return g.N == 3 * g.Hh && (g.Hh % 64) == 0 && g.bias != nullptr && (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0 &&
            g.gates_b != nullptr && g.hb_out != nullptr;
@@ -294,14 +340,16 @@ int gemm_ws(const TcGemm& g, cudaStream_t st) {
   ARCVAE_REQUIRE(gemm_ws_supported(g), "gemm_ws: unsupported shape");
   WsParams p{};
   p.M = g.M; p.N = g.N; p.K = g.K;
-  p.epi = g.epi == TC_EPI_DEC_CELL_FWD ? WS_EPI_DEC_CELL_FWD : WS_EPI_PLAIN;
+  p.epi = g.epi == TC_EPI_DEC_CELL_FWD ? WS_EPI_DEC_CELL_FWD : g.epi == TC_EPI_LSTM_P ? WS_EPI_LSTM_P : WS_EPI_PLAIN;
+  p.lp_B = g.lp_B;
+  p.lp_out = reinterpret_cast<uint4*>(g.Cb);
   p.BN = p.epi == WS_EPI_DEC_CELL_FWD ? 192 : 256;
   p.nt = g.N / p.BN;
   p.mt = cdiv(g.M, WS_BM);
   p.kblocks = g.K / WS_BK;
   p.bias = g.bias;
   p.rm = g.rm;
-  p.nslab = p.epi == WS_EPI_DEC_CELL_FWD ? 4 : 2;
+  p.nslab = p.epi == WS_EPI_DEC_CELL_FWD ? 4 : p.epi == WS_EPI_LSTM_P ? 0 : 2;
   const size_t smem = (size_t)p.kblocks * p.BN * WS_BK * 2 + (size_t)WS_STAGES * WS_A_BYTES + (size_t)p.nslab * WS_SLAB +
                       sizeof(WsShared) + 1024;
   ARCVAE_REQUIRE(smem <= 227 * 1024, "gemm_ws shared-memory budget");
@@ -312,6 +360,9 @@ int gemm_ws(const TcGemm& g, cudaStream_t st) {
   if (p.epi == WS_EPI_PLAIN) {
     ARCVAE_TRY(make_tmap_bf16(&tmC, g.Cb, rows, g.N, g.ldcb, 64, WS_BM));
     tmG = tmC;
+  } else if (p.epi == WS_EPI_LSTM_P) {
+    tmC = tmA;            // unused: this epilogue stores per thread
+    tmG = tmA;
   } else {
     ARCVAE_TRY(make_tmap_bf16(&tmC, g.hb_out, rows, g.Hh, g.Hh, 64, WS_BM));
     ARCVAE_TRY(make_tmap_bf16(&tmG, g.gates_b, rows, 3L * g.Hh, 3L * g.Hh, 64, WS_BM));

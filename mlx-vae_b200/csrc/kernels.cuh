@@ -121,10 +121,14 @@ struct TcGemm {
   // multi-segment B (nseg = 2 or 3): weight gradients that share the MN-major A operand (dA^T) run as ONE GEMM whose
   // column tile i multiplies with seg[i].B (row k of A pairs with row k - k_shift of B; rows before 0 count as zero)
   // and accumulates into seg[i].C — A is read from HBM once.  Requires a_mn, b_mn, accumulate.
+  // TC_EPI_LSTM_P (weight-stationary kernel only): Cb receives the layer's input projection in the THREAD-FRIENDLY layout
+  // of the cluster recurrence (lstm_cluster.cu: [t][tile][cta][lane quarter][unit half][gate*4 + chunk][lane] x 16 B), so
+  // that kernel's epilogue threads read their operands as 512-byte warp accesses.  N = 4*Hh, rows = t*lp_B + b.
+  int lp_B = 0;
   int nseg = 1;
   struct Seg { const __nv_bfloat16* B; int ldb; int N; int k_shift; float* C; int ldc; } seg[3] = {};
 };
-enum { TC_EPI_PLAIN = 0, TC_EPI_DEC_CELL_FWD = 1, TC_EPI_DEC_CELL_BWD = 2, TC_EPI_LSTM_FWD = 3, TC_EPI_CE = 4 };
+enum { TC_EPI_PLAIN = 0, TC_EPI_DEC_CELL_FWD = 1, TC_EPI_DEC_CELL_BWD = 2, TC_EPI_LSTM_FWD = 3, TC_EPI_CE = 4, TC_EPI_LSTM_P = 5 };
 int gemm_tc(const TcGemm& g, cudaStream_t st);
 // weight-stationary variant (gemm_ws.cu) for K <= 256, bf16 output / fused decoder cell; gemm_tc dispatches to it
 bool gemm_ws_supported(const TcGemm& g);
@@ -138,7 +142,9 @@ int transpose_to_bf16(const float* src, int R, int C, __nv_bfloat16* dst, cudaSt
 bool lstm_cluster_supported(int H);
 int lstm_cluster_forward(int B, int T, int H, const __nv_bfloat16* Whb, const int32_t* xT, const __nv_bfloat16* table0b,
                          const __nv_bfloat16* Pb, __nv_bfloat16* hb, __nv_bfloat16* gates_b, float* c, float* h_last,
-                         int* err_flag, cudaStream_t st);
+                         void* xh, int* err_flag, cudaStream_t st);
+size_t lstm_cluster_xh_bytes(int B);
+int lstm_cluster_fwd_generation(int layer);      // 3: reads the input projection from the gate tape (TC_EPI_LSTM_P layout)   // forward exchange buffer (flag-in-data vectors of h_t)
 // K-split backward: every CTA multiplies its own dA slice, partial d h reduce-scattered through `xch`
 size_t lstm_cluster_xch_bytes(int B);
 int lstm_cluster_backward2(int B, int T, int H, const __nv_bfloat16* Whb, const __nv_bfloat16* gates_b, const float* c,

@@ -25,13 +25,15 @@ def fused_loss(logits: Optional[torch.Tensor], targets: Optional[torch.Tensor], 
                logvar: Optional[torch.Tensor], hyper: _lib.LossHyper, *, eps: Optional[torch.Tensor] = None,
                seed: int = 0, offset: int = 0, pad_token: int = 0, want_grads: bool = True, want_z: bool = True,
                inplace_dlogits: bool = False, allreduce=None, stats: Optional[torch.Tensor] = None,
-               ce_T: int = 0) -> FusedLossOut:
+               ce_T: int = 0, bufs: Optional[dict] = None) -> FusedLossOut:
     """One launch (two around ``allreduce`` under data parallelism) computing every scalar of complete_vae_loss and,
     if ``want_grads``, d total / d logits, d mu, d logvar.  ``logits`` is [B,T,V] with unit stride on V and arbitrary
     (b,t) strides; ``targets`` [B,T] int32 with arbitrary strides.  ``allreduce(stats)`` (optional) must sum the first
     2L+5 doubles of ``stats`` across ranks in place on the current stream.
     ``stats`` + ``ce_T`` (with ``logits=None``): the cross-entropy sum was already accumulated into ``stats[2L+2]`` by
-    ``decoder.forward_ce`` (fc_out epilogue); the kernel only adds the token count B*ce_T and reports recon / total."""
+    ``decoder.forward_ce`` (fc_out epilogue); the kernel only adds the token count B*ce_T and reports recon / total.
+    ``bufs`` (optional): caller-owned outputs ``losses``, ``dmu``, ``dlogvar``, ``z`` (side-stream callers allocate on
+    their own stream)."""
     lib = _lib.load()
     _lib.require_cuda(logits, targets, mu, logvar, eps)
     out = FusedLossOut()
@@ -58,16 +60,18 @@ def fused_loss(logits: Optional[torch.Tensor], targets: Optional[torch.Tensor], 
     if ce_pre:
         T = int(ce_T)
     out.stats = stats if stats is not None else torch.zeros(2 * L + 6, dtype=torch.float64, device=dev)
-    out.losses = torch.empty(len(_lib.LOSS_KEYS), dtype=torch.float32, device=dev)
+    bufs = bufs or {}
+    out.losses = bufs.get("losses") if bufs.get("losses") is not None else torch.empty(len(_lib.LOSS_KEYS), dtype=torch.float32, device=dev)
     out.dlogits = out.dmu = out.dlogvar = out.z = None
     if logits is not None and want_grads:
         out.dlogits = logits if inplace_dlogits else torch.empty_strided(logits.shape, logits.stride(),
                                                                        dtype=torch.float32, device=dev)
     if mu is not None:
         if want_grads:
-            out.dmu, out.dlogvar = torch.empty_like(mu), torch.empty_like(logvar)
+            out.dmu = bufs["dmu"] if "dmu" in bufs else torch.empty_like(mu)
+            out.dlogvar = bufs["dlogvar"] if "dlogvar" in bufs else torch.empty_like(logvar)
         if want_z:
-            out.z = torch.empty_like(mu)
+            out.z = bufs["z"] if "z" in bufs else torch.empty_like(mu)
 
     def call(phases):
         _lib.check(lib.arcvae_loss_fwd_bwd(_lib.ptr(logits), ls_b, ls_t, _lib.ptr(targets), ts_b, ts_t, B, T, V,

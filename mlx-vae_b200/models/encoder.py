@@ -30,7 +30,9 @@ class MLXEncoder(Module):
         self._ctx = None
         self._last_bt = None
 
-    def __call__(self, x: torch.Tensor, conditions: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    def __call__(self, x: torch.Tensor, conditions: torch.Tensor, *, out=None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """``out=(mu, logvar)``: write into caller-owned [B,L] float32 buffers (used when the call is enqueued on a side
+        stream: the caller allocates on its own stream, so the caching allocator never crosses streams)."""
         lib = _lib.load()
         x = self._tokens(x)
         cond = self._f32(conditions)
@@ -39,8 +41,11 @@ class MLXEncoder(Module):
             raise ValueError(f"conditions must be [{B},{self.num_conditions}], got {tuple(cond.shape)}")
         nbytes = lib.arcvae_encoder_tape_bytes(self._dims, B, T)
         tape = self.ws.get("tape", nbytes)
-        mu = torch.empty((B, self.latent_dim), dtype=torch.float32, device=self.device)
-        logvar = torch.empty_like(mu)
+        if out is not None:
+            mu, logvar = out
+        else:
+            mu = torch.empty((B, self.latent_dim), dtype=torch.float32, device=self.device)
+            logvar = torch.empty_like(mu)
         _lib.check(lib.arcvae_encoder_forward(self._dims, self._cparams, x.data_ptr(), cond.data_ptr(), B, T,
                                               mu.data_ptr(), logvar.data_ptr(), tape.data_ptr(), tape.numel(),
                                               self.precision, _lib.stream_ptr()))

@@ -12,14 +12,14 @@ enc = M.MLXEncoder(80, 128, 256, 128, 1, 2, seed=1, precision="bf16")
 dx, dc = torch.as_tensor(x).cuda(), torch.as_tensor(cond).cuda()
 lib = M._lib.load()
 for mode in ("fwd", "bwd"):
-    buf = torch.zeros(4 * 64 * 16, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(4 * 64 * 32, dtype=torch.int64, device="cuda")
     mu, lv = enc(dx, dc)
     if mode == "fwd":
         lib.arcvae_debug_set_rc_stamps(buf.data_ptr()); mu, lv = enc(dx, dc)
     else:
         lib.arcvae_debug_set_rc_stamps(buf.data_ptr()); enc.zero_grad(); enc.backward(torch.ones_like(mu) / B, torch.ones_like(lv) / B)
     torch.cuda.synchronize(); lib.arcvae_debug_set_rc_stamps(None)
-    sall = buf.cpu().numpy().reshape(4, 64, 16)   # last launch (layer 1 fwd / layer 0 bwd) wins; globaltimer ns
+    sall = buf.cpu().numpy().reshape(4, 64, 32)   # last launch (layer 1 fwd / layer 0 bwd) wins; globaltimer ns
     print(f"== {mode}: per-CTA stamps (ns) relative to CTA0 'acc ready', it=21")
     b0 = sall[0][21][4]
     for c in range(4):

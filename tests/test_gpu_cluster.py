@@ -132,3 +132,33 @@ def test_fused_step_path_matches_oracle_and_unfused_path(M, H, NL, B, T):
           f"vs unfused per-step path {worst_u:.2e}; forward launches {nF} vs {nU}")
     assert e_fwd < 8e-3 and worst < 2e-2, (e_fwd, worst, name)
     assert rel_err(muF.cpu(), muU.cpu()) < 5e-3 and worst_u < 1e-2
+
+
+@pytest.mark.parametrize("B,T", [(128, 9), (200, 16), (1024, 64)])
+def test_cluster_recurrence_is_deterministic(M, B, T):
+    """The exchange of the cluster kernels polls flag-in-data vectors; a torn or stale vector shows up as run-to-run
+    noise of the gradients (seen while developing: a 128-bit poll split into scalar loads).  Same inputs, five runs:
+    outputs bit-identical, gradients equal up to the fp32 atomics of the split-K weight-gradient GEMMs."""
+    cfg = O.Config()
+    p = O.init_params(cfg, seed=5, dtype=torch.float32)
+    x, cond, eps, _ = O.synthetic_batch(B, T, cfg, seed=B + T)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    dmu = torch.randn(B, cfg.latent_dim, device="cuda", generator=g) / B
+    dlv = torch.randn(B, cfg.latent_dim, device="cuda", generator=g) / B
+    enc = M.MLXEncoder(**model_kwargs(cfg), precision="bf16").load_parameters(p["encoder"])
+    ref = None
+    for rep in range(5):
+        mu, lv = enc(cuda(x), cuda(cond))
+        enc.zero_grad()
+        enc.backward(dmu, dlv)
+        enc.check()
+        cur = {"mu": mu.clone(), "logvar": lv.clone()}
+        cur.update({k: v.clone() for k, v in O.tree_flatten(enc.gradients()).items()})
+        if ref is None:
+            ref = cur
+            continue
+        assert torch.equal(cur["mu"], ref["mu"]) and torch.equal(cur["logvar"], ref["logvar"])
+        for k in ref:
+            s = float(ref[k].abs().max())
+            if s > 0:
+                assert float((cur[k] - ref[k]).abs().max()) / s < 1e-5, (k, rep)
