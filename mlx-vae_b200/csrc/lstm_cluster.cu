@@ -1289,7 +1289,6 @@ lstm_fwd3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         tc::tc_fence_after();
       }
       if (threadIdx.x == 0) RC_STAMP(4);
-      uint4 outq[4][4];                      // activated gates [gate][chunk]
       uint4 hq[4];                           // h_t
 #pragma unroll
       for (int cu = 0; cu < 4; cu++) {
@@ -1329,7 +1328,16 @@ lstm_fwd3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
           hv[j] = go[j] * rc::tanh_fast(cn);
         }
         hq[cu] = rc::pack8(hv);
-        outq[0][cu] = rc::pack8(gi); outq[1][cu] = rc::pack8(gf); outq[2][cu] = rc::pack8(gg); outq[3][cu] = rc::pack8(go);
+        // the tape of this chunk leaves NOW: the LSU is idle during the MUFU-bound gate math, and 24 stores per thread issued
+        // in one burst after the exchange were measured to block the thread for > 1 us (1.5 us of the step)
+        if (valid) {
+          *gate_tape(t, 0, cu) = rc::pack8(gi);
+          *gate_tape(t, 1, cu) = rc::pack8(gf);
+          *gate_tape(t, 2, cu) = rc::pack8(gg);
+          *gate_tape(t, 3, cu) = rc::pack8(go);
+          *c_tape(t, 2 * cu) = make_float4(state[cu * 8], state[cu * 8 + 1], state[cu * 8 + 2], state[cu * 8 + 3]);
+          *c_tape(t, 2 * cu + 1) = make_float4(state[cu * 8 + 4], state[cu * 8 + 5], state[cu * 8 + 6], state[cu * 8 + 7]);
+        }
         if (valid && t == T - 1 && p.h_last != nullptr) {
           float* hl = p.h_last + (long)row * H + ub + cu * 8;
           *reinterpret_cast<float4*>(hl) = make_float4(hv[0], hv[1], hv[2], hv[3]);
@@ -1405,20 +1413,10 @@ lstm_fwd3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         if (threadIdx.x == 0) RC_STAMP(11);
         if (p.dbg != nullptr && threadIdx.x == 0 && blockIdx.x < 4 && it < 64) p.dbg[(blockIdx.x * 64 + it) * 32 + 13] = rounds;
         if (lane == 0) RC_STAMP(16 + warp);
-        // ---- off the critical path (under the MMAs of the next step): next step's operands (measured: issued before or
-        // inside the gate math they delay it, the loads in flight throttle the LSU), then the tape
+        // next step's operands, under the MMAs (measured: issued BEFORE the polls they cost 1.4 us per step — the polls
+        // queue behind 16 loads from HBM — and inside the gate math they throttle it)
 #pragma unroll
         for (int cu = 0; cu < 4; cu++) prefetch(t + 1, cu);
-      }
-      // ---- the tape
-      if (valid) {
-#pragma unroll
-        for (int g = 0; g < 4; g++)
-#pragma unroll
-          for (int cu = 0; cu < 4; cu++) *gate_tape(t, g, cu) = outq[g][cu];
-#pragma unroll
-        for (int i = 0; i < 8; i++)
-          *c_tape(t, i) = make_float4(state[4 * i], state[4 * i + 1], state[4 * i + 2], state[4 * i + 3]);
       }
       if (threadIdx.x == 0) RC_STAMP(12);
     }
@@ -1476,8 +1474,8 @@ static int env_gen(const char* name, int dflt) {
 // forward: layer 0 (operands gathered from the token table, an uncoalesced load pattern that the gen-2 kernel hides behind
 // its TMA exchange) and the upper layers (operands from the thread-friendly tape) are chosen separately
 int lstm_cluster_fwd_generation(int layer) {
-  static const int gen0 = env_gen("ARCVAE_RC_FWD_GEN0", 2);
-  static const int gen1 = env_gen("ARCVAE_RC_FWD_GEN", 2);
+  static const int gen0 = env_gen("ARCVAE_RC_FWD_GEN0", 3);
+  static const int gen1 = env_gen("ARCVAE_RC_FWD_GEN", 3);
   return layer == 0 ? gen0 : gen1;
 }
 static int rc_bwd_generation() {

@@ -12,7 +12,7 @@ x, cond, eps, tf = synthetic_batch(B, T)
 enc = M.MLXEncoder(80, 128, 256, 128, 1, 2, seed=1, precision="bf16")
 dx, dc = torch.as_tensor(x).cuda(), torch.as_tensor(cond).cuda()
 lib = M._lib.load()
-gen = os.environ.get("ARCVAE_RC_FWD_GEN", "2") + "/" + os.environ.get("ARCVAE_RC_BWD_GEN", "3")
+gen = os.environ.get("ARCVAE_RC_FWD_GEN", "3") + "/" + os.environ.get("ARCVAE_RC_BWD_GEN", "3")
 mu, lv = enc(dx, dc)
 enc.zero_grad(); enc.backward(torch.ones_like(mu) / B, torch.ones_like(lv) / B)
 enc.check()
