@@ -51,7 +51,8 @@ struct EncTape {
   bf16* Whb[ARCVAE_MAX_LAYERS];     // [4H,H]
   bf16* Wxb[ARCVAE_MAX_LAYERS];     // [4H,H], l >= 1
   // cluster path
-  bf16* gates_b[ARCVAE_MAX_LAYERS]; // [T*B,4H] activated gates
+  bf16* gates_b[ARCVAE_MAX_LAYERS]; // fused per-step path: [T*B,4H] activated gates
+  bf16* ktape[ARCVAE_MAX_LAYERS];   // cluster path: coefficient tape of the cell reverse (lstm_cluster.cu, RC_KV)
   void* xh;                         // forward exchange buffer of the cluster kernel (flag-in-data vectors of h_t)
   // bf16 operands of the tensor-core head products (bf16 paths)
   bf16* ub;          // [B,2H]
@@ -86,9 +87,8 @@ static size_t enc_tape_layout(const arcvae_dims& d, int B, int T, int path, void
     tt.Wlhb = a.take<bf16>((size_t)4 * H * H);
     tt.Wlvb = a.take<bf16>((size_t)d.L * 2 * H);
   }
-  const size_t Rpad = (size_t)T * (((size_t)B + 127) / 128 * 128);   // cluster path: tile-padded, thread-friendly tape
   for (int l = 0; l < d.NL; l++) {
-    tt.c[l] = a.take<float>((path == PATH_CLUSTER ? Rpad : R) * H);
+    if (path != PATH_CLUSTER) tt.c[l] = a.take<float>(R * H);   // the cluster kernels keep c_t in registers; their tape holds coefficients
     if (path == PATH_STEP_FUSED) {
       tt.gates_b[l] = a.take<bf16>(R * 4 * H);
       tt.Whp[l] = a.take<bf16>(4 * H * H);
@@ -103,7 +103,7 @@ static size_t enc_tape_layout(const arcvae_dims& d, int B, int T, int path, void
       if (l >= 1) tt.Wxb[l] = a.take<bf16>(4 * H * H);
     }
     if (path == PATH_CLUSTER) {
-      tt.gates_b[l] = a.take<bf16>(Rpad * 4 * H);
+      tt.ktape[l] = a.take<bf16>(lstm_cluster_ktape_elems(B, T, (int)H));
       if (l == 0) tt.xh = a.take<char>(lstm_cluster_xh_bytes(B));
     }
   }
@@ -301,17 +301,17 @@ extern "C" int arcvae_encoder_forward(const arcvae_dims* d, const arcvae_encoder
         g.B = tp.Wxb[l]; g.ldb = H; g.b_mn = false;
         g.C = nullptr; g.ldc = 0; g.bias = p->bias[l]; g.accumulate = false; g.splitk = 1;
         g.rm = id; g.a_rows_total = R;
-        g.Cb = tp.gates_b[l]; g.ldcb = G4; g.epi = TC_EPI_LSTM_P; g.Hh = H; g.lp_B = B;
-        p_in_tape = gemm_ws_supported(g) && std::getenv("ARCVAE_NO_WS") == nullptr && lstm_cluster_fwd_generation(l) == 3;
+        g.Cb = tp.ktape[l]; g.ldcb = G4; g.epi = TC_EPI_LSTM_P; g.Hh = H; g.lp_B = B; g.lp_vecs = 24;
+        p_in_tape = gemm_ws_supported(g) && std::getenv("ARCVAE_NO_WS") == nullptr;
         if (p_in_tape) {
           ARCVAE_TRY(gemm_ws(g, st));
         } else {
-          g.Cb = tp.Pb; g.epi = TC_EPI_PLAIN; g.Hh = 0; g.lp_B = 0;
+          g.Cb = tp.Pb; g.epi = TC_EPI_PLAIN; g.Hh = 0; g.lp_B = 0; g.lp_vecs = 16;
           ARCVAE_TRY(gemm_tc(g, st));
         }
       }
       ARCVAE_TRY(lstm_cluster_forward(B, T, H, tp.Whb[l], tp.xT, l == 0 ? tp.table0b : nullptr,
-                                      (l == 0 || p_in_tape) ? nullptr : tp.Pb, tp.hb[l], tp.gates_b[l], tp.c[l],
+                                      (l == 0 || p_in_tape) ? nullptr : tp.Pb, tp.hb[l], tp.ktape[l],
                                       l == d->NL - 1 ? tp.h_last : nullptr, tp.xh, errf, st));
     }
     return head_forward(*d, p, tp, tp.h_last, cond, B, mu, logvar, precision, st);
@@ -414,7 +414,7 @@ extern "C" int arcvae_encoder_backward(const arcvae_dims* d, const arcvae_encode
     for (int l = d->NL - 1; l >= 0; l--) {
       const bool top = (l == d->NL - 1);
       if (path == PATH_CLUSTER) {
-        ARCVAE_TRY(lstm_cluster_backward2(B, T, H, tp.Whb[l], tp.gates_b[l], tp.c[l], top ? nullptr : sc.dX,
+        ARCVAE_TRY(lstm_cluster_backward(B, T, H, tp.Whb[l], tp.ktape[l], top ? nullptr : sc.dX,
                                           top ? sc.du : nullptr, H2, sc.dAb, sc.xch, errf, st));
       } else {
         // BPTT one step per launch pair: cell reverse from the bf16 tape, then d h_{t-1} = dA_t @ Wh (split-K, fp32 atomics)

@@ -34,6 +34,7 @@ struct WsParams {
   int epi;        // WS_EPI_*
   int nslab;      // staging slabs
   int lp_B;       // WS_EPI_LSTM_P: rows per timestep
+  int lp_vecs;    // WS_EPI_LSTM_P: vectors per thread slot
   uint4* lp_out;  // WS_EPI_LSTM_P: thread-friendly output
 };
 enum { WS_EPI_PLAIN = 0, WS_EPI_DEC_CELL_FWD = 1, WS_EPI_LSTM_P = 2 };
@@ -250,7 +251,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (rvalid) {
             const long warp_slot = (((long)tile * 4 + s) * 4 + qq) * 2 + half;
-            uint4* dst = p.lp_out + (((long)tt * slots_per_t + warp_slot) * 16 + ni * 4) * 32 + ln;
+            uint4* dst = p.lp_out + (((long)tt * slots_per_t + warp_slot) * p.lp_vecs + ni * 4) * 32 + ln;
 #pragma unroll
             for (int cu = 0; cu < 4; cu++) dst[cu * 32] = make_uint4(pk[4 * cu], pk[4 * cu + 1], pk[4 * cu + 2], pk[4 * cu + 3]);
           }
@@ -328,7 +329,7 @@ bool gemm_ws_supported(const TcGemm& g) {
     return g.Cb != nullptr && (g.N % 256) == 0 && (g.ldcb % 8) == 0 && (reinterpret_cast<uintptr_t>(g.Cb) & 15) == 0 &&
            (g.bias == nullptr || (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0);
   if (g.epi == TC_EPI_LSTM_P)
-    return g.Cb != nullptr && g.N == 1024 && g.Hh == 256 && g.lp_B > 0 && g.rm.tlist == nullptr &&
+    return g.Cb != nullptr && g.N == 1024 && g.Hh == 256 && g.lp_B > 0 && g.lp_vecs >= 16 && g.rm.tlist == nullptr &&
            (reinterpret_cast<uintptr_t>(g.Cb) & 15) == 0 && (g.bias == nullptr || (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0);
   if (g.epi == TC_EPI_DEC_CELL_FWD)
     return g.N == 3 * g.Hh && (g.Hh % 64) == 0 && g.bias != nullptr && (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0 &&
@@ -342,6 +343,7 @@ int gemm_ws(const TcGemm& g, cudaStream_t st) {
   p.M = g.M; p.N = g.N; p.K = g.K;
   p.epi = g.epi == TC_EPI_DEC_CELL_FWD ? WS_EPI_DEC_CELL_FWD : g.epi == TC_EPI_LSTM_P ? WS_EPI_LSTM_P : WS_EPI_PLAIN;
   p.lp_B = g.lp_B;
+  p.lp_vecs = g.lp_vecs;
   p.lp_out = reinterpret_cast<uint4*>(g.Cb);
   p.BN = p.epi == WS_EPI_DEC_CELL_FWD ? 192 : 256;
   p.nt = g.N / p.BN;

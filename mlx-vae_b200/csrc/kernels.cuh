@@ -125,6 +125,7 @@ struct TcGemm {
   // of the cluster recurrence (lstm_cluster.cu: [t][tile][cta][lane quarter][unit half][gate*4 + chunk][lane] x 16 B), so
   // that kernel's epilogue threads read their operands as 512-byte warp accesses.  N = 4*Hh, rows = t*lp_B + b.
   int lp_B = 0;
+  int lp_vecs = 16;                             // 16-byte vectors per thread slot of that layout (gate g, chunk c -> vector g*4 + c)
   int nseg = 1;
   struct Seg { const __nv_bfloat16* B; int ldb; int N; int k_shift; float* C; int ldc; } seg[3] = {};
 };
@@ -140,16 +141,18 @@ int transpose_to_bf16(const float* src, int R, int C, __nv_bfloat16* dst, cudaSt
 
 // persistent cluster LSTM recurrence (lstm_cluster.cu), H == 256
 bool lstm_cluster_supported(int H);
+size_t lstm_cluster_xh_bytes(int B);      // forward exchange buffer (flag-in-data vectors of h_t)
+size_t lstm_cluster_xch_bytes(int B);     // backward exchange buffer (flag-in-data vectors of the partial d h)
+size_t lstm_cluster_ktape_elems(int B, int T, int H);   // bf16 elements of one layer's coefficient tape
+// table0b != null: layer 0 (operands gathered from the token table); Pb != null: row-major input projection; both null: the
+// projection sits in the tape slots (gemm_ws TC_EPI_LSTM_P, lp_vecs = 24)
 int lstm_cluster_forward(int B, int T, int H, const __nv_bfloat16* Whb, const int32_t* xT, const __nv_bfloat16* table0b,
-                         const __nv_bfloat16* Pb, __nv_bfloat16* hb, __nv_bfloat16* gates_b, float* c, float* h_last,
-                         void* xh, int* err_flag, cudaStream_t st);
-size_t lstm_cluster_xh_bytes(int B);
-int lstm_cluster_fwd_generation(int layer);      // 3: reads the input projection from the gate tape (TC_EPI_LSTM_P layout)   // forward exchange buffer (flag-in-data vectors of h_t)
+                         const __nv_bfloat16* Pb, __nv_bfloat16* hb, __nv_bfloat16* ktape, float* h_last, void* xh,
+                         int* err_flag, cudaStream_t st);
 // K-split backward: every CTA multiplies its own dA slice, partial d h reduce-scattered through `xch`
-size_t lstm_cluster_xch_bytes(int B);
-int lstm_cluster_backward2(int B, int T, int H, const __nv_bfloat16* Whb, const __nv_bfloat16* gates_b, const float* c,
-                           const float* dh_ext, const float* dh_last, int dh_last_ld, __nv_bfloat16* dAb, void* xch,
-                           int* err_flag, cudaStream_t st);
+int lstm_cluster_backward(int B, int T, int H, const __nv_bfloat16* Whb, const __nv_bfloat16* ktape, const float* dh_ext,
+                          const float* dh_last, int dh_last_ld, __nv_bfloat16* dAb, void* xch, int* err_flag,
+                          cudaStream_t st);
 int colsum_bf16(const __nv_bfloat16* X, long R, int N, int ldx, float* out, cudaStream_t st);
 // out[m] += sum_{v < V} X[m*ldx + v]   (bias gradient from the one-hot segment of a multi-segment weight-gradient GEMM)
 int rowsum_add(const float* X, int M, int ldx, int V, float* out, cudaStream_t st);

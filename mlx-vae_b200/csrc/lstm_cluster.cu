@@ -1,20 +1,21 @@
 // lstm_cluster.cu — the encoder LSTM recurrence (models/encoder.py:98-101; MLX nn.LSTM loop) as ONE persistent
 // thread-block-cluster kernel per layer and direction: all T timesteps inside the kernel, W_hh resident in shared
-// memory for the whole sequence, h_t / dA_t exchanged between the CTAs of a cluster by TMA multicast into every
-// peer's shared memory (distributed shared memory), gate math fused into the accumulator read-out.
+// memory for the whole sequence, gate math fused into the accumulator read-out, h_t / partial d h_t exchanged between the
+// CTAs of a cluster as FLAG-IN-DATA vectors through L2 (every 16-byte vector carries its own step flag; the consumer
+// thread polls exactly the vectors it needs: no fence, no barrier, no TMA round trip on the critical path).
 //
 // Decomposition (H = 256): a cluster of 4 CTAs owns a tile of 128 batch rows; CTA r owns hidden units [64r, 64r+64).
 //   forward   acc[128 x 256] = h_{t-1}[128 x 256] . Wh[rows {g*H + 64r + u}, :]^T        (4 gates x 64 units)
-//             W slice 256 x 256 bf16 = 128 KB resident; K = 256 arrives as 4 chunks of 64 (one per source CTA)
-//   backward  acc[128 x 64]  = dA_{t+1}[128 x 1024] . Wh[:, 64r .. 64r+63]                (this CTA's units)
-//             W^T slice 64 x 1024 bf16 = 128 KB resident; K = 1024 arrives as 16 chunks of 64 (4 per source CTA)
-// Every chunk is a [128 rows x 64] bf16 tile that its producer CTA has just written to HBM (the tape needs it anyway:
-// h for the next layer / weight gradients, dA for the weight gradients) and then multicasts from L2 into the same
-// 4-stage ring slot of all 4 CTAs with ONE cp.async.bulk.tensor ...multicast::cluster; the ring's `full` mbarriers
-// count the bytes, its `empty` mbarriers are signalled cluster-wide by tcgen05.commit ...multicast::cluster.
-// Roles per CTA (320 threads): warps 0-7 epilogue, warp 8 MMA/control thread, warp 9 sender thread (+ TMEM alloc)
-// (thread = batch row; two warps per TMEM lane quarter, 32 hidden units each; c_t / dc_t live in registers across
-// the whole sequence).
+//             W slice 256 x 256 bf16 = 128 KB resident (K-major); the A operand is a ring of four [128 x 64] slots, slot s =
+//             the units of CTA s: the own slot is written by the CTA's epilogue, the other three by its gather
+//   backward  partial d h_{t-1}[128 x 256] = dA_t[128 x (4 gates x own 64 units)] . Wh[those rows, :]   ("K-split")
+//             the SAME 128 KB image read as an MN-major operand; the four partials are reduce-scattered: the quarter of
+//             the CTA's own units stays in TMEM, the other three travel as flagged bf16 vectors
+// Roles per CTA (384 threads = 3 warpgroups, setmaxnreg 232 / 40): warps 0-7 epilogue (thread = batch row x 32 hidden
+// units; c_t / dL/dc_t live in registers across the whole sequence), warp 8 MMA thread, warp 9 tape thread (TMA stores of the
+// bf16 h / dA tapes) + TMEM allocation, warps 10-11 only donate registers.
+// The superseded generations (cluster mbarriers + TMA multicast / DSMEM copies) are archived, with the measurements that
+// retired them, in profiles/micro/lstm_rec_gen{1,2}_kernel*.cu.txt.
 #include <cooperative_groups.h>
 #include <cstdlib>
 
@@ -27,19 +28,20 @@ using bf16 = __nv_bfloat16;
 
 constexpr int RC_CL = 4;
 constexpr int RC_ROWS = 128;
-constexpr int RC_NSTG = 4;
-constexpr int RC_THREADS = 320;
 constexpr int RC_STAGE_BYTES = RC_ROWS * 64 * 2;   // 16 KB
 constexpr int RC_W_BYTES = 128 * 1024;
 constexpr long RC_SPIN_LIMIT = 1L << 24;           // bounded waits: a protocol bug must not hang the GPU
-
-struct __align__(8) RecShared {
-  uint64_t full[RC_NSTG];
-  uint64_t empty[RC_NSTG];
-  uint64_t w_ready, acc_full, epi_done;
-  uint32_t tmem_base;
-  int failed;
-};
+// The tape between the forward and the backward kernel holds, per hidden unit and step, the SIX coefficients of the cell
+// reverse instead of the four gates and the cell state (same 12 bytes): with dh = dL/dh_t and s = dL/dc_t carried,
+//   d c = s + dh * kc      kc = o (1 - tanh(c_t)^2)          dA_o = dh  * ko     ko = tanh(c_t) o (1 - o)
+//   dA_i = d c * ki        ki = g i (1 - i)                   dA_f = d c * kf     kf = c_{t-1} f (1 - f)
+//   dA_g = d c * kg        kg = i (1 - g^2)                   s'   = d c * f
+// The forward kernel has every factor in fp32 registers anyway (its loop is MUFU-bound, the extra multiplies ride along);
+// the backward loop shrinks from ~22 FP operations + 1 MUFU per unit to 6 and keeps 32 fewer registers alive.
+// Vector index inside a thread's slot: k * 4 + chunk, k = 0..5 = (ki, kf, kg, ko, kc, f), chunk = 8 units.  The input
+// projection of layers >= 1 (gemm_ws TC_EPI_LSTM_P) is written into vectors gate * 4 + chunk of the SAME slot and is
+// overwritten by the coefficients once the step has consumed it.
+constexpr int RC_KV = 24;
 
 struct RecParams {
   int B, T, H;
@@ -48,8 +50,7 @@ struct RecParams {
   const bf16* table0b;    // [V,4H] bf16: P_t = table0[x_t]   (layer 0)   -- or --
   const bf16* Pb;         // [T*B,4H] bf16 pre-activations incl. bias (layers >= 1)
   bf16* hb;               // [T*B,H]  h_t, bf16 (exchange + tape)
-  bf16* gates_b;          // [T*B,4H] activated gates, bf16 (tape)
-  float* c;               // [T*B,H]  cell state, fp32 (tape)
+  bf16* ktape;            // coefficient tape [T][tile][cta][quarter][half][RC_KV vectors][lane] x 16 B (see RC_KV)
   float* h_last;          // [B,H]    h_{T-1}, fp32 (encoder head)
   // backward
   const float* dh_ext;    // [T*B,H] gradient from the layer above (or null)
@@ -71,37 +72,12 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
-                                               uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(tc::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1),
-        "h"(mask)
-      : "memory");
-}
-__device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask) {
-  asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-      ::"r"(tc::smem_u32(bar)), "h"(mask)
-      : "memory");
-}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr));
 }
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-// bounded wait; returns false (and flags the failure) if the barrier never flips
-__device__ __forceinline__ bool wait_or_fail(uint64_t* bar, uint32_t parity, RecShared* sh) {
-  for (long i = 0; i < RC_SPIN_LIMIT; i++) {
-    if (tc::mbar_try_wait(bar, parity)) return true;
-    if ((i & 1023) == 1023 && *(volatile int*)&sh->failed) return false;
-  }
-  *(volatile int*)&sh->failed = 1;
-  return false;
-}
 __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
   const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
 #pragma unroll
@@ -127,41 +103,8 @@ __device__ __forceinline__ float sigmoid_fast(float x) { return sigmoid_approx_(
 
 long long* g_rc_dbg = nullptr;   // set by arcvae_debug_set_rc_stamps (tests only)
 
-// =====================================================================================================================
-// Backward, second design ("K-split").  d h_{t-1} = dA_t . Wh has K = 4H: four times the exchange of the forward if the
-// wide operand dA_t is all-gathered (the first design above: 16 chunks per step through a 4-slot ring = 4 serialized
-// round trips, and 64 issue-bound N=64 MMAs).  Here every CTA multiplies only ITS OWN slice of dA_t (4 gates x its 64
-// units, K = 256, written by its own epilogue straight into a shared-memory operand tile) with the matching rows of Wh
-// (the SAME resident 128 KB image the forward kernel holds, read as an MN-major operand) into a partial
-// d h_{t-1}[128 x 256] for ALL hidden units; the four partials are reduce-scattered: a CTA keeps the quarter of its own
-// units in TMEM and sends the other three quarters (bf16) to their owners through L2-resident exchange buffers,
-// signalled by cluster-scope mbarrier arrivals.  16 full-rate N=256 MMAs per step, one exchange round trip, and the dA
-// tape is written by TMA stores from the operand tile (no per-thread global stores on the critical path).
-struct __align__(8) Bwd2Shared {
-  uint64_t w_ready, a_ready, a_free, acc_full, part_full;
-  uint32_t tmem_base;
-  int failed;
-};
-
+// ---- helpers shared by the kernels below ----------------------------------------------------------------------------
 namespace rc {
-__device__ __forceinline__ uint32_t mapa(uint32_t saddr, uint32_t cta) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(cta));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t raddr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\tselp.b32 %0, 1, 0, P;\n\t}\n"
-      : "=r"(ok)
-      : "r"(tc::smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void fence_acq_rel_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(tc::smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
@@ -178,575 +121,9 @@ __device__ __forceinline__ bool wait_flag(uint64_t* bar, uint32_t parity, volati
   *failed = 1;
   return false;
 }
-__device__ __forceinline__ bool wait_flag_cluster(uint64_t* bar, uint32_t parity, volatile int* failed) {
-  for (long i = 0; i < RC_SPIN_LIMIT; i++) {
-    if (mbar_try_wait_cluster(bar, parity)) return true;
-    if ((i & 1023) == 1023 && *failed) return false;
-  }
-  *failed = 1;
-  return false;
-}
 }  // namespace rc
 
 constexpr int RC_THREADS2 = 384;   // 3 full warpgroups: setmaxnreg is a warpgroup-wide operation (warps 10, 11 only donate registers)
-
-__global__ void __launch_bounds__(RC_THREADS2, 1)
-lstm_bwd2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmD, const RecParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* Wsm = smem;                         // 4 gate panels x [64 k-rows x 256 units] bf16, MN-major, 32 KB each
-  uint8_t* At = smem + RC_W_BYTES;             // 4 gate panels x [128 rows x 64 units] bf16, K-major, 16 KB each
-  Bwd2Shared* sh = reinterpret_cast<Bwd2Shared*>(At + 4 * RC_STAGE_BYTES);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rank = (int)rc::cluster_ctarank();
-  const int tile = blockIdx.x / RC_CL;
-  const int ntiles = gridDim.x / RC_CL;
-  const int row0 = tile * RC_ROWS;
-  const int B = p.B, T = p.T, H = p.H;
-  volatile int* failed = &sh->failed;
-
-  if (threadIdx.x == 0) {
-    tc::mbar_init(&sh->w_ready, 1);
-    tc::mbar_init(&sh->a_ready, 8);
-    tc::mbar_init(&sh->a_free, 2);
-    tc::mbar_init(&sh->acc_full, 1);
-    tc::mbar_init(&sh->part_full, 8 * (RC_CL - 1));
-    sh->failed = 0;
-    tc::fence_barrier_init();
-    tc::prefetch_tmap(&tmW);
-    tc::prefetch_tmap(&tmD);
-  }
-  if (warp == 9) tc::tmem_alloc(&sh->tmem_base, 256);
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  rc::cluster_sync_all();                      // every CTA's barriers exist before any remote arrive
-  const uint32_t tmem_base = sh->tmem_base;
-
-  if (warp >= 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");   // control warpgroup releases registers (4 x 32 x 136) ...
-  if (warp == 8) {
-    // =========================================================== control: resident weights, then 16 MMAs per step
-    if (lane == 0) {
-      tc::mbar_expect_tx(&sh->w_ready, RC_W_BYTES);
-      for (int g = 0; g < 4; g++)
-        for (int j = 0; j < 4; j++)
-          tc::tma_load_2d(Wsm + g * 32768 + j * 8192, &tmW, &sh->w_ready, 64 * j, g * H + 64 * rank);
-      bool ok = rc::wait_flag(&sh->w_ready, 0, failed);
-      const uint32_t idesc = tc::make_idesc_bf16(RC_ROWS, 256, false, true);
-      for (int it = 0; it + 1 < T && ok; it++) {
-        ok = rc::wait_flag(&sh->a_ready, it & 1, failed);
-        if (!ok) break;
-        RC_STAMP(0);
-        tc::tc_fence_after();
-#pragma unroll
-        for (int g = 0; g < 4; g++) {
-          const uint32_t a_addr = tc::smem_u32(At + g * RC_STAGE_BYTES);
-          const uint32_t b_addr = tc::smem_u32(Wsm + g * 32768);
-#pragma unroll
-          for (int k = 0; k < 4; k++)
-            tc::mma_bf16(tmem_base, tc::make_smem_desc(a_addr + 32 * k, 16, 1024),
-                         tc::make_smem_desc(b_addr + 2048 * k, 8192, 1024), idesc, (g > 0 || k > 0) ? 1u : 0u);
-        }
-        tc::mma_commit(&sh->a_free);             // operand tile may be rewritten once these MMAs have read it
-        tc::mma_commit(&sh->acc_full);
-        RC_STAMP(2);
-      }
-    }
-  } else if (warp == 9) {
-    // =========================================================== tape: dA_t tile -> HBM by TMA (rows >= B are clipped)
-    if (lane == 0) {
-      bool ok = true;
-      for (int it = 0; it < T && ok; it++) {
-        ok = rc::wait_flag(&sh->a_ready, it & 1, failed);
-        if (!ok) break;
-        const int t = T - 1 - it;
-        RC_STAMP(8);
-#pragma unroll
-        for (int g = 0; g < 4; g++) rc::tma_store_3d(&tmD, At + g * RC_STAGE_BYTES, g * H + 64 * rank, row0, t);
-        rc::bulk_commit();
-        rc::bulk_wait_read0();
-        RC_STAMP(9);
-        tc::mbar_arrive(&sh->a_free);
-      }
-      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the last tile is in HBM before the kernel ends
-    }
-  } else if (warp < 8) {
-    // =========================================================== epilogue: cell backward, state in registers
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");                // ... which the eight epilogue warps take (8 x 32 x 64)
-    const int q = warp & 3;                  // TMEM lane quarter this warp may read
-    const int hs = warp >> 2;                // which 32 of the CTA's 64 hidden units
-    const int rl = q * 32 + lane;            // row inside the tile
-    const int row = row0 + rl;
-    const bool valid = row < B;
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const int ub = 64 * rank + hs * 32;      // first global hidden unit of this thread
-    const long warp_slot = ((((long)tile * RC_CL + rank) * 4 + q) * 2 + hs);
-    const long slots_per_t = (long)ntiles * RC_CL * 4 * 2;
-    auto gate_tape = [&](int tt, int g, int cu) -> const uint4* {
-      return reinterpret_cast<const uint4*>(p.gates_b) + (((long)tt * slots_per_t + warp_slot) * 16 + g * 4 + cu) * 32 + lane;
-    };
-    auto c_tape = [&](int tt, int i) -> const float4* {
-      return reinterpret_cast<const float4*>(p.c) + (((long)tt * slots_per_t + warp_slot) * 8 + i) * 32 + lane;
-    };
-    // exchange buffer [parity][tile][dst][src][warp][chunk][lane] x 16 B: reader and writer threads have the same
-    // (warp, lane), so every warp-wide access is 512 contiguous bytes
-    auto xch = [&](int par, int dst, int src, int ch) -> uint4* {
-      return p.xch + ((((((long)par * ntiles + tile) * RC_CL + dst) * RC_CL + src) * 8 + warp) * 4 + ch) * 32 + lane;
-    };
-    uint32_t peer_bar[RC_CL];
-#pragma unroll
-    for (int c = 0; c < RC_CL; c++) peer_bar[c] = rc::mapa(tc::smem_u32(&sh->part_full), (uint32_t)c);
-
-    float state[32];                         // dL/dc_t carried to t-1
-    float cnow[32];                          // c_t
-#pragma unroll
-    for (int i = 0; i < 32; i++) { state[i] = 0.f; cnow[i] = 0.f; }
-    uint4 pf[4][4];                          // [chunk][gate] activated gates of the step being prefetched
-    float4 cpf[8];                           // c_{t-1}
-    float4 epf[8];                           // d h from the layer above (dh_ext) for the step being prefetched
-#pragma unroll
-    for (int i = 0; i < 8; i++) epf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    auto prefetch = [&](int tt) {
-      if (!valid) return;
-      if (p.dh_ext != nullptr) {
-        const float4* e = reinterpret_cast<const float4*>(p.dh_ext + ((long)tt * B + row) * H + ub);
-#pragma unroll
-        for (int i = 0; i < 8; i++) epf[i] = __ldg(e + i);
-      }
-#pragma unroll
-      for (int cu = 0; cu < 4; cu++)
-#pragma unroll
-        for (int g = 0; g < 4; g++) pf[cu][g] = __ldg(gate_tape(tt, g, cu));
-      if (tt > 0) {
-#pragma unroll
-        for (int i = 0; i < 8; i++) cpf[i] = __ldg(c_tape(tt - 1, i));
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; i++) cpf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    };
-    if (valid) {
-#pragma unroll
-      for (int i = 0; i < 8; i++) {
-        const float4 v = __ldg(c_tape(T - 1, i));
-        cnow[4 * i] = v.x; cnow[4 * i + 1] = v.y; cnow[4 * i + 2] = v.z; cnow[4 * i + 3] = v.w;
-      }
-    }
-    prefetch(T - 1);
-    bool ok = true;
-    for (int it = 0; it < T && ok; it++) {
-      const int t = T - 1 - it;
-      const long r = (long)t * B + row;
-      if (it > 0) {
-        ok = rc::wait_flag_cluster(&sh->part_full, (it - 1) & 1, failed);     // the three remote partials of d h_t
-        if (ok) ok = rc::wait_flag(&sh->a_free, (it - 1) & 1, failed);         // operand tile reusable
-        if (!ok) break;
-      }
-      if (threadIdx.x == 0) RC_STAMP(4);
-      // all twelve remote partial vectors at once: ONE L2 round trip on the critical path instead of one per chunk
-      uint4 xr[RC_CL - 1][4];
-      if (it > 0) {
-#pragma unroll
-        for (int c = 0, s3 = 0; c < RC_CL; c++) {
-          if (c == rank) continue;
-#pragma unroll
-          for (int cu = 0; cu < 4; cu++) xr[s3][cu] = __ldcg(xch((it - 1) & 1, rank, c, cu));
-          s3++;
-        }
-      }
-#pragma unroll
-      for (int cu = 0; cu < 4; cu++) {
-        const int ug = ub + cu * 8;                  // global hidden-unit index
-        float dh[8];
-        if (it > 0) {
-          // this CTA's own partial (its units) is still in TMEM: the next MMAs are issued only after this epilogue
-          uint32_t rr[8];
-          rc::tmem_ld8(taddr + (uint32_t)(64 * rank + hs * 32 + cu * 8), rr);
-          tc::tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 8; j++) dh[j] = __uint_as_float(rr[j]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; j++) dh[j] = 0.f;
-        }
-        if (it > 0) {
-#pragma unroll
-          for (int s3 = 0; s3 < RC_CL - 1; s3++) {
-            float f[8];
-            rc::unpack8(xr[s3][cu], f);
-#pragma unroll
-            for (int j = 0; j < 8; j++) dh[j] += f[j];
-          }
-        }
-        if (valid) {
-          {
-            const float4 v0 = epf[2 * cu], v1 = epf[2 * cu + 1];
-            dh[0] += v0.x; dh[1] += v0.y; dh[2] += v0.z; dh[3] += v0.w;
-            dh[4] += v1.x; dh[5] += v1.y; dh[6] += v1.z; dh[7] += v1.w;
-          }
-          if (t == T - 1 && p.dh_last != nullptr) {
-            const float* e = p.dh_last + (long)row * p.dh_last_ld + ug;
-#pragma unroll
-            for (int j = 0; j < 8; j++) dh[j] += e[j];
-          }
-        }
-        float gi[8], gf[8], gg[8], go[8], cp[8];
-        rc::unpack8(pf[cu][0], gi);
-        rc::unpack8(pf[cu][1], gf);
-        rc::unpack8(pf[cu][2], gg);
-        rc::unpack8(pf[cu][3], go);
-        cp[0] = cpf[2 * cu].x; cp[1] = cpf[2 * cu].y; cp[2] = cpf[2 * cu].z; cp[3] = cpf[2 * cu].w;
-        cp[4] = cpf[2 * cu + 1].x; cp[5] = cpf[2 * cu + 1].y; cp[6] = cpf[2 * cu + 1].z; cp[7] = cpf[2 * cu + 1].w;
-        float ai[8], af[8], ag[8], ao[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-          const float tcv = rc::tanh_fast(cnow[cu * 8 + j]);
-          const float dct = state[cu * 8 + j] + dh[j] * go[j] * (1.f - tcv * tcv);
-          ao[j] = dh[j] * tcv * go[j] * (1.f - go[j]);
-          ai[j] = dct * gg[j] * gi[j] * (1.f - gi[j]);
-          ag[j] = dct * gi[j] * (1.f - gg[j] * gg[j]);
-          af[j] = dct * cp[j] * gf[j] * (1.f - gf[j]);
-          state[cu * 8 + j] = dct * gf[j];
-          cnow[cu * 8 + j] = cp[j];              // c_{t-1} is next iteration's c_t
-        }
-        // dA_t of these 8 units -> operand tile (gate panel g, row rl, 16-byte chunk hs*4+cu, SWIZZLE_128B)
-        uint8_t* arow = At + rl * 128 + (((hs * 4 + cu) ^ (rl & 7)) << 4);
-        *reinterpret_cast<uint4*>(arow) = rc::pack8(ai);
-        *reinterpret_cast<uint4*>(arow + RC_STAGE_BYTES) = rc::pack8(af);
-        *reinterpret_cast<uint4*>(arow + 2 * RC_STAGE_BYTES) = rc::pack8(ag);
-        *reinterpret_cast<uint4*>(arow + 3 * RC_STAGE_BYTES) = rc::pack8(ao);
-      }
-      if (threadIdx.x == 0) RC_STAMP(5);
-      tc::fence_proxy_async();               // generic-proxy smem writes -> visible to tcgen05.mma / TMA store
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&sh->a_ready);
-      if (threadIdx.x == 0) RC_STAMP(7);
-      if (it + 1 < T) {
-        prefetch(t - 1);                     // tape of the next step: latency hides behind the MMAs
-        if (threadIdx.x == 0) RC_STAMP(10);
-        ok = rc::wait_flag(&sh->acc_full, it & 1, failed);
-        if (!ok) break;
-        if (threadIdx.x == 0) RC_STAMP(11);
-        tc::tc_fence_after();
-        // partial d h_{t-1}[128 x 256]: the quarter of this CTA's units stays in TMEM (read by the next epilogue), the
-        // other three go to their owners
-#pragma unroll
-        for (int c = 0; c < RC_CL; c++) {
-          if (c == rank) continue;
-#pragma unroll
-          for (int hf = 0; hf < 2; hf++) {
-            uint32_t v[16];
-            tc::tmem_ld16(taddr + (uint32_t)(64 * c + hs * 32 + hf * 16), v);
-            tc::tmem_ld_wait();
-#pragma unroll
-            for (int ch = 0; ch < 2; ch++) {
-              float f[8];
-#pragma unroll
-              for (int j = 0; j < 8; j++) f[j] = __uint_as_float(v[ch * 8 + j]);
-              __stcg(xch(it & 1, c, rank, hf * 2 + ch), rc::pack8(f));
-            }
-          }
-        }
-        if (threadIdx.x == 0) RC_STAMP(12);
-        tc::tc_fence_before();
-        rc::fence_acq_rel_cluster();         // this lane's exchange stores are ordered before the arrivals below
-        if (threadIdx.x == 0) RC_STAMP(13);
-        __syncwarp();
-        if (lane == 0) {
-#pragma unroll
-          for (int c = 0; c < RC_CL; c++)
-            if (c != rank) rc::mbar_arrive_remote(peer_bar[c]);
-        }
-      }
-    }
-  }
-
-  tc::tc_fence_before();
-  __syncthreads();
-  if (threadIdx.x == 0 && sh->failed && p.err_flag != nullptr) atomicExch(p.err_flag, 1);
-  rc::cluster_sync_all();                    // nobody exits while a peer may still arrive on its barriers
-  if (warp == 9) {
-    tc::tc_fence_after();
-    tc::tmem_dealloc(tmem_base, 256);
-  }
-}
-
-// =====================================================================================================================
-// Forward, second design: h_t is exchanged through DISTRIBUTED SHARED MEMORY.  The first design publishes h_t to HBM,
-// pays a generic->async proxy fence over global memory (~0.8 us) and an L2 round trip for the TMA multicast (~1 us) on
-// every step.  Here the epilogue writes h_t (bf16, SWIZZLE_128B operand layout) into the CTA's OWN ring slot and a
-// sender thread forwards that 16 KB slot to the same slot of the three peer CTAs with DSMEM bulk copies
-// (cp.async.bulk.shared::cluster.shared::cta) whose bytes complete the peers' `full` mbarriers; the MMA warp of every
-// CTA starts as soon as its four slots are complete.  (Per-thread st.shared::cluster stores were measured at ~4 us per
-// step for the same 48 KB and rejected.)  The bf16 h tape for the next layer / the weight gradients leaves the SM by a
-// TMA store from the own slot, off the critical path.  Three full warpgroups so that setmaxnreg can hand the control warps' registers to
-// the epilogue (no spills).
-struct __align__(8) Fwd2Shared {
-  uint64_t full[RC_CL];      // slot s holds h_t of source CTA s: one arrival (+ 16 KB of DSMEM copy bytes for s != rank)
-  uint64_t empty[RC_CL];     // slot s consumed by the MMAs of all CTAs: RC_CL arrivals (tcgen05.commit multicast)
-  uint64_t own_ready;        // this CTA's epilogue has written h_t into its own slot: 8 arrivals
-  uint64_t slot_free;        // own slot read by the TMA store
-  uint64_t w_ready, acc_full;
-  uint32_t tmem_base;
-  int failed;
-};
-
-namespace rc {
-__device__ __forceinline__ void tma_load_3d_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
-                                               uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
-      ::"r"(tc::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
-        "h"(mask)
-      : "memory");
-}
-// bulk copy local shared memory -> a peer CTA's shared memory; completion (bytes) is signalled on the PEER's mbarrier
-__device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_caddr, const void* src, uint32_t bytes, uint32_t bar_caddr) {
-  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst_caddr), "r"(tc::smem_u32(src)), "r"(bytes), "r"(bar_caddr)
-               : "memory");
-}
-}  // namespace rc
-
-__global__ void __launch_bounds__(RC_THREADS2, 1)
-lstm_fwd2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH, const RecParams p) {
-  constexpr int BN = 256;
-  constexpr int WPANEL = BN * 128;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* Wsm = smem;
-  uint8_t* ring = smem + RC_W_BYTES;
-  Fwd2Shared* sh = reinterpret_cast<Fwd2Shared*>(ring + RC_CL * RC_STAGE_BYTES);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rank = (int)rc::cluster_ctarank();
-  const int tile = blockIdx.x / RC_CL;
-  const int row0 = tile * RC_ROWS;
-  const int B = p.B, T = p.T, H = p.H;
-  const uint16_t ALL = (uint16_t)((1u << RC_CL) - 1);
-  volatile int* failed = &sh->failed;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < RC_CL; s++) {
-      tc::mbar_init(&sh->full[s], 1);
-      tc::mbar_init(&sh->empty[s], RC_CL);
-    }
-    tc::mbar_init(&sh->own_ready, 8);
-    tc::mbar_init(&sh->slot_free, 1);
-    tc::mbar_init(&sh->w_ready, 1);
-    tc::mbar_init(&sh->acc_full, 1);
-    sh->failed = 0;
-    tc::fence_barrier_init();
-    tc::prefetch_tmap(&tmW);
-    tc::prefetch_tmap(&tmH);
-  }
-  if (warp == 9) tc::tmem_alloc(&sh->tmem_base, BN);
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  rc::cluster_sync_all();                      // every CTA's barriers exist before any remote store / arrive
-  const uint32_t tmem_base = sh->tmem_base;
-
-  if (warp >= 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-  if (warp == 8) {
-    // =========================================================== control: weights once, then the MMAs of every step
-    if (lane == 0) {
-      tc::mbar_expect_tx(&sh->w_ready, RC_W_BYTES);
-      for (int kp = 0; kp < 4; kp++)
-        for (int g = 0; g < 4; g++)
-          tc::tma_load_2d(Wsm + kp * WPANEL + g * 8192, &tmW, &sh->w_ready, 64 * kp, g * H + 64 * rank);
-      bool ok = rc::wait_flag(&sh->w_ready, 0, failed);
-      const uint32_t idesc = tc::make_idesc_bf16(RC_ROWS, BN, false, false);
-      for (int it = 1; it < T && ok; it++) {
-        // arm the three slots the peers fill by DSMEM bulk copies (the bytes may already have landed)
-#pragma unroll
-        for (int s = 0; s < RC_CL; s++)
-          if (s != rank) tc::mbar_expect_tx(&sh->full[s], RC_STAGE_BYTES);
-#pragma unroll
-        for (int s = 0; s < RC_CL; s++) {
-          ok = ok && rc::wait_flag_cluster(&sh->full[s], (it - 1) & 1, failed);
-          if (s == 0) RC_STAMP(0);
-        }
-        RC_STAMP(1);
-        if (!ok) break;
-        tc::tc_fence_after();
-#pragma unroll
-        for (int kq = 0; kq < RC_CL; kq++) {
-          const uint32_t a_addr = tc::smem_u32(ring + kq * RC_STAGE_BYTES);
-          const uint32_t b_addr = tc::smem_u32(Wsm + kq * WPANEL);
-#pragma unroll
-          for (int j = 0; j < 4; j++)
-            tc::mma_bf16(tmem_base, tc::make_smem_desc(a_addr + 32 * j, 16, 1024),
-                         tc::make_smem_desc(b_addr + 32 * j, 16, 1024), idesc, (kq > 0 || j > 0) ? 1u : 0u);
-        }
-#pragma unroll
-        for (int s = 0; s < RC_CL; s++) rc::mma_commit_mc(&sh->empty[s], ALL);   // slot s free in ALL CTAs once read
-        tc::mma_commit(&sh->acc_full);
-        RC_STAMP(2);
-      }
-    }
-  } else if (warp == 9) {
-    // =========================================================== sender: own slot -> the three peers (DSMEM bulk copies)
-    //                                                              and -> HBM (TMA store of the bf16 h tape, rows >= B clipped)
-    if (lane == 0) {
-      uint32_t slot_at[RC_CL], full_at[RC_CL];
-#pragma unroll
-      for (int c = 0; c < RC_CL; c++) {
-        slot_at[c] = rc::mapa(tc::smem_u32(ring + rank * RC_STAGE_BYTES), (uint32_t)c);
-        full_at[c] = rc::mapa(tc::smem_u32(&sh->full[rank]), (uint32_t)c);
-      }
-      bool ok = true;
-      for (int it = 0; it < T && ok; it++) {
-        ok = rc::wait_flag(&sh->own_ready, it & 1, failed);
-        if (!ok) break;
-        RC_STAMP(8);
-        // tape first (the next layer and the weight gradients need h_t in HBM anyway) ...
-        rc::tma_store_3d(&tmH, ring + rank * RC_STAGE_BYTES, 64 * rank, row0, it);
-        rc::bulk_commit();
-        if (it + 1 < T) {
-          // ... and once the store has completed, ONE multicast load brings the tile from L2 into slot `rank` of the
-          // three peers (own slot already holds it): measured faster than 3 x 16 KB DSMEM bulk copies (~8 B/clk)
-          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-          rc::tma_load_3d_mc(ring + rank * RC_STAGE_BYTES, &tmH, &sh->full[rank], 64 * rank, row0, it,
-                             (uint16_t)(ALL & ~(1u << rank)));
-          tc::mbar_arrive(&sh->full[rank]);
-        } else {
-          rc::bulk_wait_read0();
-        }
-        RC_STAMP(9);
-        tc::mbar_arrive(&sh->slot_free);
-      }
-      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    }
-  } else if (warp < 8) {
-    // =========================================================== epilogue: gate math, cell state in registers
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-    const int q = warp & 3;
-    const int hs = warp >> 2;
-    const int rl = q * 32 + lane;
-    const int row = row0 + rl;
-    const bool valid = row < B;
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const int ub = 64 * rank + hs * 32;
-    const int ntiles = gridDim.x / RC_CL;
-    const long warp_slot = ((((long)tile * RC_CL + rank) * 4 + q) * 2 + hs);
-    const long slots_per_t = (long)ntiles * RC_CL * 4 * 2;
-    auto gate_tape = [&](int tt, int g, int cu) -> uint4* {
-      return reinterpret_cast<uint4*>(p.gates_b) + (((long)tt * slots_per_t + warp_slot) * 16 + g * 4 + cu) * 32 + lane;
-    };
-    auto c_tape = [&](int tt, int i) -> float4* {
-      return reinterpret_cast<float4*>(p.c) + (((long)tt * slots_per_t + warp_slot) * 8 + i) * 32 + lane;
-    };
-    uint8_t* own_row = ring + rank * RC_STAGE_BYTES + rl * 128;      // this thread's row of the CTA's own slot
-    float state[32];                         // c_{t-1}
-#pragma unroll
-    for (int i = 0; i < 32; i++) state[i] = 0.f;
-    uint4 pf[4][4];                          // [chunk][gate] 8 x bf16 of P_t, prefetched one step ahead
-    auto prefetch = [&](int tt) {
-      if (!valid) return;
-      const long rr = (long)tt * B + row;
-      const bf16* prow = (p.table0b != nullptr ? p.table0b + (long)__ldg(p.xT + rr) * 4 * H : p.Pb + rr * 4 * H) + ub;
-#pragma unroll
-      for (int cu = 0; cu < 4; cu++)
-#pragma unroll
-        for (int g = 0; g < 4; g++) pf[cu][g] = __ldg(reinterpret_cast<const uint4*>(prow + g * H + cu * 8));
-    };
-    prefetch(0);
-    bool ok = true;
-    for (int it = 0; it < T && ok; it++) {
-      const int t = it;
-      if (it > 0) {
-        ok = rc::wait_flag(&sh->acc_full, (it - 1) & 1, failed);
-        if (!ok) break;
-        tc::tc_fence_after();
-      }
-      if (threadIdx.x == 0) RC_STAMP(4);
-      uint4 outq[4][4];                      // activated gates [gate][chunk]
-      uint4 hq[4];                           // h_t
-#pragma unroll
-      for (int cu = 0; cu < 4; cu++) {
-        const int u0 = hs * 32 + cu * 8;             // unit offset inside the CTA's 64
-        float a[4][8];
-        if (it > 0) {
-#pragma unroll
-          for (int g = 0; g < 4; g++) {
-            uint32_t rr[8];
-            rc::tmem_ld8(taddr + (uint32_t)(g * 64 + u0), rr);
-#pragma unroll
-            for (int j = 0; j < 8; j++) a[g][j] = __uint_as_float(rr[j]);
-          }
-          tc::tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int g = 0; g < 4; g++)
-#pragma unroll
-            for (int j = 0; j < 8; j++) a[g][j] = 0.f;
-        }
-#pragma unroll
-        for (int g = 0; g < 4; g++) {
-          float f[8];
-          rc::unpack8(pf[cu][g], f);
-#pragma unroll
-          for (int j = 0; j < 8; j++) a[g][j] += f[j];
-        }
-        float hv[8], gi[8], gf[8], gg[8], go[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-          gi[j] = rc::sigmoid_fast(a[0][j]);
-          gf[j] = rc::sigmoid_fast(a[1][j]);
-          gg[j] = rc::tanh_fast(a[2][j]);
-          go[j] = rc::sigmoid_fast(a[3][j]);
-          const float cn = fmaf(gf[j], state[cu * 8 + j], gi[j] * gg[j]);   // t = 0: state = 0 -> c = i*g
-          state[cu * 8 + j] = cn;
-          hv[j] = go[j] * rc::tanh_fast(cn);
-        }
-        hq[cu] = rc::pack8(hv);
-        outq[0][cu] = rc::pack8(gi); outq[1][cu] = rc::pack8(gf); outq[2][cu] = rc::pack8(gg); outq[3][cu] = rc::pack8(go);
-        if (valid && t == T - 1 && p.h_last != nullptr) {
-          float* hl = p.h_last + (long)row * H + ub + cu * 8;
-          *reinterpret_cast<float4*>(hl) = make_float4(hv[0], hv[1], hv[2], hv[3]);
-          *reinterpret_cast<float4*>(hl + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
-        }
-      }
-      if (threadIdx.x == 0) RC_STAMP(5);
-      // ---- exchange: this thread's 64 bytes of h_t into the CTA's own slot; the sender thread forwards the slot
-      if (it > 0) {
-        ok = rc::wait_flag_cluster(&sh->empty[rank], (it - 1) & 1, failed);   // every CTA's MMAs have read h_{t-1}
-        if (ok) ok = rc::wait_flag(&sh->slot_free, (it - 1) & 1, failed);      // and the tape store has read it
-        if (!ok) break;
-      }
-      if (threadIdx.x == 0) RC_STAMP(6);
-#pragma unroll
-      for (int cu = 0; cu < 4; cu++) *reinterpret_cast<uint4*>(own_row + (((hs * 4 + cu) ^ (rl & 7)) << 4)) = hq[cu];
-      tc::fence_proxy_async();               // generic-proxy smem writes -> visible to the bulk copies / tcgen05.mma / TMA
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&sh->own_ready);
-      if (threadIdx.x == 0) RC_STAMP(7);
-      // ---- off the critical path: the tape, then the operands of the next step
-      if (valid) {
-#pragma unroll
-        for (int g = 0; g < 4; g++)
-#pragma unroll
-          for (int cu = 0; cu < 4; cu++) *gate_tape(t, g, cu) = outq[g][cu];
-#pragma unroll
-        for (int i = 0; i < 8; i++)
-          *c_tape(t, i) = make_float4(state[4 * i], state[4 * i + 1], state[4 * i + 2], state[4 * i + 3]);
-      }
-      if (it + 1 < T) prefetch(t + 1);
-    }
-  }
-
-  tc::tc_fence_before();
-  __syncthreads();
-  if (threadIdx.x == 0 && sh->failed && p.err_flag != nullptr) atomicExch(p.err_flag, 1);
-  rc::cluster_sync_all();                    // nobody exits while a peer may still store into / arrive on its smem
-  if (warp == 9) {
-    tc::tc_fence_after();
-    tc::tmem_dealloc(tmem_base, BN);
-  }
-}
 
 // =====================================================================================================================
 // Third design: FLAG-IN-DATA exchange ("LL": every 16-byte vector that crosses CTAs carries 12 bytes of payload and a
@@ -935,19 +312,14 @@ lstm_bwd3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     const int ub = 64 * rank + hs * 32;      // first global hidden unit of this thread
     const long warp_slot = ((((long)tile * RC_CL + rank) * 4 + q) * 2 + hs);
     const long slots_per_t = (long)ntiles * RC_CL * 4 * 2;
-    auto gate_tape = [&](int tt, int g, int cu) -> const uint4* {
-      return reinterpret_cast<const uint4*>(p.gates_b) + (((long)tt * slots_per_t + warp_slot) * 16 + g * 4 + cu) * 32 + lane;
-    };
-    auto c_tape = [&](int tt, int i) -> const float4* {
-      return reinterpret_cast<const float4*>(p.c) + (((long)tt * slots_per_t + warp_slot) * 8 + i) * 32 + lane;
+    auto ktape = [&](int tt, int kk, int cu) -> const uint4* {
+      return reinterpret_cast<const uint4*>(p.ktape) + (((long)tt * slots_per_t + warp_slot) * RC_KV + kk * 4 + cu) * 32 + lane;
     };
 
     float state[32];                         // dL/dc_t carried to t-1
-    float cnow[32];                          // c_t
 #pragma unroll
-    for (int i = 0; i < 32; i++) { state[i] = 0.f; cnow[i] = 0.f; }
-    uint4 pf[4][4];                          // [chunk][gate] activated gates of the step being prefetched
-    float4 cpf[8];                           // c_{t-1}
+    for (int i = 0; i < 32; i++) state[i] = 0.f;
+    uint4 pf[4][6];                          // [chunk][coefficient] of the step being prefetched
     float dhx[32];                           // d h_t of this thread's units: starts as the gradient from the layer above
                                              // (dh_ext, prefetched), then + own partial (TMEM) + three remote partials
 #pragma unroll
@@ -962,21 +334,13 @@ lstm_bwd3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         dhx[8 * cu + 4] = v1.x; dhx[8 * cu + 5] = v1.y; dhx[8 * cu + 6] = v1.z; dhx[8 * cu + 7] = v1.w;
       }
 #pragma unroll
-      for (int g = 0; g < 4; g++) pf[cu][g] = __ldg(gate_tape(tt, g, cu));
-      if (tt > 0) {
-        cpf[2 * cu] = __ldg(c_tape(tt - 1, 2 * cu));
-        cpf[2 * cu + 1] = __ldg(c_tape(tt - 1, 2 * cu + 1));
-      } else {
-        cpf[2 * cu] = make_float4(0.f, 0.f, 0.f, 0.f);
-        cpf[2 * cu + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      for (int kk = 0; kk < 6; kk++) pf[cu][kk] = __ldcs(ktape(tt, kk, cu));
     };
-    if (valid) {
+    if (!valid) {
 #pragma unroll
-      for (int i = 0; i < 8; i++) {
-        const float4 v = __ldg(c_tape(T - 1, i));
-        cnow[4 * i] = v.x; cnow[4 * i + 1] = v.y; cnow[4 * i + 2] = v.z; cnow[4 * i + 3] = v.w;
-      }
+      for (int cu = 0; cu < 4; cu++)
+#pragma unroll
+        for (int kk = 0; kk < 6; kk++) pf[cu][kk] = make_uint4(0u, 0u, 0u, 0u);   // rows beyond the batch: zero gradients
     }
 #pragma unroll
     for (int cu = 0; cu < 4; cu++) prefetch(T - 1, cu);
@@ -1055,24 +419,22 @@ lstm_bwd3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
             for (int j = 0; j < 8; j++) dh[j] += e[j];
           }
         }
-        float gi[8], gf[8], gg[8], go[8], cp[8];
-        rc::unpack8(pf[cu][0], gi);
-        rc::unpack8(pf[cu][1], gf);
-        rc::unpack8(pf[cu][2], gg);
-        rc::unpack8(pf[cu][3], go);
-        cp[0] = cpf[2 * cu].x; cp[1] = cpf[2 * cu].y; cp[2] = cpf[2 * cu].z; cp[3] = cpf[2 * cu].w;
-        cp[4] = cpf[2 * cu + 1].x; cp[5] = cpf[2 * cu + 1].y; cp[6] = cpf[2 * cu + 1].z; cp[7] = cpf[2 * cu + 1].w;
+        float ki[8], kf[8], kg[8], ko[8], kc[8], gf[8];
+        rc::unpack8(pf[cu][0], ki);
+        rc::unpack8(pf[cu][1], kf);
+        rc::unpack8(pf[cu][2], kg);
+        rc::unpack8(pf[cu][3], ko);
+        rc::unpack8(pf[cu][4], kc);
+        rc::unpack8(pf[cu][5], gf);
         float ai[8], af[8], ag[8], ao[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-          const float tcv = rc::tanh_fast(cnow[cu * 8 + j]);
-          const float dct = state[cu * 8 + j] + dh[j] * go[j] * (1.f - tcv * tcv);
-          ao[j] = dh[j] * tcv * go[j] * (1.f - go[j]);
-          ai[j] = dct * gg[j] * gi[j] * (1.f - gi[j]);
-          ag[j] = dct * gi[j] * (1.f - gg[j] * gg[j]);
-          af[j] = dct * cp[j] * gf[j] * (1.f - gf[j]);
+          const float dct = fmaf(dh[j], kc[j], state[cu * 8 + j]);
+          ao[j] = dh[j] * ko[j];
+          ai[j] = dct * ki[j];
+          af[j] = dct * kf[j];
+          ag[j] = dct * kg[j];
           state[cu * 8 + j] = dct * gf[j];
-          cnow[cu * 8 + j] = cp[j];              // c_{t-1} is next iteration's c_t
         }
         // dA_t of these 8 units -> operand tile (gate panel g, row rl, 16-byte chunk hs*4+cu, SWIZZLE_128B)
         uint8_t* arow = At + rl * 128 + (((hs * 4 + cu) ^ (rl & 7)) << 4);
@@ -1246,11 +608,8 @@ lstm_fwd3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     const int ub = 64 * rank + hs * 32;
     const long warp_slot = ((((long)tile * RC_CL + rank) * 4 + q) * 2 + hs);
     const long slots_per_t = (long)ntiles * RC_CL * 4 * 2;
-    auto gate_tape = [&](int tt, int g, int cu) -> uint4* {
-      return reinterpret_cast<uint4*>(p.gates_b) + (((long)tt * slots_per_t + warp_slot) * 16 + g * 4 + cu) * 32 + lane;
-    };
-    auto c_tape = [&](int tt, int i) -> float4* {
-      return reinterpret_cast<float4*>(p.c) + (((long)tt * slots_per_t + warp_slot) * 8 + i) * 32 + lane;
+    auto ktape = [&](int tt, int kk, int cu) -> uint4* {
+      return reinterpret_cast<uint4*>(p.ktape) + (((long)tt * slots_per_t + warp_slot) * RC_KV + kk * 4 + cu) * 32 + lane;
     };
     const uint32_t row_off = (uint32_t)rl * 128;                     // this thread's row inside a ring slot
     float state[32];                         // c_{t-1}
@@ -1261,10 +620,10 @@ lstm_fwd3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     auto prefetch = [&](int tt, int cu) {
       if (!valid) return;
       if (p.table0b == nullptr && p.Pb == nullptr) {
-        // input projection written by the weight-stationary GEMM (TC_EPI_LSTM_P) into THIS layer's gate tape, in the
-        // tape's own thread-friendly layout: 512-byte warp accesses; the activated gates overwrite it in place
+        // input projection written by the weight-stationary GEMM (TC_EPI_LSTM_P) into THIS layer's tape slots, in the
+        // tape's own thread-friendly layout: 512-byte warp accesses; the coefficients overwrite it once consumed
 #pragma unroll
-        for (int g = 0; g < 4; g++) pf[cu][g] = __ldcs(gate_tape(tt, g, cu));
+        for (int g = 0; g < 4; g++) pf[cu][g] = __ldcs(ktape(tt, g, cu));
         return;
       }
       const long rr = (long)tt * B + row;
@@ -1316,27 +675,35 @@ lstm_fwd3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 8; j++) a[g][j] += f[j];
         }
-        float hv[8], gi[8], gf[8], gg[8], go[8];
+        float hv[8], ki[8], kf[8], kg[8], ko[8], kc[8], gfv[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-          gi[j] = rc::sigmoid_fast(a[0][j]);
-          gf[j] = rc::sigmoid_fast(a[1][j]);
-          gg[j] = rc::tanh_fast(a[2][j]);
-          go[j] = rc::sigmoid_fast(a[3][j]);
-          const float cn = fmaf(gf[j], state[cu * 8 + j], gi[j] * gg[j]);   // t = 0: state = 0 -> c = i*g
+          const float gi = rc::sigmoid_fast(a[0][j]);
+          const float gf = rc::sigmoid_fast(a[1][j]);
+          const float gg = rc::tanh_fast(a[2][j]);
+          const float go = rc::sigmoid_fast(a[3][j]);
+          const float cp = state[cu * 8 + j];                              // t = 0: c_{-1} = 0 -> c = i*g, kf = 0
+          const float cn = fmaf(gf, cp, gi * gg);
           state[cu * 8 + j] = cn;
-          hv[j] = go[j] * rc::tanh_fast(cn);
+          const float tcv = rc::tanh_fast(cn);
+          hv[j] = go * tcv;
+          ki[j] = gg * gi * (1.f - gi);
+          kf[j] = cp * gf * (1.f - gf);
+          kg[j] = gi * (1.f - gg * gg);
+          ko[j] = tcv * go * (1.f - go);
+          kc[j] = go * (1.f - tcv * tcv);
+          gfv[j] = gf;
         }
         hq[cu] = rc::pack8(hv);
         // the tape of this chunk leaves NOW: the LSU is idle during the MUFU-bound gate math, and 24 stores per thread issued
         // in one burst after the exchange were measured to block the thread for > 1 us (1.5 us of the step)
         if (valid) {
-          *gate_tape(t, 0, cu) = rc::pack8(gi);
-          *gate_tape(t, 1, cu) = rc::pack8(gf);
-          *gate_tape(t, 2, cu) = rc::pack8(gg);
-          *gate_tape(t, 3, cu) = rc::pack8(go);
-          *c_tape(t, 2 * cu) = make_float4(state[cu * 8], state[cu * 8 + 1], state[cu * 8 + 2], state[cu * 8 + 3]);
-          *c_tape(t, 2 * cu + 1) = make_float4(state[cu * 8 + 4], state[cu * 8 + 5], state[cu * 8 + 6], state[cu * 8 + 7]);
+          *ktape(t, 0, cu) = rc::pack8(ki);
+          *ktape(t, 1, cu) = rc::pack8(kf);
+          *ktape(t, 2, cu) = rc::pack8(kg);
+          *ktape(t, 3, cu) = rc::pack8(ko);
+          *ktape(t, 4, cu) = rc::pack8(kc);
+          *ktape(t, 5, cu) = rc::pack8(gfv);
         }
         if (valid && t == T - 1 && p.h_last != nullptr) {
           float* hl = p.h_last + (long)row * H + ub + cu * 8;
@@ -1462,87 +829,56 @@ static int launch_cluster384(const void* fn, size_t smem, int B, const CUtensorM
   return 0;
 }
 
-// generation of the exchange protocol per direction: 3 = flag-in-data vectors, 2 = cluster mbarriers + TMA multicast.
-// Measured at B = 4096 x T = 128 (profiles/rc_stamps3.py): forward 6.9 us (gen 2) vs 8.4 us (gen 3) per step, backward
-// 10.8 us (gen 2) vs 8.5 us (gen 3)
-static int env_gen(const char* name, int dflt) {
-  const char* e = getenv(name);
-  if (e == nullptr) return dflt;
-  const int g = atoi(e);
-  return (g == 2 || g == 3) ? g : dflt;
-}
-// forward: layer 0 (operands gathered from the token table, an uncoalesced load pattern that the gen-2 kernel hides behind
-// its TMA exchange) and the upper layers (operands from the thread-friendly tape) are chosen separately
-int lstm_cluster_fwd_generation(int layer) {
-  static const int gen0 = env_gen("ARCVAE_RC_FWD_GEN0", 3);
-  static const int gen1 = env_gen("ARCVAE_RC_FWD_GEN", 3);
-  return layer == 0 ? gen0 : gen1;
-}
-static int rc_bwd_generation() {
-  static const int gen = env_gen("ARCVAE_RC_BWD_GEN", 3);
-  return gen;
-}
-
-static int rc_flags() {
+static int rc_flags() {   // experiment switches of the profiling scripts (ARCVAE_RC_FLAGS; bit 0: issue all 16 backward MMAs at once)
   static const int f = [] { const char* e = getenv("ARCVAE_RC_FLAGS"); return e ? atoi(e) : 0; }();
   return f;
 }
 
 size_t lstm_cluster_xh_bytes(int B) { return (size_t)2 * cdiv(B, RC_ROWS) * RC_CL * 8 * rc::LL_NV * 32 * sizeof(uint4); }
+size_t lstm_cluster_xch_bytes(int B) { return (size_t)2 * cdiv(B, RC_ROWS) * RC_CL * RC_CL * 8 * rc::LL_NV * 32 * sizeof(uint4); }
+// coefficient tape of one layer (bf16 elements): T x tile-padded batch x 6 coefficients per hidden unit
+size_t lstm_cluster_ktape_elems(int B, int T, int H) { return (size_t)T * cdiv(B, RC_ROWS) * RC_ROWS * 6 * H; }
 
+// Pb == nullptr && table0b == nullptr: the input projection sits in the tape slots (gemm_ws TC_EPI_LSTM_P)
 int lstm_cluster_forward(int B, int T, int H, const bf16* Whb, const int32_t* xT, const bf16* table0b, const bf16* Pb,
-                         bf16* hb, bf16* gates_b, float* c, float* h_last, void* xh, int* err_flag, cudaStream_t st) {
+                         bf16* hb, bf16* ktape, float* h_last, void* xh, int* err_flag, cudaStream_t st) {
   ARCVAE_REQUIRE(lstm_cluster_supported(H), "cluster recurrence kernel is built for hidden_dim 256");
   ARCVAE_REQUIRE(T < (1 << 30), "sequence length");
+  ARCVAE_REQUIRE(xh != nullptr && ktape != nullptr, "forward exchange buffer / tape");
   CUtensorMap tmW, tmH;
   ARCVAE_TRY(make_tmap_bf16(&tmW, Whb, 4L * H, H, H, 64, 64));
   ARCVAE_TRY(make_tmap_bf16_3d(&tmH, hb, T, B, H, H, 64, RC_ROWS));
   RecParams p{};
   p.B = B; p.T = T; p.H = H;
-  p.xT = xT; p.table0b = table0b; p.Pb = Pb; p.hb = hb; p.gates_b = gates_b; p.c = c; p.h_last = h_last;
+  p.xT = xT; p.table0b = table0b; p.Pb = Pb; p.hb = hb; p.ktape = ktape; p.h_last = h_last;
   p.xch = reinterpret_cast<uint4*>(xh);
   p.err_flag = err_flag;
   p.dbg = g_rc_dbg;
   p.flags = rc_flags();
-  if (lstm_cluster_fwd_generation(table0b != nullptr ? 0 : 1) == 2) {
-    const size_t smem = RC_W_BYTES + RC_CL * RC_STAGE_BYTES + sizeof(Fwd2Shared) + 1024;
-    if (first_use_on_device(ONCE_FWD2))
-      ARCVAE_CUDA(cudaFuncSetAttribute(lstm_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    return launch_cluster384((const void*)lstm_fwd2_kernel, smem, B, tmW, tmH, p, st);
-  }
-  ARCVAE_REQUIRE(xh != nullptr, "forward exchange buffer");
   const size_t smem = RC_W_BYTES + RC_CL * RC_STAGE_BYTES + sizeof(Fwd3Shared) + 1024;
   if (first_use_on_device(ONCE_FWD3))
     ARCVAE_CUDA(cudaFuncSetAttribute(lstm_fwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   return launch_cluster384((const void*)lstm_fwd3_kernel, smem, B, tmW, tmH, p, st);
 }
 
-size_t lstm_cluster_xch_bytes(int B) { return (size_t)2 * cdiv(B, RC_ROWS) * RC_CL * RC_CL * 8 * rc::LL_NV * 32 * sizeof(uint4); }
-
-// K-split backward (lstm_bwd2_kernel): Whb is the SAME [4H,H] bf16 matrix the forward kernel uses
-int lstm_cluster_backward2(int B, int T, int H, const bf16* Whb, const bf16* gates_b, const float* c, const float* dh_ext,
-                           const float* dh_last, int dh_last_ld, bf16* dAb, void* xch, int* err_flag, cudaStream_t st) {
+// K-split backward: Whb is the SAME [4H,H] bf16 matrix the forward kernel uses
+int lstm_cluster_backward(int B, int T, int H, const bf16* Whb, const bf16* ktape, const float* dh_ext, const float* dh_last,
+                          int dh_last_ld, bf16* dAb, void* xch, int* err_flag, cudaStream_t st) {
   ARCVAE_REQUIRE(lstm_cluster_supported(H), "cluster recurrence kernel is built for hidden_dim 256");
   CUtensorMap tmW, tmD;
   ARCVAE_TRY(make_tmap_bf16(&tmW, Whb, 4L * H, H, H, 64, 64));
   ARCVAE_TRY(make_tmap_bf16_3d(&tmD, dAb, T, B, 4L * H, 4L * H, 64, RC_ROWS));
   RecParams p{};
   p.B = B; p.T = T; p.H = H;
-  p.gates_b = const_cast<bf16*>(gates_b); p.c = const_cast<float*>(c);
+  p.ktape = const_cast<bf16*>(ktape);
   p.dh_ext = dh_ext; p.dh_last = dh_last; p.dh_last_ld = dh_last_ld; p.dAb = dAb; p.err_flag = err_flag;
   p.xch = reinterpret_cast<uint4*>(xch);
   p.dbg = g_rc_dbg;
   p.flags = rc_flags();
-  const bool g2 = rc_bwd_generation() == 2;
-  const size_t smem = RC_W_BYTES + 4 * RC_STAGE_BYTES + (g2 ? sizeof(Bwd2Shared) : sizeof(Bwd3Shared)) + 1024;
-  if (g2) {
-    if (first_use_on_device(ONCE_BWD2))
-      ARCVAE_CUDA(cudaFuncSetAttribute(lstm_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  } else {
-    if (first_use_on_device(ONCE_BWD3))
-      ARCVAE_CUDA(cudaFuncSetAttribute(lstm_bwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
-  return launch_cluster384(g2 ? (const void*)lstm_bwd2_kernel : (const void*)lstm_bwd3_kernel, smem, B, tmW, tmD, p, st);
+  const size_t smem = RC_W_BYTES + 4 * RC_STAGE_BYTES + sizeof(Bwd3Shared) + 1024;
+  if (first_use_on_device(ONCE_BWD3))
+    ARCVAE_CUDA(cudaFuncSetAttribute(lstm_bwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return launch_cluster384((const void*)lstm_bwd3_kernel, smem, B, tmW, tmD, p, st);
 }
 
 }  // namespace arcvae

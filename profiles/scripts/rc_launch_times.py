@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Device time of the recurrence launches alone (library timing scopes): encoder forward = layer 0 + layer 1 launches,
-backward = layer 1 + layer 0 launches, un-instrumented (no stamps).  Env: ARCVAE_RC_FWD_GEN0 / ARCVAE_RC_FWD_GEN / ARCVAE_RC_BWD_GEN."""
+backward = layer 1 + layer 0 launches, un-instrumented (no stamps)."""
 import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -27,5 +27,4 @@ torch.cuda.synchronize()
 fb = M._lib.timing_read()["recurrence"]
 M._lib.timing_enable(False)
 enc.check()
-tag = "/".join(os.environ.get(k, d) for k, d in (("ARCVAE_RC_FWD_GEN0", "3"), ("ARCVAE_RC_FWD_GEN", "3"), ("ARCVAE_RC_BWD_GEN", "3")))
-print(f"gen L0fwd/L1fwd/bwd {tag} B={B} T={T}: forward launches {f[0] / n:.3f} ms ({f[1] // n} launches), backward launches {(fb[0] - f[0]) / n:.3f} ms")
+print(f"B={B} T={T}: forward launches {f[0] / n:.3f} ms ({f[1] // n} launches), backward launches {(fb[0] - f[0]) / n:.3f} ms")
