@@ -433,8 +433,8 @@ def main():
         t_ms = per_step["recurrence"]
         n = max(1.0, launches_cat["recurrence"])
         ach = flop / (t_ms * 1e-3) / 1e12
-        tape = NL * R * (4 * H * 2 * 2 + H * 4 * 2 + H * 2 + 4 * H * 2 + H * 4)   # gates w+r, c w+r, h w, dA w, P/dX r (bf16/fp32 mix)
-        roofs["recurrence"] = {"kernel": "lstm_fwd2_kernel+lstm_bwd2_kernel" if H == 256 else
+        tape = NL * R * (6 * H * 2 * 2 + H * 2 + 4 * H * 2 + H * 4)   # coefficient tape w+r (6 bf16 per unit), h w, dA w, P/dX r
+        roofs["recurrence"] = {"kernel": "lstm_fwd3_kernel+lstm_bwd3_kernel" if H == 256 else
                                          ("gemm_tc_kernel<LSTM-step epilogue> per timestep + k_lstm_cell_bwd_b / split-K gemm_tc_kernel (W_hh L2-resident)"
                                           if H % 64 == 0 else "per-step gemm_tc_kernel + k_lstm_cell_*"),
                                "bound": "tensor", "achieved": ach,
@@ -446,12 +446,12 @@ def main():
                                "hbm_tape_gbs": tape / (t_ms * 1e-3) / 1e9, "hbm_tape_frac": tape / (t_ms * 1e-3) / 1e9 / pk["hbm"],
                                # cluster kernels (H = 256): per step and 128-row tile the tensor core reads the h / dA operand
                                # tile (64 KB) and the resident W_hh slice (128 KB) from shared memory in each of the 4 CTAs;
-                               # the exchange moves 3 x 16 KB per CTA into peer shared memory (forward: TMA multicast) or
-                               # 3 x 16 KB of bf16 partials per CTA through L2 (backward)
+                               # the exchange moves 3 x 16 KB per CTA through L2 as flag-in-data vectors (forward: h_t,
+                               # backward: bf16 partial sums of d h)
                                "smem_operand_gbs": (NL * 2 * T * ((B + 127) // 128) * 4 * 192 * 1024) / (t_ms * 1e-3) / 1e9 if H == 256 else None,
                                "cluster_exchange_gbs": (NL * 2 * T * ((B + 127) // 128) * 4 * 48 * 1024) / (t_ms * 1e-3) / 1e9 if H == 256 else None,
                                "us_per_timestep": 1e3 * t_ms / (NL * 2 * T),
-                               "note": "latency-bound by construction (T sequential cluster exchanges); algorithmic FLOP = "
+                               "note": "latency-bound by construction (T sequential exchanges between the 4 CTAs of a cluster); algorithmic FLOP = "
                                        "2*4H*H per row-step, forward + d h backward, all layers"}
     if "gemm_tc" in per_step:
         # time-parallel contractions: everything of SURVEY 8d's 3 x 341.8 MFLOP/molecule that is not the recurrence.
