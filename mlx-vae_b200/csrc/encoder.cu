@@ -131,6 +131,7 @@ struct EncScratch {
   bf16* dlvhb;      // [B,2H]
   bf16* onehot;     // [T*B,SCATTER_NW] one-hot tokens (tensor-core scatter)
   void* xch;        // cluster backward: exchange buffers of the partial d h
+  bf16* dXtf;       // cluster backward: d h for the layer below, bf16, thread-friendly layout (gemm_tc TC_EPI_LSTM_DH)
   float* segtmp;    // [4H,SCATTER_NW] one-hot segment of the fused weight-gradient GEMM (dtable0^T / bias row sums)
   float* dh_part;   // [4][B,H] split-K partials of d h_{t-1} (fused per-step path)
 };
@@ -155,6 +156,7 @@ static size_t enc_scratch_layout(const arcvae_dims& d, int B, int T, int path, v
   }
   ss.onehot = (path != PATH_STEP_F32) ? a.take<bf16>((size_t)T * B * SCATTER_NW) : nullptr;
   ss.xch = (path != PATH_STEP_F32) ? a.take<char>(lstm_cluster_xch_bytes(B)) : nullptr;
+  ss.dXtf = (path != PATH_STEP_F32 && d.NL > 1) ? a.take<bf16>(lstm_cluster_dh_tf_elems(B, T, d.H)) : nullptr;
   ss.segtmp = (path != PATH_STEP_F32) ? a.take<float>((size_t)4 * d.H * SCATTER_NW) : nullptr;
   ss.dh_part = (path != PATH_STEP_F32) ? a.take<float>((size_t)4 * B * d.H) : nullptr;
   if (s) *s = ss;
@@ -410,11 +412,12 @@ extern "C" int arcvae_encoder_backward(const arcvae_dims* d, const arcvae_encode
     int* const errf = device_error_flag();
     ARCVAE_REQUIRE(errf != nullptr, "device error flag allocation failed");
     const bool fuse_dw = path == PATH_CLUSTER && scatter_onehot_supported(G4, d->V, 0) && (H % 64) == 0 && H <= 256;
+    const bool dx_tf = fuse_dw && H == 256;     // the d X GEMM feeds the next cluster kernel directly
     if (fuse_dw) ARCVAE_TRY(build_onehot(tp.xT, R, d->V, nullptr, B, 0, sc.onehot, st));
     for (int l = d->NL - 1; l >= 0; l--) {
       const bool top = (l == d->NL - 1);
       if (path == PATH_CLUSTER) {
-        ARCVAE_TRY(lstm_cluster_backward(B, T, H, tp.Whb[l], tp.ktape[l], top ? nullptr : sc.dX,
+        ARCVAE_TRY(lstm_cluster_backward(B, T, H, tp.Whb[l], tp.ktape[l], (top || dx_tf) ? nullptr : sc.dX, (top || !dx_tf) ? nullptr : sc.dXtf,
                                           top ? sc.du : nullptr, H2, sc.dAb, sc.xch, errf, st));
       } else {
         // BPTT one step per launch pair: cell reverse from the bf16 tape, then d h_{t-1} = dA_t @ Wh (split-K, fp32 atomics)
@@ -466,8 +469,20 @@ extern "C" int arcvae_encoder_backward(const arcvae_dims* d, const arcvae_encode
         ARCVAE_TRY(gemm_tc(q, st));
         if (l > 0) {
           ARCVAE_TRY(rowsum_add(sc.segtmp, G4, SCATTER_NW, d->V, g->bias[l], st));
-          ARCVAE_TRY(gemm_any(precision, 0, 0, (int)R, H, G4, Mat{nullptr, sc.dAb, G4}, Mat{nullptr, tp.Wxb[l], H}, sc.dX, H,
-                              nullptr, false, id, R, st));
+          if (dx_tf) {
+            // d h_{l-1} = dA_l @ Wx_l, bf16 in the layout the cluster BPTT of layer l-1 reads (no fp32 [T*B,H] round trip)
+            TcGemm q2{};
+            q2.M = (int)R; q2.N = H; q2.K = G4;
+            q2.A = sc.dAb; q2.lda = G4; q2.a_mn = false;
+            q2.B = tp.Wxb[l]; q2.ldb = H; q2.b_mn = true;
+            q2.Cb = sc.dXtf; q2.ldcb = H; q2.accumulate = false; q2.splitk = 1;
+            q2.rm = id; q2.a_rows_total = R;
+            q2.epi = TC_EPI_LSTM_DH; q2.lp_B = B;
+            ARCVAE_TRY(gemm_tc(q2, st));
+          } else {
+            ARCVAE_TRY(gemm_any(precision, 0, 0, (int)R, H, G4, Mat{nullptr, sc.dAb, G4}, Mat{nullptr, tp.Wxb[l], H}, sc.dX, H,
+                                nullptr, false, id, R, st));
+          }
         } else {
           ARCVAE_TRY(transpose_f32(sc.segtmp, G4, SCATTER_NW, SCATTER_NW, sc.dtable0, st));   // -> [SCATTER_NW, 4H]
           ARCVAE_TRY(layer0_input_backward(*d, p, g, sc, st));

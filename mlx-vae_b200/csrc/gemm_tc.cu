@@ -51,6 +51,7 @@ struct TcParams {
   // (rows shifted by seg_shift[ni]; negative TMA coordinates zero-fill) into its own C
   int nseg; int segN[3]; int seg_shift[3]; float* segC[3]; int seg_ldc[3];
   int bm2;           // 256-row tiles (two M=128 MMAs share every B tile): halves the B re-reads of the long-K weight-gradient shapes
+  int lp_B;          // TC_EPI_LSTM_DH: rows per timestep of the thread-friendly output
   int use_scratch;   // per-warp transposition scratch present after the TcShared block
   int scr_pitch;     // bytes per scratch row
 };
@@ -597,6 +598,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             scr_store_rows(scr, TC_SCR_PITCH, reinterpret_cast<uint8_t*>(p.dg_out + goff), 3L * H * 2, 384, rows_here, lane);
           __syncwarp();
         }
+      } else if (p.epi == TC_EPI_LSTM_DH) {
+        // d h for the cluster BPTT of the layer below (d X = dA @ Wx): bf16, written in the layout that kernel's epilogue
+        // thread (batch row x 32 hidden units) reads — [t][tile][cta = unit/64][lane quarter][unit half][chunk 4][lane] x 16 B —
+        // so thread = row stores 16-byte chunks and a warp covers 512 consecutive bytes (no scratch, no fp32 round trip)
+        {
+          // (tcgen05.ld is warp-collective: every lane runs the loop, rows beyond M only skip the stores)
+          const int tt = (int)(grow / p.lp_B), bb = (int)(grow - (long)tt * p.lp_B);
+          const long slots_per_t = (long)((p.lp_B + 127) >> 7) * 32;
+          const int tile_b = bb >> 7, qq = (bb >> 5) & 3, ln = bb & 31;
+          uint4* const base = reinterpret_cast<uint4*>(p.Cb) + (long)tt * slots_per_t * 128 + ln;
+#pragma unroll 1
+          for (int ch = ch_lo; ch < ch_hi; ch++) {
+            uint32_t r[16];
+            tc::tmem_ld16(taddr + ch * 16, r);
+            tc::tmem_ld_wait();
+            const int c0 = n0 + ch * 16;                         // hidden unit of the chunk's first column
+            const long warp_slot = (((long)tile_b * 4 + (c0 >> 6)) * 4 + qq) * 2 + ((c0 >> 5) & 1);
+            uint4* dst = base + (warp_slot * 4 + ((c0 >> 3) & 3)) * 32;
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+              pk[j] = *reinterpret_cast<uint32_t*>(&t2);
+            }
+            if (row_ok) {
+              dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              dst[32] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
+          }
+        }
       } else if (p.use_scratch) {
         // plain bf16 output, full tiles: this warp's half of the tile's columns, staged and written along the rows
         const int nb = (ch_hi - ch_lo) * 32;                    // bytes per row
@@ -813,6 +844,9 @@ int gemm_tc(const TcGemm& g, cudaStream_t st) {
   p.C = g.C; p.ldc = g.ldc; p.Cb = g.Cb; p.ldcb = g.ldcb; p.bias = g.bias; p.accumulate = g.accumulate ? 1 : 0;
   p.rm = g.rm;
   p.epi = g.epi; p.gates_b = g.gates_b; p.hb_out = g.hb_out; p.dg_out = g.dg_out;
+  p.lp_B = g.lp_B;
+  ARCVAE_REQUIRE(g.epi != TC_EPI_LSTM_DH || (g.lp_B > 0 && g.Cb != nullptr && g.N == 256 && g.splitk <= 1 && g.rm.tlist == nullptr),
+                 "d h epilogue: N = 256, bf16 thread-friendly output");
   p.Hh = g.Hh;
   p.pre_b = g.pre_b; p.c_prev = g.c_prev; p.c_out = g.c_out; p.hf_out = g.hf_out;
   p.ce_target = g.ce_target; p.ce_fb = g.ce_fb; p.ce_tok = g.ce_tok; p.ce_B = g.ce_B; p.ce_dl = g.ce_dl; p.ce_ldl = g.ce_ldl;

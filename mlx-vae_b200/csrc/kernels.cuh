@@ -129,7 +129,7 @@ struct TcGemm {
   int nseg = 1;
   struct Seg { const __nv_bfloat16* B; int ldb; int N; int k_shift; float* C; int ldc; } seg[3] = {};
 };
-enum { TC_EPI_PLAIN = 0, TC_EPI_DEC_CELL_FWD = 1, TC_EPI_DEC_CELL_BWD = 2, TC_EPI_LSTM_FWD = 3, TC_EPI_CE = 4, TC_EPI_LSTM_P = 5 };
+enum { TC_EPI_PLAIN = 0, TC_EPI_DEC_CELL_FWD = 1, TC_EPI_DEC_CELL_BWD = 2, TC_EPI_LSTM_FWD = 3, TC_EPI_CE = 4, TC_EPI_LSTM_P = 5, TC_EPI_LSTM_DH = 6 };
 int gemm_tc(const TcGemm& g, cudaStream_t st);
 // weight-stationary variant (gemm_ws.cu) for K <= 256, bf16 output / fused decoder cell; gemm_tc dispatches to it
 bool gemm_ws_supported(const TcGemm& g);
@@ -149,9 +149,11 @@ size_t lstm_cluster_ktape_elems(int B, int T, int H);   // bf16 elements of one 
 int lstm_cluster_forward(int B, int T, int H, const __nv_bfloat16* Whb, const int32_t* xT, const __nv_bfloat16* table0b,
                          const __nv_bfloat16* Pb, __nv_bfloat16* hb, __nv_bfloat16* ktape, float* h_last, void* xh,
                          int* err_flag, cudaStream_t st);
-// K-split backward: every CTA multiplies its own dA slice, partial d h reduce-scattered through `xch`
+// K-split backward: every CTA multiplies its own dA slice, partial d h reduce-scattered through `xch`.  Gradient from the
+// layer above: dh_ext (fp32 [T*B,H], row-major) or dh_tf (bf16, thread-friendly layout written by gemm_tc TC_EPI_LSTM_DH)
+size_t lstm_cluster_dh_tf_elems(int B, int T, int H);
 int lstm_cluster_backward(int B, int T, int H, const __nv_bfloat16* Whb, const __nv_bfloat16* ktape, const float* dh_ext,
-                          const float* dh_last, int dh_last_ld, __nv_bfloat16* dAb, void* xch, int* err_flag,
+                          const __nv_bfloat16* dh_tf, const float* dh_last, int dh_last_ld, __nv_bfloat16* dAb, void* xch, int* err_flag,
                           cudaStream_t st);
 int colsum_bf16(const __nv_bfloat16* X, long R, int N, int ldx, float* out, cudaStream_t st);
 // out[m] += sum_{v < V} X[m*ldx + v]   (bias gradient from the one-hot segment of a multi-segment weight-gradient GEMM)

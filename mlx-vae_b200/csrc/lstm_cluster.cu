@@ -54,6 +54,7 @@ struct RecParams {
   float* h_last;          // [B,H]    h_{T-1}, fp32 (encoder head)
   // backward
   const float* dh_ext;    // [T*B,H] gradient from the layer above (or null)
+  const bf16* dh_tf;      // the same gradient, bf16, in the thread-friendly layout [t][tile][cta][quarter][half][chunk 4][lane] x 16 B
   const float* dh_last;   // [B, dh_last_ld] gradient into h_{T-1} from the head (or null)
   int dh_last_ld;
   bf16* dAb;              // [T*B,4H] pre-activation gradients, bf16 (exchange + tape)
@@ -327,7 +328,12 @@ lstm_bwd3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     // tape of step tt for one 8-unit chunk
     auto prefetch = [&](int tt, int cu) {
       if (!valid) return;
-      if (p.dh_ext != nullptr) {
+      if (p.dh_tf != nullptr) {
+        float f[8];
+        rc::unpack8(__ldcs(reinterpret_cast<const uint4*>(p.dh_tf) + (((long)tt * slots_per_t + warp_slot) * 4 + cu) * 32 + lane), f);
+#pragma unroll
+        for (int j = 0; j < 8; j++) dhx[8 * cu + j] = f[j];
+      } else if (p.dh_ext != nullptr) {
         const float4* e = reinterpret_cast<const float4*>(p.dh_ext + ((long)tt * B + row) * H + ub) + 2 * cu;
         const float4 v0 = __ldg(e), v1 = __ldg(e + 1);
         dhx[8 * cu] = v0.x; dhx[8 * cu + 1] = v0.y; dhx[8 * cu + 2] = v0.z; dhx[8 * cu + 3] = v0.w;
@@ -837,6 +843,7 @@ static int rc_flags() {   // experiment switches of the profiling scripts (ARCVA
 size_t lstm_cluster_xh_bytes(int B) { return (size_t)2 * cdiv(B, RC_ROWS) * RC_CL * 8 * rc::LL_NV * 32 * sizeof(uint4); }
 size_t lstm_cluster_xch_bytes(int B) { return (size_t)2 * cdiv(B, RC_ROWS) * RC_CL * RC_CL * 8 * rc::LL_NV * 32 * sizeof(uint4); }
 // coefficient tape of one layer (bf16 elements): T x tile-padded batch x 6 coefficients per hidden unit
+size_t lstm_cluster_dh_tf_elems(int B, int T, int H) { return (size_t)T * cdiv(B, RC_ROWS) * RC_ROWS * H; }
 size_t lstm_cluster_ktape_elems(int B, int T, int H) { return (size_t)T * cdiv(B, RC_ROWS) * RC_ROWS * 6 * H; }
 
 // Pb == nullptr && table0b == nullptr: the input projection sits in the tape slots (gemm_ws TC_EPI_LSTM_P)
@@ -862,8 +869,8 @@ int lstm_cluster_forward(int B, int T, int H, const bf16* Whb, const int32_t* xT
 }
 
 // K-split backward: Whb is the SAME [4H,H] bf16 matrix the forward kernel uses
-int lstm_cluster_backward(int B, int T, int H, const bf16* Whb, const bf16* ktape, const float* dh_ext, const float* dh_last,
-                          int dh_last_ld, bf16* dAb, void* xch, int* err_flag, cudaStream_t st) {
+int lstm_cluster_backward(int B, int T, int H, const bf16* Whb, const bf16* ktape, const float* dh_ext, const bf16* dh_tf,
+                          const float* dh_last, int dh_last_ld, bf16* dAb, void* xch, int* err_flag, cudaStream_t st) {
   ARCVAE_REQUIRE(lstm_cluster_supported(H), "cluster recurrence kernel is built for hidden_dim 256");
   CUtensorMap tmW, tmD;
   ARCVAE_TRY(make_tmap_bf16(&tmW, Whb, 4L * H, H, H, 64, 64));
@@ -871,7 +878,7 @@ int lstm_cluster_backward(int B, int T, int H, const bf16* Whb, const bf16* ktap
   RecParams p{};
   p.B = B; p.T = T; p.H = H;
   p.ktape = const_cast<bf16*>(ktape);
-  p.dh_ext = dh_ext; p.dh_last = dh_last; p.dh_last_ld = dh_last_ld; p.dAb = dAb; p.err_flag = err_flag;
+  p.dh_ext = dh_ext; p.dh_tf = dh_tf; p.dh_last = dh_last; p.dh_last_ld = dh_last_ld; p.dAb = dAb; p.err_flag = err_flag;
   p.xch = reinterpret_cast<uint4*>(xch);
   p.dbg = g_rc_dbg;
   p.flags = rc_flags();
