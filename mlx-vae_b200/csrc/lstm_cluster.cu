@@ -100,7 +100,13 @@ __device__ __forceinline__ float tanh_fast(float x) { return tanh_approx_(x); }
 __device__ __forceinline__ float sigmoid_fast(float x) { return sigmoid_approx_(x); }
 }  // namespace rc
 
+// per-step globaltimer stamps for profiles/rc_stamps3.py: compiled in only with `make STAMPS=1` (they cost registers in
+// loops that are tuned to the last one, and the stamping thread runs ~1 us behind its peers)
+#ifdef ARCVAE_RC_STAMPS
 #define RC_STAMP(slot) do { if (p.dbg != nullptr && blockIdx.x < 4 && it < 64) { unsigned long long _gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_gt)); p.dbg[(blockIdx.x * 64 + it) * 32 + (slot)] = (long long)_gt; } } while (0)
+#else
+#define RC_STAMP(slot) do { } while (0)
+#endif
 
 long long* g_rc_dbg = nullptr;   // set by arcvae_debug_set_rc_stamps (tests only)
 
@@ -361,7 +367,8 @@ lstm_bwd3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         const uint32_t flag = (uint32_t)it;
         const uint4* src[RC_CL - 1];
 #pragma unroll
-        for (int j3 = 1; j3 < RC_CL; j3++) src[j3 - 1] = xch((it - 1) & 1, rank, (rank + j3) & (RC_CL - 1), warp);
+        // poll in the order the peers SEND: CTA s sends to s+1 first, so this CTA's first vectors come from rank-1 = rank+3
+        for (int j3 = 1; j3 < RC_CL; j3++) src[j3 - 1] = xch((it - 1) & 1, rank, (rank + RC_CL - j3) & (RC_CL - 1), warp);
         uint4 va[rc::LL_NV], vb[rc::LL_NV];
         auto issue = [&](uint4 (&v)[rc::LL_NV], const uint4* q) {
 #pragma unroll
@@ -784,7 +791,9 @@ lstm_fwd3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         if (ok) deliver(vc, s3);
         if (!ok) break;
         if (threadIdx.x == 0) RC_STAMP(11);
+#ifdef ARCVAE_RC_STAMPS
         if (p.dbg != nullptr && threadIdx.x == 0 && blockIdx.x < 4 && it < 64) p.dbg[(blockIdx.x * 64 + it) * 32 + 13] = rounds;
+#endif
         if (lane == 0) RC_STAMP(16 + warp);
         // next step's operands, under the MMAs (measured: issued BEFORE the polls they cost 1.4 us per step — the polls
         // queue behind 16 loads from HBM — and inside the gate math they throttle it)

@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""Per-step timelines (globaltimer ns) of the flag-in-data cluster recurrence kernels lstm_fwd3_kernel / lstm_bwd3_kernel
+"""(needs a stamp-enabled library: make -C mlx-vae_b200/csrc clean all STAMPS=1)
+Per-step timelines (globaltimer ns) of the flag-in-data cluster recurrence kernels lstm_fwd3_kernel / lstm_bwd3_kernel
 and launch times of the four recurrence launches (debug aid; the stamping thread itself runs ~1 us behind the other warps — read per-warp slots, not thread 0)."""
 import os, sys
 import numpy as np, torch
