@@ -60,7 +60,6 @@ struct RecParams {
   bf16* dAb;              // [T*B,4H] pre-activation gradients, bf16 (exchange + tape)
   uint4* xch;             // backward, K-split design: exchange buffers of the partial d h (lstm_cluster_xch_bytes)
   int* err_flag;
-  int flags;             // experiment switches (ARCVAE_RC_FLAGS)
   long long* dbg;        // optional: per-step clock64 stamps of CTA 0 (layout: [cta 4][it 64][slot 32])
 };
 
@@ -259,26 +258,22 @@ lstm_bwd3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
       bool ok = rc::wait_flag(&sh->w_ready, 0, failed);
       const uint32_t idesc = tc::make_idesc_bf16(RC_ROWS, 256, false, true);
       for (int it = 0; it + 1 < T && ok; it++) {
-        const bool nosplit = (p.flags & 1) != 0;   // experiment: issue all 16 MMAs after the second half
 #pragma unroll
         for (int half = 0; half < 2; half++) {
           // half 0: the units every epilogue thread finishes first (16-unit K blocks 0 and 2), half 1: blocks 1 and 3
-          if (half == 0 && nosplit) continue;
           ok = ok && rc::wait_flag(&sh->a_ready[half], it & 1, failed);
           if (!ok) break;
           if (half == 0) RC_STAMP(0); else RC_STAMP(1);
           tc::tc_fence_after();
-          for (int pass = (half == 1 && nosplit) ? 0 : half; pass <= half; pass++) {
 #pragma unroll
-            for (int g = 0; g < 4; g++) {
-              const uint32_t a_addr = tc::smem_u32(At + g * RC_STAGE_BYTES);
-              const uint32_t b_addr = tc::smem_u32(Wsm + g * 32768);
+          for (int g = 0; g < 4; g++) {
+            const uint32_t a_addr = tc::smem_u32(At + g * RC_STAGE_BYTES);
+            const uint32_t b_addr = tc::smem_u32(Wsm + g * 32768);
 #pragma unroll
-              for (int kk = 0; kk < 2; kk++) {
-                const int k = 2 * kk + pass;
-                tc::mma_bf16(tmem_base, tc::make_smem_desc(a_addr + 32 * k, 16, 1024),
-                             tc::make_smem_desc(b_addr + 2048 * k, 8192, 1024), idesc, (pass > 0 || g > 0 || kk > 0) ? 1u : 0u);
-              }
+            for (int kk = 0; kk < 2; kk++) {
+              const int k = 2 * kk + half;
+              tc::mma_bf16(tmem_base, tc::make_smem_desc(a_addr + 32 * k, 16, 1024),
+                           tc::make_smem_desc(b_addr + 2048 * k, 8192, 1024), idesc, (half > 0 || g > 0 || kk > 0) ? 1u : 0u);
             }
           }
           if (half == 0) RC_STAMP(3);
@@ -844,11 +839,6 @@ static int launch_cluster384(const void* fn, size_t smem, int B, const CUtensorM
   return 0;
 }
 
-static int rc_flags() {   // experiment switches of the profiling scripts (ARCVAE_RC_FLAGS; bit 0: issue all 16 backward MMAs at once)
-  static const int f = [] { const char* e = getenv("ARCVAE_RC_FLAGS"); return e ? atoi(e) : 0; }();
-  return f;
-}
-
 size_t lstm_cluster_xh_bytes(int B) { return (size_t)2 * cdiv(B, RC_ROWS) * RC_CL * 8 * rc::LL_NV * 32 * sizeof(uint4); }
 size_t lstm_cluster_xch_bytes(int B) { return (size_t)2 * cdiv(B, RC_ROWS) * RC_CL * RC_CL * 8 * rc::LL_NV * 32 * sizeof(uint4); }
 // coefficient tape of one layer (bf16 elements): T x tile-padded batch x 6 coefficients per hidden unit
@@ -870,7 +860,6 @@ int lstm_cluster_forward(int B, int T, int H, const bf16* Whb, const int32_t* xT
   p.xch = reinterpret_cast<uint4*>(xh);
   p.err_flag = err_flag;
   p.dbg = g_rc_dbg;
-  p.flags = rc_flags();
   const size_t smem = RC_W_BYTES + RC_CL * RC_STAGE_BYTES + sizeof(Fwd3Shared) + 1024;
   if (first_use_on_device(ONCE_FWD3))
     ARCVAE_CUDA(cudaFuncSetAttribute(lstm_fwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -890,7 +879,6 @@ int lstm_cluster_backward(int B, int T, int H, const bf16* Whb, const bf16* ktap
   p.dh_ext = dh_ext; p.dh_tf = dh_tf; p.dh_last = dh_last; p.dh_last_ld = dh_last_ld; p.dAb = dAb; p.err_flag = err_flag;
   p.xch = reinterpret_cast<uint4*>(xch);
   p.dbg = g_rc_dbg;
-  p.flags = rc_flags();
   const size_t smem = RC_W_BYTES + 4 * RC_STAGE_BYTES + sizeof(Bwd3Shared) + 1024;
   if (first_use_on_device(ONCE_BWD3))
     ARCVAE_CUDA(cudaFuncSetAttribute(lstm_bwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
