@@ -165,12 +165,93 @@ gemm_f32_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const
   }
 }
 
+// Small problems (the token-table products of layer 0 and their gradients: 80..1024 x 80..1024 x 80..1024).  With 128 x 128
+// tiles they occupy 1-8 CTAs that walk K serially with unpipelined loads: ~30 us each, seven of them per training step.
+// 32 x 64 tiles, BK = 32: 30-100 CTAs, 3-4 iterations each.  Same summation order per output element (sequential k).
+constexpr int SBM = 32, SBN = 64, SBK = 32;
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256)
+gemm_f32_small_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                      float* __restrict__ C, int ldc, const float* __restrict__ bias, int accumulate, RowMap rm, int kchunk) {
+  __shared__ float As[SBK][SBM + 1];
+  __shared__ __align__(16) float Bs[SBK][SBN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * SBM, n0 = blockIdx.x * SBN;
+  const int kbeg = blockIdx.z * kchunk;
+  const int kend = min(K, kbeg + kchunk);
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  for (int k0 = kbeg; k0 < kend; k0 += SBK) {
+#pragma unroll
+    for (int it = 0; it < SBM * SBK / 256; it++) {
+      const int idx = tid + it * 256;
+      const int r = TA ? (idx & (SBM - 1)) : (idx / SBK), kk = TA ? (idx / SBM) : (idx & (SBK - 1));
+      const int m = m0 + r, k = k0 + kk;
+      float v = 0.f;
+      if (m < M && k < kend) v = TA ? A[(long)k * lda + m] : A[rm(m) * (long)lda + k];
+      As[kk][r] = v;
+    }
+#pragma unroll
+    for (int it = 0; it < SBN * SBK / 256; it++) {
+      const int idx = tid + it * 256;
+      const int c = TB ? (idx / SBK) : (idx & (SBN - 1)), kk = TB ? (idx & (SBK - 1)) : (idx / SBN);
+      const int n = n0 + c, k = k0 + kk;
+      float v = 0.f;
+      if (n < N && k < kend) v = TB ? B[(long)n * ldb + k] : B[(long)k * ldb + n];
+      Bs[kk][c] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < SBK; kk++) {
+      const float a0 = As[kk][ty * 2], a1 = As[kk][ty * 2 + 1];
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      acc[0][0] = fmaf(a0, b.x, acc[0][0]); acc[0][1] = fmaf(a0, b.y, acc[0][1]);
+      acc[0][2] = fmaf(a0, b.z, acc[0][2]); acc[0][3] = fmaf(a0, b.w, acc[0][3]);
+      acc[1][0] = fmaf(a1, b.x, acc[1][0]); acc[1][1] = fmaf(a1, b.y, acc[1][1]);
+      acc[1][2] = fmaf(a1, b.z, acc[1][2]); acc[1][3] = fmaf(a1, b.w, acc[1][3]);
+    }
+    __syncthreads();
+  }
+  const bool split = gridDim.z > 1;
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    const int m = m0 + ty * 2 + i;
+    if (m >= M) continue;
+    float* crow = C + rm(m) * (long)ldc;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j];
+      if (bias != nullptr && blockIdx.z == 0) v += bias[n];
+      if (split) atomicAdd(crow + n, v);
+      else if (accumulate) crow[n] += v;
+      else crow[n] = v;
+    }
+  }
+}
+
 int gemm_f32(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
              int ldc, const float* bias, bool accumulate, RowMap rm, int splitk, cudaStream_t st) {
   if (M <= 0 || N <= 0) return 0;
   ARCVAE_REQUIRE(!(transA && rm.tlist != nullptr), "row map only with transA=0");
   ARCVAE_REQUIRE(splitk <= 1 || accumulate, "split-K needs accumulate semantics");
   if (splitk < 1) splitk = 1;
+  if ((long)cdiv(M, BM) * cdiv(N, BN) * splitk <= 16 && (long)M * N <= 1024 * 1024 && K <= 4096 && !(transA && transB)) {
+    // few 128 x 128 tiles: the small-tile kernel (more CTAs, short K loops); split K only where the caller allows atomics
+    int sk = 1;
+    if (accumulate && K >= 256) sk = K / 128 < 16 ? K / 128 : 16;
+    int kchunk = cdiv(cdiv(K, sk), SBK) * SBK;
+    sk = cdiv(K, kchunk);
+    dim3 grid(cdiv(N, SBN), cdiv(M, SBM), sk);
+    TimeScope ts(TIME_GEMM_F32, st);
+    const int acc = accumulate ? 1 : 0;
+    if (!transA && !transB) gemm_f32_small_kernel<false, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, acc, rm, kchunk);
+    else if (!transA) gemm_f32_small_kernel<false, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, acc, rm, kchunk);
+    else gemm_f32_small_kernel<true, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, acc, rm, kchunk);
+    ARCVAE_LAUNCHED();
+    return 0;
+  }
   int kchunk = cdiv(cdiv(K, splitk), BK) * BK;
   if (kchunk <= 0) kchunk = BK;
   splitk = cdiv(K, kchunk);
