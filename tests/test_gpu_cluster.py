@@ -43,8 +43,9 @@ def run_encoder(M, p, x, cond, prec, cluster, dmu=None, dlv=None):
         os.environ.pop("ARCVAE_NO_CLUSTER", None)
 
 
-@pytest.mark.parametrize("B,T", [(64, 1), (130, 3), (128, 2), (128, 9), (256, 24), (200, 16), (4096, 128)])
+@pytest.mark.parametrize("B,T", [(64, 1), (130, 3), (128, 2), (128, 9), (256, 24), (200, 16), (4096, 128), (8320, 12)])
 def test_cluster_matches_per_step_paths(M, B, T):
+    # (8320, 12): 65 row tiles = 260 CTAs > 148 SMs, i.e. several waves of clusters share the exchange buffers' layout
     cfg = O.Config()
     p = O.init_params(cfg, seed=3, dtype=torch.float32)
     x, cond, eps, _ = O.synthetic_batch(B, T, cfg, seed=B + T)
