@@ -53,7 +53,8 @@ struct __align__(8) SfShared {
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
   uint64_t out_full, out_empty;
-  uint64_t a_ready;
+  uint64_t a_ready;        // the one-hot tile of the step is written (8 arrivals)
+  uint64_t p_ready[8];     // K panel kp of the layer output being produced is complete (8 arrivals per production)
   uint32_t tmem_base;
 };
 
@@ -97,6 +98,7 @@ sampler_fused_kernel(const __grid_constant__ SfMaps maps, const SfParams p) {
     tc::mbar_init(&sh->out_full, 1);
     tc::mbar_init(&sh->out_empty, 8);
     tc::mbar_init(&sh->a_ready, 8);
+    for (int k = 0; k < 8; k++) tc::mbar_init(&sh->p_ready[k], 8);
     tc::fence_barrier_init();
     for (int l = 0; l < NL; l++) tc::prefetch_tmap(&maps.w[l]);
     tc::prefetch_tmap(&maps.wout);
@@ -139,13 +141,15 @@ sampler_fused_kernel(const __grid_constant__ SfMaps maps, const SfParams p) {
       const uint32_t idesc_g = tc::make_idesc_bf16(SF_ROWS, SF_BN, false, false);
       const uint32_t idesc_o = tc::make_idesc_bf16(SF_ROWS, p.VN, false, false);
       int stage = 0;
-      uint32_t phase = 0, acc_it = 0, out_it = 0, ar = 0;
+      uint32_t phase = 0, acc_it = 0, out_it = 0, ar = 0, cons = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int t = 0; t < T; t++) {
           for (int l = 0; l < NL; l++) {
-            tc::mbar_wait(&sh->a_ready, ar & 1);
-            ar++;
-            tc::tc_fence_after();
+            if (l == 0) {
+              tc::mbar_wait(&sh->a_ready, ar & 1);
+              ar++;
+              tc::tc_fence_after();
+            }
             const uint8_t* A = (l == 0) ? hB : ((l & 1) ? hA : hB);   // layer l reads the output tile of layer l-1
             const int kpn = (l == 0) ? VP : KP;
             for (int j = 0; j < KP; j++) {
@@ -154,6 +158,12 @@ sampler_fused_kernel(const __grid_constant__ SfMaps maps, const SfParams p) {
               tc::tc_fence_after();
               const uint32_t d_tmem = tmem_base + acc * SF_BN;
               for (int kp = 0; kp < kpn; kp++) {
+                if (l > 0 && j == 0) {
+                  // K panel kp of this layer's input = block kp of the previous layer's output: start as soon as THAT
+                  // block's cell math is done (the first block of a layer overlaps the last blocks of the layer below)
+                  tc::mbar_wait(&sh->p_ready[kp], cons & 1);
+                  tc::tc_fence_after();
+                }
                 tc::mbar_wait(&sh->full[stage], phase);
                 tc::tc_fence_after();
                 const int ks = (l == 0) ? min(4, VKS - 4 * kp) : 4;
@@ -167,16 +177,16 @@ sampler_fused_kernel(const __grid_constant__ SfMaps maps, const SfParams p) {
               }
               tc::mma_commit(&sh->acc_full[acc]);
               acc_it++;
+              if (l > 0 && j == 0) cons++;
             }
           }
-          // fc_out on the top layer's tile
-          tc::mbar_wait(&sh->a_ready, ar & 1);
-          ar++;
-          tc::tc_fence_after();
+          // fc_out on the top layer's tile, panel by panel as the top layer's blocks complete
           const uint8_t* A = ((NL - 1) & 1) ? hB : hA;
           tc::mbar_wait(&sh->out_empty, (out_it & 1) ^ 1);
           tc::tc_fence_after();
           for (int kp = 0; kp < KP; kp++) {
+            tc::mbar_wait(&sh->p_ready[kp], cons & 1);
+            tc::tc_fence_after();
             tc::mbar_wait(&sh->full[stage], phase);
             tc::tc_fence_after();
             const uint32_t a_addr = tc::smem_u32(A + (size_t)kp * SF_PANEL);
@@ -190,6 +200,7 @@ sampler_fused_kernel(const __grid_constant__ SfMaps maps, const SfParams p) {
           }
           tc::mma_commit(&sh->out_full);
           out_it++;
+          cons++;
         }
       }
     }
@@ -283,14 +294,14 @@ sampler_fused_kernel(const __grid_constant__ SfMaps maps, const SfParams p) {
             if (l > 0 && j + 1 < KP) load_bias(bl, nb + SF_BN, a0);
             cell16(taddr, hs * 32 + 16, a1, drow);
             tc::tc_fence_before();
+            tc::fence_proxy_async();         // this block = K panel j of the next product: generic-proxy writes -> async proxy
             __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&sh->acc_empty[acc]);
+            if (lane == 0) {
+              tc::mbar_arrive(&sh->acc_empty[acc]);
+              tc::mbar_arrive(&sh->p_ready[j]);
+            }
             acc_it++;
           }
-          // h_l tile complete: generic-proxy smem writes -> visible to the tensor core (async proxy), then signal
-          tc::fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) tc::mbar_arrive(&sh->a_ready);
         }
         // ---- selection (decoder_sampling.py:110-123): thread per row, hs == 0 warps
         tc::mbar_wait(&sh->out_full, out_it & 1);
