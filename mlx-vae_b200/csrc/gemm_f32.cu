@@ -237,7 +237,7 @@ int gemm_f32(int transA, int transB, int M, int N, int K, const float* A, int ld
   ARCVAE_REQUIRE(!(transA && rm.tlist != nullptr), "row map only with transA=0");
   ARCVAE_REQUIRE(splitk <= 1 || accumulate, "split-K needs accumulate semantics");
   if (splitk < 1) splitk = 1;
-  if ((long)cdiv(M, BM) * cdiv(N, BN) * splitk <= 16 && (long)M * N <= 1024 * 1024 && K <= 4096 && !(transA && transB)) {
+  if ((long)cdiv(M, BM) * cdiv(N, BN) <= 16 && (long)M * N <= 1024 * 1024 && K <= 8192 && !(transA && transB)) {
     // few 128 x 128 tiles: the small-tile kernel (more CTAs, short K loops); split K only where the caller allows atomics
     int sk = 1;
     if (accumulate && K >= 256) sk = K / 128 < 16 ? K / 128 : 16;
