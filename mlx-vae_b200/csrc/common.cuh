@@ -48,7 +48,7 @@ extern std::atomic<uint64_t> g_launches;
 // ---- per-device one-time state (the library is usable from several devices of one process) ----------------------
 // true exactly once per (slot, current device): guards cudaFuncSetAttribute calls and other per-device set-up
 enum { ONCE_GEMM_TC = 0, ONCE_CELL0, ONCE_SCATTER_F32, ONCE_SCATTER_BF16, ONCE_SAMPLER,
-       ONCE_GEMM_WS, ONCE_FWD3, ONCE_BWD3, ONCE_NSLOTS = 16 };
+       ONCE_GEMM_WS, ONCE_FWD3, ONCE_BWD3, ONCE_CELL0B, ONCE_NSLOTS = 16 };
 bool first_use_on_device(int slot);
 int device_sm_count();            // multiprocessors of the current device (cached per device)
 // STICKY per-device error flag raised by the bounded waits of the persistent kernels; the library never clears it except

@@ -112,7 +112,7 @@ static size_t dec_tape_layout(const arcvae_dims& d, int B, int T, void* base, si
   tt.tlists = a.take<int>((size_t)2 * T + 2);
   tt.mask = a.take<uint8_t>((size_t)T + 16);
   for (int l = 0; l < d.NL; l++) tt.hdb[l] = a.take<__nv_bfloat16>(R * d.H);
-  for (int l = 0; l < d.NL; l++) tt.gates_b[l] = a.take<__nv_bfloat16>(R * 3 * d.H);   // layer 0 too: no recompute in backward
+  for (int l = 0; l < d.NL; l++) tt.gates_b[l] = a.take<__nv_bfloat16>(R * 3 * d.H);   // layer 0: unused when its gates are recomputed
   tt.dlb = a.take<__nv_bfloat16>(R * (size_t)((d.V + 7) / 8 * 8));
   tt.xT = a.take<int32_t>(R);
   tt.fb = a.take<uint8_t>((size_t)T + 16);
@@ -199,7 +199,7 @@ static int dec_stack_forward(const arcvae_dims& d, const arcvae_decoder_params* 
   const int H = d.H, H3 = 3 * d.H;
   const bool bf = precision == ARCVAE_PREC_BF16;
   ARCVAE_TRY(dec_cell0_fwd(pr.table, pr.wc, in_tok, cond, B, d.C, H, d.V, nrows, rm, fused ? nullptr : hd[0],
-                           bf ? hdb[0] : nullptr, fused ? gates_b[0] : nullptr, st));
+                           bf ? hdb[0] : nullptr, (fused && !dec_cell0_recompute_ok(H, d.V, d.C)) ? gates_b[0] : nullptr, st));
   for (int l = 1; l < d.NL; l++) {
     if (fused) {
       // GEMM + zero-state cell in the epilogue: h_{l-1} @ Wxp_l^T + bp_l -> (i,g,o) -> h_l ; gates saved as bf16
@@ -414,7 +414,15 @@ extern "C" int arcvae_decoder_backward(const arcvae_dims* d, const arcvae_decode
       q.A = A; q.lda = lda; q.a_mn = false;
       q.B = Bw; q.ldb = H; q.b_mn = true;                       // B[k*H + n]: row-major [K,H]
       q.accumulate = false; q.splitk = 1; q.rm = id; q.a_rows_total = R; q.Hh = H; q.dg_out = out;
-      q.epi = TC_EPI_DEC_CELL_BWD; q.gates_b = tp.gates_b[layer_below];      // layer 0 keeps its gate tape as well
+      if (layer_below == 0 && dec_cell0_recompute_ok(H, V, C)) {
+        // layer 0 has no gate tape: plain GEMM to bf16 d h_0 (in the idle fp32 d h scratch), then the cell reverse with
+        // the gates recomputed from the token table
+        __nv_bfloat16* dh0b = reinterpret_cast<__nv_bfloat16*>(sc.dh[0]);
+        q.Cb = dh0b; q.ldcb = H; q.dg_out = nullptr; q.epi = TC_EPI_PLAIN;
+        ARCVAE_TRY(gemm_tc(q, st));
+        return dec_cell0_bwd_recompute(tp.prep.table, tp.prep.wc, tp.in_tok, cond, B, C, H, V, R, dh0b, out, st);
+      }
+      q.epi = TC_EPI_DEC_CELL_BWD; q.gates_b = tp.gates_b[layer_below];
       return gemm_tc(q, st);
     };
     // one-hot of the fed tokens (+ cond hi/lo columns): operand of the layer-0 table scatter and, through its row sums,

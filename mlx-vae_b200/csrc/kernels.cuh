@@ -32,6 +32,10 @@ int gather_rows_bf16(const __nv_bfloat16* table, const int32_t* tok, long R, int
 // layer 0: a = table[tok[r]] + cond[r % B] @ wc^T   (table [V,3H], wc [3H,C]); rows r = rm(i), i < R
 // gates_b (optional, fused bf16 path): activated (i,g,o) in the tile-permuted layout of the fused GEMM epilogues
 // V = rows of the table (sizes the shared-memory copy of the large-batch bf16 kernel)
+// layer-0 decoder cell reverse with the gates recomputed from the token table (no gate tape); see pointwise.cu
+bool dec_cell0_recompute_ok(int H, int V, int C);
+int dec_cell0_bwd_recompute(const float* table, const float* wc, const int32_t* tok, const float* cond, int B, int C, int H, int V,
+                            long R, const __nv_bfloat16* dhb, __nv_bfloat16* dg_out, cudaStream_t st);
 int dec_cell0_fwd(const float* table, const float* wc, const int32_t* tok, const float* cond, int B, int C, int H, int V,
                   int R, RowMap rm, float* h, __nv_bfloat16* hb, __nv_bfloat16* gates_b, cudaStream_t st);
 // layers >= 1: G [.,3H] pre-activation -> activated in place; h out

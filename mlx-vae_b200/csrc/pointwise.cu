@@ -1,5 +1,7 @@
 // pointwise.cu — element-wise / gather / scatter / reduction kernels of the AR-CVAE step.
 // All are HBM-bound: coalesced along the hidden/gate axis, grid-stride loops sized to the 148 SMs.
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace arcvae {
@@ -409,6 +411,139 @@ k_dec_cell0_fwd_smem(const float* __restrict__ table, const float* __restrict__ 
     for (int k = 0; k < 4; k++) po[k] = __floats2bfloat162_rn(hv[2 * k], hv[2 * k + 1]);
     *reinterpret_cast<uint4*>(hb + r * H + j) = o;
   }
+}
+
+// Reverse of the layer-0 decoder cell WITHOUT a gate tape: the gates are a function of (token, cond) only, so they are
+// recomputed from the same shared-memory table the forward kernel uses (4 MUFU per unit) instead of being written
+// (0.8 GB) by the forward pass and read back (0.8 GB) by the d h GEMM's epilogue.  In: dhb [R,H] bf16 (d h_0 from the plain
+// GEMM dG_1 @ Wx_1); out: dG_0 [R,3H] bf16 in the tile-permuted compact layout the table scatter expects.
+__global__ void __launch_bounds__(768, 1)
+k_dec_cell0_bwd_smem(const float* __restrict__ table, const float* __restrict__ wc, const int32_t* __restrict__ tok,
+                     const float* __restrict__ cond, int B, int C, int H, int V, long R,
+                     const __nv_bfloat16* __restrict__ dhb, __nv_bfloat16* __restrict__ dg_out) {
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  __nv_bfloat16* tb = reinterpret_cast<__nv_bfloat16*>(sm_raw);                       // [V,3H]
+  float* wcs = reinterpret_cast<float*>(sm_raw + (size_t)V * 3 * H * sizeof(__nv_bfloat16));   // [3H,C]
+  const int H3 = 3 * H;
+  for (int i = threadIdx.x; i < V * H3 / 2; i += blockDim.x) {
+    const float2 v = reinterpret_cast<const float2*>(table)[i];
+    reinterpret_cast<__nv_bfloat162*>(tb)[i] = __floats2bfloat162_rn(v.x, v.y);
+  }
+  for (int i = threadIdx.x; i < H3 * C; i += blockDim.x) wcs[i] = wc[i];
+  __syncthreads();
+  const int cpr = H >> 3;
+  const long total = R * cpr;
+  const long stride = (long)gridDim.x * blockDim.x;
+  long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  // the grid stride is a multiple of the chunks per row, so a thread always owns the SAME 8 hidden units: its 24 cond
+  // weights live in registers (C == 1; from shared memory they are an 8-way bank conflict per item)
+  const bool wreg_ok = (C == 1) && (stride % cpr) == 0;
+  float wreg[3][8];
+  if (wreg_ok && idx < total) {
+    const int j0 = (int)(idx % cpr) << 3;
+#pragma unroll
+    for (int g = 0; g < 3; g++)
+#pragma unroll
+      for (int k = 0; k < 8; k++) wreg[g][k] = wcs[g * H + j0 + k];
+  }
+  long r_n = 0;
+  int tok_n = 0, j_n = 0;
+  float c0_n = 0.f;
+  uint4 dh_n = make_uint4(0, 0, 0, 0);
+  if (idx < total) {
+    r_n = idx / cpr;
+    j_n = (int)(idx - r_n * cpr) << 3;
+    tok_n = __ldg(tok + r_n);
+    c0_n = __ldg(cond + (r_n % B) * C);
+    dh_n = __ldcs(reinterpret_cast<const uint4*>(dhb + r_n * H + j_n));
+  }
+  for (; idx < total; idx += stride) {
+    const long r = r_n;
+    const int j = j_n, tokv = tok_n;
+    const uint4 dhv = dh_n;
+    const float cond0 = c0_n;
+    if (idx + stride < total) {                  // next item's dependent loads under this item's math
+      const long nidx = idx + stride;
+      r_n = nidx / cpr;
+      j_n = (int)(nidx - r_n * cpr) << 3;
+      tok_n = __ldg(tok + r_n);
+      c0_n = __ldg(cond + (r_n % B) * C);
+      dh_n = __ldcs(reinterpret_cast<const uint4*>(dhb + r_n * H + j_n));
+    }
+    const __nv_bfloat16* trow = tb + (long)tokv * H3 + j;
+    float a[3][8];
+#pragma unroll
+    for (int g = 0; g < 3; g++) {
+      const uint4 v = *reinterpret_cast<const uint4*>(trow + g * H);
+      const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const float2 t = __bfloat1622float2(pv[k]);
+        a[g][2 * k] = t.x; a[g][2 * k + 1] = t.y;
+      }
+    }
+    if (wreg_ok) {
+#pragma unroll
+      for (int g = 0; g < 3; g++)
+#pragma unroll
+        for (int k = 0; k < 8; k++) a[g][k] = fmaf(cond0, wreg[g][k], a[g][k]);
+    } else {
+      const float* crow = cond + (r % B) * C;
+      for (int c = 0; c < C; c++) {
+        const float cv = (c == 0) ? cond0 : __ldg(crow + c);
+#pragma unroll
+        for (int g = 0; g < 3; g++)
+#pragma unroll
+          for (int k = 0; k < 8; k++) a[g][k] = fmaf(cv, wcs[(g * H + j + k) * C + c], a[g][k]);
+      }
+    }
+    float dh[8];
+    {
+      const __nv_bfloat162* pd = reinterpret_cast<const __nv_bfloat162*>(&dhv);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const float2 t = __bfloat1622float2(pd[k]);
+        dh[2 * k] = t.x; dh[2 * k + 1] = t.y;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const float i_ = sigmoid_approx_(a[0][k]), g_ = tanh_approx_(a[1][k]), o_ = sigmoid_approx_(a[2][k]);
+      const float tcv = tanh_approx_(i_ * g_);
+      const float dcc = dh[k] * o_ * (1.f - tcv * tcv);
+      a[2][k] = dh[k] * tcv * o_ * (1.f - o_);
+      a[0][k] = dcc * g_ * i_ * (1.f - i_);
+      a[1][k] = dcc * i_ * (1.f - g_ * g_);
+    }
+    __nv_bfloat16* gb = dg_out + r * 3L * H + (j >> 6) * 192 + (j & 63);
+#pragma unroll
+    for (int g = 0; g < 3; g++) {
+      uint4 o;
+      __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+      for (int k = 0; k < 4; k++) po[k] = __floats2bfloat162_rn(a[g][2 * k], a[g][2 * k + 1]);
+      *reinterpret_cast<uint4*>(gb + g * 64) = o;
+    }
+  }
+}
+bool dec_cell0_recompute_ok(int H, int V, int C) {
+  return (H % 64) == 0 && V > 0 && (size_t)V * 3 * H * sizeof(__nv_bfloat16) + (size_t)3 * H * C * sizeof(float) <= 200 * 1024 &&
+         std::getenv("ARCVAE_NO_CELL0_RECOMPUTE") == nullptr;
+}
+int dec_cell0_bwd_recompute(const float* table, const float* wc, const int32_t* tok, const float* cond, int B, int C, int H, int V,
+                            long R, const __nv_bfloat16* dhb, __nv_bfloat16* dg_out, cudaStream_t st) {
+  if (R <= 0) return 0;
+  ARCVAE_REQUIRE(dec_cell0_recompute_ok(H, V, C), "layer-0 cell recompute: table must fit shared memory");
+  TimeScope ts(TIME_POINTWISE, st);
+  const size_t smem_tab = (size_t)V * 3 * H * sizeof(__nv_bfloat16) + (size_t)3 * H * C * sizeof(float);
+  if (first_use_on_device(ONCE_CELL0B))
+    ARCVAE_CUDA(cudaFuncSetAttribute(k_dec_cell0_bwd_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  const long items = R * (H >> 3);
+  int grid = (int)((items + 767) / 768);
+  if (grid > 148) grid = 148;
+  k_dec_cell0_bwd_smem<<<grid, 768, smem_tab, st>>>(table, wc, tok, cond, B, C, H, V, R, dhb, dg_out);
+  ARCVAE_LAUNCHED();
+  return 0;
 }
 
 int dec_cell0_fwd(const float* table, const float* wc, const int32_t* tok, const float* cond, int B, int C, int H, int V,
