@@ -232,3 +232,42 @@ def test_fused_cross_entropy_epilogue_equals_unfused_path(M, B, T, tf):
         worst = max(worst, float((ga[n] - gb[n]).abs().max()) / s)
     print(f"fused CE epilogue B={B} T={T} tf={tf}: worst gradient difference to the unfused path {worst:.2e}; launches {na} vs {nb}")
     assert worst < 2e-3
+
+
+@pytest.mark.parametrize("B,T,tf", [(256, 24, 0.7), (130, 9, 0.0)])
+def test_layer0_cell_recompute_equals_gate_tape_path(M, B, T, tf):
+    """Decoder layer 0 keeps no gate tape: the reverse pass recomputes the gates from (token, cond) through the same
+    shared-memory table as the forward kernel (csrc/pointwise.cu k_dec_cell0_bwd_smem) and takes d h_0 from a plain GEMM in
+    bf16.  ARCVAE_NO_CELL0_RECOMPUTE=1 restores the tape path (gates stored in bf16, cell reverse in the GEMM epilogue on the
+    fp32 accumulator): identical forward, gradients equal up to the bf16 rounding of d h_0 / of the stored gates."""
+    import os
+    cfg = O.Config()
+    x, cond, eps, tf_mask = O.synthetic_batch(B, T, cfg, seed=B + T, tf_ratio=tf)
+    p = O.init_params(cfg, seed=23, dtype=torch.float32)
+    p["decoder"] = O.tree_map(lambda t: t * 4.0, p["decoder"])
+    kw = model_kwargs(cfg)
+    hyper = dict(beta=0.05, lambda_prop=0.1, lambda_collapse=0.001, free_bits=1.0, lambda_mi=0.01, target_mi=4.85)
+    res = {}
+    for tag in ("recompute", "tape"):
+        if tag == "tape":
+            os.environ["ARCVAE_NO_CELL0_RECOMPUTE"] = "1"
+        try:
+            enc = M.MLXEncoder(**kw, precision="bf16").load_parameters(p["encoder"])
+            dec = M.MLXAutoregressiveDecoder(**kw, precision="bf16").load_parameters(p["decoder"])
+            d, (ge, gd) = M.loss_and_grad(enc, dec, None, cuda(x), cuda(cond), eps=cuda(eps), tf_mask=tf_mask, **hyper)
+            torch.cuda.synchronize()
+            res[tag] = ({k: float(d[k]) for k in M._lib.LOSS_KEYS}, {k: v.clone() for k, v in O.tree_flatten(gd).items()})
+        finally:
+            os.environ.pop("ARCVAE_NO_CELL0_RECOMPUTE", None)
+    (la, ga), (lb, gb) = res["recompute"], res["tape"]
+    for k in la:
+        assert abs(la[k] - lb[k]) <= 2e-6 * max(1.0, abs(lb[k])), (k, la[k], lb[k])
+    worst = 0.0
+    for n in ga:
+        s = float(gb[n].abs().max())
+        if s == 0.0:
+            assert float(ga[n].abs().max()) == 0.0, n
+            continue
+        worst = max(worst, float((ga[n] - gb[n]).abs().max()) / s)
+    print(f"layer-0 recompute B={B} T={T} tf={tf}: worst decoder gradient difference to the gate-tape path {worst:.2e}")
+    assert worst < 1e-2
