@@ -341,12 +341,19 @@ k_dec_cell0_fwd_smem(const float* __restrict__ table, const float* __restrict__ 
   long r_n = 0;
   int tok_n = 0, j_n = 0;
   float c0_n = 0.f;
+  // 32-bit index arithmetic (R * H / 8 < 2^31, checked by the launcher): the 64-bit divisions and the 64-bit `r % B` of the
+  // first version were a large part of the instruction stream of a kernel that is not memory-bound
+  auto split = [&](long id, int& i, int& j) {
+    const unsigned u = (unsigned)id;
+    i = (int)(u / (unsigned)cpr);
+    j = (int)(u - (unsigned)i * (unsigned)cpr) << 3;
+  };
   if (idx < total) {
-    const int i = (int)(idx / cpr);
-    j_n = (int)(idx - (long)i * cpr) << 3;
+    int i;
+    split(idx, i, j_n);
     r_n = rm(i);
     tok_n = __ldg(tok + r_n);
-    c0_n = __ldg(cond + (r_n % B) * C);
+    c0_n = __ldg(cond + (long)((unsigned)r_n % (unsigned)B) * C);
   }
   for (; idx < total; idx += stride) {
     const long r = r_n;
@@ -354,12 +361,11 @@ k_dec_cell0_fwd_smem(const float* __restrict__ table, const float* __restrict__ 
     const int tokv = tok_n;
     const float cond0 = c0_n;
     if (idx + stride < total) {
-      const long nidx = idx + stride;
-      const int i = (int)(nidx / cpr);
-      j_n = (int)(nidx - (long)i * cpr) << 3;
+      int i;
+      split(idx + stride, i, j_n);
       r_n = rm(i);
       tok_n = __ldg(tok + r_n);
-      c0_n = __ldg(cond + (r_n % B) * C);
+      c0_n = __ldg(cond + (long)((unsigned)r_n % (unsigned)B) * C);
     }
     const __nv_bfloat16* trow = tb + (long)tokv * H3 + j;
     float a[3][8];
@@ -379,7 +385,7 @@ k_dec_cell0_fwd_smem(const float* __restrict__ table, const float* __restrict__ 
 #pragma unroll
         for (int k = 0; k < 8; k++) a[g][k] = fmaf(cond0, wreg[g][k], a[g][k]);
     } else {
-      const float* crow = cond + (r % B) * C;
+      const float* crow = cond + (long)((unsigned)r % (unsigned)B) * C;
       for (int c = 0; c < C; c++) {
         const float cv = (c == 0) ? cond0 : __ldg(crow + c);
 #pragma unroll
@@ -450,11 +456,16 @@ k_dec_cell0_bwd_smem(const float* __restrict__ table, const float* __restrict__ 
   int tok_n = 0, j_n = 0;
   float c0_n = 0.f;
   uint4 dh_n = make_uint4(0, 0, 0, 0);
+  auto split = [&](long id, long& r, int& j) {        // 32-bit index arithmetic (R * H / 8 < 2^31, checked by the launcher)
+    const unsigned u = (unsigned)id;
+    const unsigned i = u / (unsigned)cpr;
+    r = (long)i;
+    j = (int)(u - i * (unsigned)cpr) << 3;
+  };
   if (idx < total) {
-    r_n = idx / cpr;
-    j_n = (int)(idx - r_n * cpr) << 3;
+    split(idx, r_n, j_n);
     tok_n = __ldg(tok + r_n);
-    c0_n = __ldg(cond + (r_n % B) * C);
+    c0_n = __ldg(cond + (long)((unsigned)r_n % (unsigned)B) * C);
     dh_n = __ldcs(reinterpret_cast<const uint4*>(dhb + r_n * H + j_n));
   }
   for (; idx < total; idx += stride) {
@@ -463,11 +474,9 @@ k_dec_cell0_bwd_smem(const float* __restrict__ table, const float* __restrict__ 
     const uint4 dhv = dh_n;
     const float cond0 = c0_n;
     if (idx + stride < total) {                  // next item's dependent loads under this item's math
-      const long nidx = idx + stride;
-      r_n = nidx / cpr;
-      j_n = (int)(nidx - r_n * cpr) << 3;
+      split(idx + stride, r_n, j_n);
       tok_n = __ldg(tok + r_n);
-      c0_n = __ldg(cond + (r_n % B) * C);
+      c0_n = __ldg(cond + (long)((unsigned)r_n % (unsigned)B) * C);
       dh_n = __ldcs(reinterpret_cast<const uint4*>(dhb + r_n * H + j_n));
     }
     const __nv_bfloat16* trow = tb + (long)tokv * H3 + j;
@@ -488,7 +497,7 @@ k_dec_cell0_bwd_smem(const float* __restrict__ table, const float* __restrict__ 
 #pragma unroll
         for (int k = 0; k < 8; k++) a[g][k] = fmaf(cond0, wreg[g][k], a[g][k]);
     } else {
-      const float* crow = cond + (r % B) * C;
+      const float* crow = cond + (long)((unsigned)r % (unsigned)B) * C;
       for (int c = 0; c < C; c++) {
         const float cv = (c == 0) ? cond0 : __ldg(crow + c);
 #pragma unroll
@@ -534,6 +543,7 @@ int dec_cell0_bwd_recompute(const float* table, const float* wc, const int32_t* 
                             long R, const __nv_bfloat16* dhb, __nv_bfloat16* dg_out, cudaStream_t st) {
   if (R <= 0) return 0;
   ARCVAE_REQUIRE(dec_cell0_recompute_ok(H, V, C), "layer-0 cell recompute: table must fit shared memory");
+  ARCVAE_REQUIRE(R * (H >> 3) < (1L << 31) && R < (1L << 31), "layer-0 cell recompute: 32-bit item index");
   TimeScope ts(TIME_POINTWISE, st);
   const size_t smem_tab = (size_t)V * 3 * H * sizeof(__nv_bfloat16) + (size_t)3 * H * C * sizeof(float);
   if (first_use_on_device(ONCE_CELL0B))
@@ -552,7 +562,8 @@ int dec_cell0_fwd(const float* table, const float* wc, const int32_t* tok, const
   TimeScope ts(TIME_POINTWISE, st);
   ARCVAE_REQUIRE(gates_b == nullptr || (h == nullptr && (H % 64) == 0), "layer-0 gate tape: fused bf16 path, H % 64 == 0");
   const size_t smem_tab = (size_t)V * 3 * H * sizeof(__nv_bfloat16) + (size_t)3 * H * C * sizeof(float);
-  if (h == nullptr && hb != nullptr && (H & 7) == 0 && V > 0 && smem_tab <= 200 * 1024 && (long)R * H >= (1L << 24)) {
+  if (h == nullptr && hb != nullptr && (H & 7) == 0 && V > 0 && smem_tab <= 200 * 1024 && (long)R * H >= (1L << 24) &&
+      (long)R * (H >> 3) < (1L << 31)) {
     if (first_use_on_device(ONCE_CELL0))
       ARCVAE_CUDA(cudaFuncSetAttribute(k_dec_cell0_fwd_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     k_dec_cell0_fwd_smem<<<148, 768, smem_tab, st>>>(table, wc, tok, cond, B, C, H, V, R, rm, hb, gates_b);
