@@ -8,7 +8,8 @@
 // Execution paths, same math:
 //   ARCVAE_PREC_FP32              per-step fp32 FFMA GEMM + cell kernels (reference precision)
 //   ARCVAE_PREC_BF16, H == 256    persistent cluster kernel per layer and direction (lstm_cluster.cu): W_hh resident in
-//                                 shared memory for all T steps, bf16 tape (gates, h, dA), fp32 cell state
+//                                 shared memory for all T steps, bf16 tapes (cell-reverse coefficients, h, dA), cell
+//                                 state in registers, flag-in-data exchange between the cluster's CTAs
 //   ARCVAE_PREC_BF16, H % 64 == 0 (e.g. the scaled config, H = 1024: W_hh = 8 MB bf16 does not fit any cluster's shared
 //                                 memory) ONE launch per timestep: tcgen05 GEMM h_{t-1} @ Wh^T with the whole LSTM cell in
 //                                 its epilogue (gemm_tc.cu TC_EPI_LSTM_FWD); W_hh split over the N tiles of the grid

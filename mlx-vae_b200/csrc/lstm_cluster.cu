@@ -132,14 +132,16 @@ __device__ __forceinline__ bool wait_flag(uint64_t* bar, uint32_t parity, volati
 constexpr int RC_THREADS2 = 384;   // 3 full warpgroups: setmaxnreg is a warpgroup-wide operation (warps 10, 11 only donate registers)
 
 // =====================================================================================================================
-// Third design: FLAG-IN-DATA exchange ("LL": every 16-byte vector that crosses CTAs carries 12 bytes of payload and a
-// 4-byte step flag).  The second design signals with cluster-scope mbarriers: the producer must wait until its stores
+// FLAG-IN-DATA exchange ("LL": every 16-byte vector that crosses CTAs carries 12 bytes of payload and a 4-byte step
+// flag).  The previous generation (profiles/micro/lstm_rec_gen2_kernels.cu.txt) signalled with cluster-scope mbarriers: the producer must wait until its stores
 // are acknowledged (TMA store completion 1.3 us forward, fence.acq_rel.cluster 0.8 us backward), then signal, then the
 // consumer starts its own L2 round trip (multicast load 0.5 us / 12 loads 0.8 us) — three serialized L2 latencies plus
 // the skew of waiting for the slowest of 24 remote warps.  Here the consumer THREAD polls the very vectors it needs
 // (ld.relaxed.gpu, L2) until their flags show the current step: one store latency + one load latency, no fence, no
-// remote arrive, and thread-granular instead of CTA-granular waiting.  A 16-byte aligned vector store is a single L2
-// transaction, so payload and flag become visible together.  Buffers are double-buffered by step parity; the
+// remote arrive, and thread-granular instead of CTA-granular waiting.  ASSUMPTION: a 16-byte aligned vector store / load
+// of one thread is a single L2 transaction on sm_100, so payload and flag become visible together (PTX only promises
+// per-element atomicity; ptxas must not split the accesses — see ll_send16 — and
+// tests/test_gpu_cluster.py::test_cluster_recurrence_is_deterministic fails on any tearing).  Buffers are double-buffered by step parity; the
 // dependency chain of the recurrence itself guarantees that a slot has been consumed before it is rewritten two steps
 // later (a producer's step t+2 needs every peer's step t+1, which needed this producer's step t in full).  Every
 // producer zeroes its outbound slots before the initial cluster barrier, so stale flags of an earlier launch can never
