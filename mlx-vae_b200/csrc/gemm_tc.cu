@@ -52,6 +52,8 @@ struct TcParams {
   int nseg; int segN[3]; int seg_shift[3]; float* segC[3]; int seg_ldc[3];
   int bm2;           // 256-row tiles (two M=128 MMAs share every B tile): halves the B re-reads of the long-K weight-gradient shapes
   int lp_B;          // TC_EPI_LSTM_DH: rows per timestep of the thread-friendly output
+  int fs;            // two-segment weight gradients in ONE CTA: the A tile is loaded once and multiplied with both B segments
+                     // (accumulators side by side in TMEM); see the host side for why
   int use_scratch;   // per-warp transposition scratch present after the TcShared block
   int scr_pitch;     // bytes per scratch row
 };
@@ -298,7 +300,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int kblocks = (p.K + TC_BK - 1) / TC_BK;
   uint32_t tmem_cols = 32;
   while (tmem_cols < 2u * (uint32_t)p.BN) tmem_cols <<= 1;
-  if (p.bm2) tmem_cols = 512;                              // two 256-column accumulators, one per row half
+  if (p.bm2 || p.fs) tmem_cols = 512;                      // two 256-column accumulators, one per row half / per-segment accumulators
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmA);
@@ -338,7 +340,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc::mbar_wait(&sh->empty[stage], phase ^ 1);
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
           uint8_t* sb = sa + a_bytes;
-          const int bn_t = p.nseg > 1 ? p.segN[ni] : p.BN;
+          const int bn_t = p.fs ? p.segN[0] + p.segN[1] : (p.nseg > 1 ? p.segN[ni] : p.BN);
           tc::mbar_expect_tx(&sh->full[stage], a_bytes + (uint32_t)bn_t * TC_BK * 2);
           const int k0 = kb * TC_BK;
           if (!p.a_mn) {
@@ -350,6 +352,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (!p.b_mn) {
             tc::tma_load_2d(sb, &tmB, &sh->full[stage], k0, n0);                        // box {64 k, BN rows}
+          } else if (p.fs) {
+            for (int j = 0; j < p.segN[0] / 64; j++)
+              tc::tma_load_2d(sb + j * 8192, &tmB, &sh->full[stage], j * 64, k0 - p.seg_shift[0]);
+            for (int j = 0; j < p.segN[1] / 64; j++)
+              tc::tma_load_2d(sb + (p.segN[0] / 64 + j) * 8192, &tmB1, &sh->full[stage], j * 64, k0 - p.seg_shift[1]);
           } else if (p.nseg > 1) {
             const CUtensorMap* tb = ni == 0 ? &tmB : (ni == 1 ? &tmB1 : &tmB2);
             for (int j = 0; j < bn_t / 64; j++)
@@ -368,12 +375,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t phase = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
-      const uint32_t idesc = tc::make_idesc_bf16(TC_BM, p.nseg > 1 ? p.segN[tile % p.nt] : p.BN, p.a_mn != 0, p.b_mn != 0);
+      const uint32_t idesc = tc::make_idesc_bf16(TC_BM, p.fs ? p.segN[0] : (p.nseg > 1 ? p.segN[tile % p.nt] : p.BN), p.a_mn != 0, p.b_mn != 0);
+      const uint32_t idesc1 = tc::make_idesc_bf16(TC_BM, p.fs ? p.segN[1] : 64, p.a_mn != 0, p.b_mn != 0);
       const int ks = tile / (p.mt * p.nt);
       const int kb0 = ks * p.kb_per;
       const int kb1 = min(kblocks, kb0 + p.kb_per);
-      const int acc = p.bm2 ? 0 : (it & 1);                  // 256-row tiles own all of TMEM: no accumulator double-buffering
-      const uint32_t acc_phase = p.bm2 ? (it & 1) : ((it >> 1) & 1);
+      const bool one_acc = p.bm2 || p.fs;                    // these tiles own all of TMEM: no accumulator double-buffering
+      const int acc = one_acc ? 0 : (it & 1);
+      const uint32_t acc_phase = one_acc ? (it & 1) : ((it >> 1) & 1);
       if (lane == 0) tc::mbar_wait(&sh->tmem_empty[acc], acc_phase ^ 1);
       __syncwarp();
       tc::tc_fence_after();
@@ -392,6 +401,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint64_t db = p.b_mn ? tc::make_smem_desc(sb + k * 2048, 8192, 1024)
                                        : tc::make_smem_desc(sb + k * 32, 16, 1024);
             tc::mma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (p.fs)                                             // the same A tile against the second segment
+              tc::mma_bf16(tmem_base + (uint32_t)p.segN[0], da,
+                           tc::make_smem_desc(sb + (p.segN[0] / 64) * 8192 + k * 2048, 8192, 1024), idesc1, (kb > kb0 || k > 0) ? 1u : 0u);
             if (p.bm2)                                            // rows 128..255 of the tile against the same B
               tc::mma_bf16(tmem_base + 256,
                            p.a_mn ? tc::make_smem_desc(sa + 16384 + k * 2048, 8192, 1024)
@@ -415,9 +427,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int it = 0;
     float ce_acc = 0.f;                        // MODE 2: this thread's cross-entropy sum
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
-      const int ni = tile % p.nt;
       const int mi = (tile / p.nt) % p.mt;
       const bool mseg = p.nseg > 1;
+      const bool one_acc = p.bm2 || p.fs;
+      const int acc = one_acc ? 0 : (it & 1);
+      const uint32_t acc_phase = one_acc ? (it & 1) : ((it >> 1) & 1);
+      tc::mbar_wait(&sh->tmem_full[acc], acc_phase);
+      tc::tc_fence_after();
+      for (int fsi = 0; fsi < (p.fs ? 2 : 1); fsi++) {         // fs: the two segments' accumulators sit side by side
+      const int ni = p.fs ? fsi : tile % p.nt;
+      const uint32_t fs_col = p.fs ? (uint32_t)(fsi * p.segN[0]) : 0u;
       const int nchunks = (mseg ? p.segN[ni] : p.BN) >> 4;
       const int ch_lo = half == 0 ? 0 : (nchunks + 1) >> 1;
       const int ch_hi = half == 0 ? (nchunks + 1) >> 1 : nchunks;
@@ -425,16 +444,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       float* const Ct = mseg ? p.segC[ni] : (p.split_stride > 0 ? p.C + (long)(tile / (p.mt * p.nt)) * p.split_stride : p.C);
       const int ldct = mseg ? p.seg_ldc[ni] : p.ldc;
       const int Nt = mseg ? p.segN[ni] : p.N;
-      const int acc = p.bm2 ? 0 : (it & 1);
-      const uint32_t acc_phase = p.bm2 ? (it & 1) : ((it >> 1) & 1);
-      tc::mbar_wait(&sh->tmem_full[acc], acc_phase);
-      tc::tc_fence_after();
       for (int sub = 0; sub < (p.bm2 ? 2 : 1); sub++) {      // row halves of a 256-row tile (plain epilogue only)
       const int m0 = mi * BMt + sub * TC_BM;
       const int row_local = m0 + q * 32 + lane;
       const bool row_ok = row_local < p.M;
       const long grow = row_ok ? p.rm(row_local) : 0;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.bm2 ? sub * 256 : acc * p.BN);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.bm2 ? sub * 256 : acc * p.BN) + fs_col;
       const bool atomic = p.splitk > 1 && p.split_stride == 0;
       const bool add_bias = p.bias != nullptr && (tile / (p.mt * p.nt)) == 0;
       const int TC_SCR_PITCH = p.scr_pitch;
@@ -706,6 +721,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       }
       }   // sub
+      }   // fsi
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&sh->tmem_empty[acc]);
@@ -823,7 +839,13 @@ int gemm_tc(const TcGemm& g, cudaStream_t st) {
   // long-K weight-gradient shapes (both operands MN-major, fp32 atomics): 256-row tiles
   p.bm2 = (g.a_mn && g.b_mn && g.epi == TC_EPI_PLAIN && g.Cb == nullptr && g.accumulate && (g.M % 256) == 0 &&
            g.K >= 64 * 64 && std::getenv("ARCVAE_NO_BM256") == nullptr) ? 1 : 0;
-  p.mt = cdiv(g.M, p.bm2 ? 2 * TC_BM : TC_BM); p.nt = g.nseg > 1 ? g.nseg : cdiv(g.N, p.BN);
+  // Two-segment weight gradients (dA^T [h | onehot]): as separate column tiles the 128-column one-hot segment runs ~35 %
+  // faster than its 256-column sibling, drifts out of the sibling's L2 window and the shared A operand comes from HBM
+  // 1.5x (ncu r02e: 2.27 GB for 1.47 GB algorithmic).  One CTA per 128-row tile computes BOTH segments from one A tile:
+  // every CTA does the same work, A is read exactly once, 384 TMEM columns.
+  p.fs = (g.nseg == 2 && g.a_mn && g.b_mn && g.seg[0].N + g.seg[1].N <= 512 && std::getenv("ARCVAE_NO_FUSED_SEGMENTS") == nullptr) ? 1 : 0;
+  if (p.fs) { p.bm2 = 0; p.BN = g.seg[0].N + g.seg[1].N; }
+  p.mt = cdiv(g.M, p.bm2 ? 2 * TC_BM : TC_BM); p.nt = p.fs ? 1 : (g.nseg > 1 ? g.nseg : cdiv(g.N, p.BN));
   const int kblocks = cdiv(g.K, TC_BK);
   int splitk = g.splitk;
   if (splitk <= 0) {                        // auto: (tiles x splits) fills two waves of the 148 SMs
@@ -833,6 +855,8 @@ int gemm_tc(const TcGemm& g, cudaStream_t st) {
     splitk = sk < 1 ? 1 : (int)sk;
   } else if (p.bm2 && g.a_mn && splitk > 1) {
     splitk *= 2;                            // the caller sized the split for 128-row tiles
+  } else if (p.fs && splitk > 1) {
+    splitk *= 2;                            // the caller counted one tile per segment
   }
   if (splitk > kblocks) splitk = kblocks;
   p.kb_per = cdiv(kblocks, splitk);
