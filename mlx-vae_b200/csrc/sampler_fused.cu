@@ -23,6 +23,13 @@ namespace arcvae {
 
 using bf16 = __nv_bfloat16;
 
+#ifdef ARCVAE_RC_STAMPS
+extern long long* g_rc_dbg;     // lstm_cluster.cu; profiles/scripts/sampler_stamps.py
+#define SF_STAMP(slot) do { if (p.dbg != nullptr && blockIdx.x == 0 && t == 10) { unsigned long long _gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_gt)); p.dbg[(slot)] = (long long)_gt; } } while (0)
+#else
+#define SF_STAMP(slot) do { } while (0)
+#endif
+
 constexpr int SF_ROWS = 128;
 constexpr int SF_BN = 192;
 constexpr int SF_STAGES = 4;
@@ -45,6 +52,7 @@ struct SfParams {
   const float* cond;                 // [B, C]
   int32_t* tokens;                   // [B, max_length]
   int32_t* ended_count;              // [0] rows that emitted end_token, [1] max over rows of (end position + 1)
+  long long* dbg;                    // stamps (STAMPS build only)
 };
 
 struct __align__(8) SfShared {
@@ -162,6 +170,7 @@ sampler_fused_kernel(const __grid_constant__ SfMaps maps, const SfParams p) {
               const uint32_t acc = acc_it & 1;
               tc::mbar_wait(&sh->acc_empty[acc], ((acc_it >> 1) & 1) ^ 1);
               tc::tc_fence_after();
+              SF_STAMP((l * 4 + j) * 4 + 0);
               const uint32_t d_tmem = tmem_base + acc * SF_BN;
               for (int kp = 0; kp < kpn; kp++) {
                 if (l > 0 && j == 0) {
@@ -182,6 +191,7 @@ sampler_fused_kernel(const __grid_constant__ SfMaps maps, const SfParams p) {
                 if (++stage == SF_STAGES) { stage = 0; phase ^= 1; }
               }
               tc::mma_commit(&sh->acc_full[acc]);
+              SF_STAMP((l * 4 + j) * 4 + 1);
               acc_it++;
               if (l > 0 && j == 0) cons++;
             }
@@ -320,6 +330,7 @@ sampler_fused_kernel(const __grid_constant__ SfMaps maps, const SfParams p) {
             const uint32_t acc = acc_it & 1;
             tc::mbar_wait(&sh->acc_full[acc], (acc_it >> 1) & 1);
             tc::tc_fence_after();
+            if (threadIdx.x == 64) SF_STAMP((l * 4 + j) * 4 + 2);
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * SF_BN;
             uint8_t* drow = dst + (size_t)j * SF_PANEL + row * 128;
             const int nb = j * SF_BN + hs * 32;
@@ -333,12 +344,14 @@ sampler_fused_kernel(const __grid_constant__ SfMaps maps, const SfParams p) {
               tc::mbar_arrive(&sh->acc_empty[acc]);
               tc::mbar_arrive(&sh->p_ready[j]);
             }
+            if (threadIdx.x == 64) SF_STAMP((l * 4 + j) * 4 + 3);
             acc_it++;
           }
         }
         // ---- selection (decoder_sampling.py:110-123): thread per row, hs == 0 warps
         tc::mbar_wait(&sh->out_full, out_it & 1);
         tc::tc_fence_after();
+        if (threadIdx.x == 64) SF_STAMP(60);
         int choice = 0;
         if (hs == 0) {
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + SF_OUT_COL;
@@ -418,6 +431,7 @@ sampler_fused_kernel(const __grid_constant__ SfMaps maps, const SfParams p) {
           tc::fence_proxy_async();
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(&sh->a_ready);
+          if (threadIdx.x == 64) SF_STAMP(61);
         }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");   // nobody re-initialises hB for the next tile while a peer still selects
@@ -492,6 +506,11 @@ int sampler_fused_run(const arcvae_dims& d, const float* table, const float* wc,
     p.B = B; p.H = H; p.V = d.V; p.VN = ((d.V + 15) / 16) * 16; p.C = d.C; p.NL = d.NL; p.max_length = max_length;
     p.end_token = d.end_token; p.multinomial = multinomial; p.temperature = temperature; p.seed = seed;
     p.bout = bout; p.cond = cond; p.tokens = tokens; p.ended_count = ended_count;
+#ifdef ARCVAE_RC_STAMPS
+    p.dbg = g_rc_dbg;
+#else
+    p.dbg = nullptr;
+#endif
     ARCVAE_TRY(make_tmap_bf16(&maps.w[0], Tt, H3, 128, 128, 64, SF_BN));
     for (int l = 1; l < SF_MAX_LAYERS; l++) {
       p.bpb[l] = l < d.NL ? biasb + (size_t)l * H3 : nullptr;
